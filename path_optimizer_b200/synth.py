@@ -1,0 +1,147 @@
+"""Synthetic corridor batches for the BASELINE.json configs.
+
+Counter-based RNG (splitmix64 of a key built from seed/config/path/field/point) so that any shard
+of any batch can be regenerated independently on any rank.  Pure numpy; no CUDA, no oracle.
+
+A batch is a dict:
+  n_points  int32 [B]            stations per path
+  offsets   int32 [B+1]          exclusive prefix sum
+  ref       STATE_DTYPE [sum N]  reference states (x, y, z=heading, k, s)
+  bounds    BOUNDS_DTYPE [sum N] clearance bounds of the four covering circles
+  x0        float64 [B,3]        (init offset, init heading error, start curvature)
+  end_heading float64 [B]        goal heading (VehicleState end state z)
+"""
+import numpy as np
+
+from .abi import BOUNDS_DTYPE, STATE_DTYPE
+
+BASE_SEED = 20260923
+_M64 = np.uint64(0xFFFFFFFFFFFFFFFF)
+
+
+def splitmix64(x):
+    """splitmix64 finaliser on a uint64 array (wrap-around arithmetic)."""
+    x = np.asarray(x, dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        z = x + np.uint64(0x9E3779B97F4A7C15)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    return z
+
+
+def uniform(seed, config, path_id, field, point=0):
+    """U[0,1) doubles; arguments broadcast like numpy arrays."""
+    key = (np.uint64(seed)
+           ^ (np.asarray(config, dtype=np.uint64) << np.uint64(56))
+           ^ (np.asarray(path_id, dtype=np.uint64) << np.uint64(24))
+           ^ (np.asarray(field, dtype=np.uint64) << np.uint64(16))
+           ^ np.asarray(point, dtype=np.uint64))
+    return (splitmix64(key) >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0)
+
+
+def _accumulate_s(n, ds=0.3):
+    """s_i accumulated in double by += ds, as a resampler would produce them (this is what makes
+    keep_control_steps_ = int(1.2/0.3000..4) = 3)."""
+    s = np.empty(n, dtype=np.float64)
+    acc = 0.0
+    for i in range(n):
+        s[i] = acc
+        acc += ds
+    return s
+
+
+def _pack(n_points, ref, bounds, x0, end_heading):
+    n_points = np.ascontiguousarray(n_points, dtype=np.int32)
+    offsets = np.zeros(len(n_points) + 1, dtype=np.int32)
+    np.cumsum(n_points, out=offsets[1:])
+    return dict(n_points=n_points, offsets=offsets, ref=np.ascontiguousarray(ref),
+                bounds=np.ascontiguousarray(bounds), x0=np.ascontiguousarray(x0, dtype=np.float64),
+                end_heading=np.ascontiguousarray(end_heading, dtype=np.float64))
+
+
+def straight_corridors(batch, n=100, seed=BASE_SEED, first_path=0, config=2, wide_fraction=0.0):
+    """BASELINE config 2 / 4: straight reference, constant symmetric corridor per path.
+
+    ref[i] = (s_i, 0, 0, 0, s_i); half clearance w ~ U(0.5, 1.2) quantised down to 0.1 m (the
+    reference's ray-march resolution, reference_path_impl.cpp:288,444); all four circles
+    (lb, ub) = (-w, +w); x0 = (U(-0.3,0.3), U(-0.05,0.05), 0); goal heading 0.
+    `wide_fraction` > 0 marks that share of paths as wide (w ~ U(1.5, 3)): ill-conditioned regime.
+    """
+    pid = np.arange(first_path, first_path + batch, dtype=np.uint64)
+    s = _accumulate_s(n)
+    ref = np.zeros((batch, n), dtype=STATE_DTYPE)
+    ref["x"] = s[None, :]
+    ref["s"] = s[None, :]
+    w = 0.5 + 0.7 * uniform(seed, config, pid, 1)
+    if wide_fraction > 0:
+        wide = uniform(seed, config, pid, 5) < wide_fraction
+        w = np.where(wide, 1.5 + 1.5 * uniform(seed, config, pid, 6), w)
+    w = np.floor(w * 10.0 + 1e-9) / 10.0
+    bounds = np.zeros((batch, n), dtype=BOUNDS_DTYPE)
+    for c in range(4):
+        bounds[f"c{c}_ub"] = w[:, None]
+        bounds[f"c{c}_lb"] = -w[:, None]
+    x0 = np.zeros((batch, 3))
+    x0[:, 0] = -0.3 + 0.6 * uniform(seed, config, pid, 2)
+    x0[:, 1] = -0.05 + 0.1 * uniform(seed, config, pid, 3)
+    end_heading = np.zeros(batch)
+    return _pack(np.full(batch, n), ref.reshape(-1), bounds.reshape(-1), x0, end_heading)
+
+
+def curvy_corridors(batch, n=100, seed=BASE_SEED, first_path=0, config=3, n_points=None):
+    """Analytic curved corridors (config 5 / "config 3-lite"): kappa_ref(s) = A sin(2 pi s / L),
+    A ~ U(0, 0.05), L ~ U(30, 80) m integrated to (x, y, heading); corridor centre follows a smooth
+    lateral wave c(s) of amplitude U(0, 0.6) m, half widths per circle U(0.6, 1.6) quantised to
+    0.1 m, so bounds differ per station and per circle (some above the 1.3 m soft margin).
+    `n_points` (int array [batch]) gives mixed lengths; otherwise every path has n stations."""
+    if n_points is None:
+        n_points = np.full(batch, n, dtype=np.int32)
+    n_points = np.asarray(n_points, dtype=np.int32)
+    total = int(n_points.sum())
+    ref = np.zeros(total, dtype=STATE_DTYPE)
+    bounds = np.zeros(total, dtype=BOUNDS_DTYPE)
+    x0 = np.zeros((batch, 3))
+    end_heading = np.zeros(batch)
+    off = 0
+    for b in range(batch):
+        nb = int(n_points[b])
+        pid = np.uint64(first_path + b)
+        s = _accumulate_s(nb)
+        A = 0.05 * uniform(seed, config, pid, 1)
+        L = 30.0 + 50.0 * uniform(seed, config, pid, 2)
+        k = A * np.sin(2 * np.pi * s / L)
+        theta = np.concatenate([[0.0], np.cumsum(0.5 * (k[1:] + k[:-1]) * np.diff(s))])
+        x = np.concatenate([[0.0], np.cumsum(np.cos(0.5 * (theta[1:] + theta[:-1])) * np.diff(s))])
+        y = np.concatenate([[0.0], np.cumsum(np.sin(0.5 * (theta[1:] + theta[:-1])) * np.diff(s))])
+        r = ref[off:off + nb]
+        r["x"], r["y"], r["z"], r["k"], r["s"] = x, y, theta, k, s
+        amp = 0.6 * uniform(seed, config, pid, 3)
+        lam = 20.0 + 40.0 * uniform(seed, config, pid, 4)
+        ph = 2 * np.pi * uniform(seed, config, pid, 5)
+        centre = amp * (np.sin(2 * np.pi * s / lam + ph) - np.sin(ph)) * np.minimum(s / 6.0, 1.0)
+        bb = bounds[off:off + nb]
+        for c in range(4):
+            hw = 0.6 + 1.0 * uniform(seed, config, pid, 8 + c, np.arange(nb, dtype=np.uint64) // np.uint64(10))
+            hw = np.floor(hw * 10.0 + 1e-9) / 10.0
+            bb[f"c{c}_ub"] = np.round(centre + hw, 1)
+            bb[f"c{c}_lb"] = np.round(centre - hw, 1)
+        x0[b, 0] = -0.2 + 0.4 * uniform(seed, config, pid, 6)
+        x0[b, 1] = -0.04 + 0.08 * uniform(seed, config, pid, 7)
+        x0[b, 2] = k[0]
+        end_heading[b] = theta[-1]
+        off += nb
+    return _pack(n_points, ref, bounds, x0, end_heading)
+
+
+def slice_batch(batch, begin, end):
+    """Paths [begin, end) of a batch as a new batch (views where possible)."""
+    o = batch["offsets"]
+    lo, hi = int(o[begin]), int(o[end])
+    out = dict(n_points=batch["n_points"][begin:end].copy(),
+               ref=batch["ref"][lo:hi], bounds=batch["bounds"][lo:hi],
+               x0=batch["x0"][begin:end], end_heading=batch["end_heading"][begin:end])
+    offsets = np.zeros(end - begin + 1, dtype=np.int32)
+    np.cumsum(out["n_points"], out=offsets[1:])
+    out["offsets"] = offsets
+    return out
