@@ -1,0 +1,309 @@
+#!/usr/bin/env python
+"""bench.py -- batched path-QP solves/s on B200 (BASELINE.json metric), one rank per GPU.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A "step" is one pass of the hot path (QP assembly -> ADMM solve -> state extraction) over one batch
+of synthetic corridor paths: BASELINE config 2 = 1024 paths x 100 stations per GPU (weak scaling:
+every rank solves its own 1024-path shard; at N > 1 each step ends with ONE NCCL all-gather of the
+solved Frenet states, BASELINE config 4).  Prints one JSON line on rank 0.
+
+  value        solves/s with the inputs already resident in HBM (pqp_solve_batch_device), timed with
+               CUDA events on the launching stream, L2 flushed between timed steps, max over ranks.
+  e2e          the same metric through the host-buffer C-ABI call (pqp_solve_batch): pinned host
+               inputs, H2D + kernel + D2H inside the timed region every step.
+  roofline     dominant kernel's algorithmic HBM bytes (52 N + 32 B per solve) / its
+               average launch time, against the measured HBM copy bandwidth.
+  cpu_baseline the CPU oracle (OSQP-algorithm restatement, oracle/) on the host cores, bounded sample.
+
+--impl reference times the CPU oracle (the reference's own OSQP-based path cannot be built here:
+no Eigen/OSQP/osqp-eigen in the image) on all host cores, same workload, same JSON contract.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from path_optimizer_b200 import synth  # noqa: E402
+from path_optimizer_b200.abi import BOUNDS_DTYPE, STATE_DTYPE, Stats  # noqa: E402
+
+PATHS_PER_GPU = 1024
+N_POINTS = 100
+METRIC = "path_qp_solves_per_sec"
+UNIT = "solves/s"
+
+
+def io_bytes_per_solve(n):
+    """SURVEY.md 8(d) contract figure B_io(N) = 52 N + 32 (fp32-packed compulsory I/O)."""
+    return 52 * n + 32
+
+
+def measured_peak_gbs():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.samples = []
+        self._stop = threading.Event()
+        self._t = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                parts = [p.strip() for p in out.strip().split(",")]
+                if len(parts) >= 6:
+                    self.samples.append(parts)
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def start(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._t:
+            self._t.join(timeout=6)
+        sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(s[2 + k].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+def cpu_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_reference(args, rank, world):
+    """CPU arm: the oracle (port of the reference's algorithm) on all host cores."""
+    if rank != 0:
+        return
+    from oracle import oracle
+    params = oracle.default_params()
+    cores = cpu_threads()
+    batch = synth.straight_corridors(PATHS_PER_GPU, N_POINTS)
+    for _ in range(args.warmup):
+        oracle.solve_batch(params, 0, synth.slice_batch(batch, 0, min(PATHS_PER_GPU, 4 * cores)), threads=cores)
+    secs = 0.0
+    solved = 0
+    for _ in range(args.steps):
+        r = oracle.solve_batch(params, 0, batch, threads=cores)
+        secs += r["seconds"]
+        solved += int((r["status"] == 1).sum())
+    value = PATHS_PER_GPU * args.steps / secs
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"BASELINE config 2: {PATHS_PER_GPU} paths x {N_POINTS} stations, straight corridors, KP",
+                   "paths_per_step": PATHS_PER_GPU, "n_points": N_POINTS,
+                   "note": "CPU arm: fp64 C restatement of the reference's assembly + OSQP recurrence (oracle/); "
+                           "the reference's own binary needs Eigen/OSQP/osqp-eigen, absent from this image"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{args.steps} x {PATHS_PER_GPU} paths (whole batch per step)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "solved_fraction": solved / (PATHS_PER_GPU * args.steps), "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from path_optimizer_b200 import _lib
+    from path_optimizer_b200.solver import BatchPathSolver
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B, N = PATHS_PER_GPU, N_POINTS
+    batch = synth.straight_corridors(B, N, first_path=rank * B)  # this rank's shard of the global batch
+    total = B * N
+    solver = BatchPathSolver(device=local_rank, max_batch=B, max_total_points=total)
+    L = _lib.load()
+
+    def dev_bytes(arr):
+        t = torch.from_numpy(np.frombuffer(np.ascontiguousarray(arr).tobytes(), dtype=np.uint8).copy())
+        return t.to(dev)
+
+    d_n = dev_bytes(batch["n_points"]); d_off = dev_bytes(batch["offsets"])
+    d_ref = dev_bytes(batch["ref"]); d_bounds = dev_bytes(batch["bounds"])
+    d_x0 = dev_bytes(batch["x0"]); d_end = dev_bytes(batch["end_heading"])
+    d_out = torch.zeros(total * STATE_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+    d_frenet = torch.zeros(total * 3, dtype=torch.float64, device=dev)
+    d_status = torch.zeros(B, dtype=torch.int32, device=dev)
+    d_iters = torch.zeros(B, dtype=torch.int32, device=dev)
+    gathered = torch.zeros(world * total * 3, dtype=torch.float64, device=dev) if world > 1 else None
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    stream = torch.cuda.current_stream()
+
+    def device_step():
+        rc = L.pqp_solve_batch_device(solver._h, 0, B, total, d_n.data_ptr(), d_off.data_ptr(), d_ref.data_ptr(),
+                                      d_bounds.data_ptr(), d_x0.data_ptr(), d_end.data_ptr(), None, None,
+                                      d_out.data_ptr(), d_frenet.data_ptr(), d_status.data_ptr(),
+                                      d_iters.data_ptr(), C.c_void_p(stream.cuda_stream), None)
+        assert rc == 0, _lib.last_error()
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, d_frenet)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident arm ("value")
+    for _ in range(args.warmup):
+        device_step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    t_wall0 = time.perf_counter()
+    for k in range(args.steps):
+        flush.fill_(k & 0xFF)          # L2 flush between timed steps (outside the events)
+        ev[k][0].record(stream)
+        device_step()
+        ev[k][1].record(stream)
+    barrier()
+    wall = time.perf_counter() - t_wall0
+    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+    status = d_status.cpu().numpy()
+    iters = d_iters.cpu().numpy()
+
+    # ---- end-to-end arm ("e2e"): host buffers through pqp_solve_batch
+    pin = lambda a: torch.from_numpy(np.frombuffer(np.ascontiguousarray(a).tobytes(), dtype=np.uint8).copy()).pin_memory()  # noqa: E731
+    h_ref, h_bounds = pin(batch["ref"]), pin(batch["bounds"])
+    h_x0, h_end, h_n = pin(batch["x0"]), pin(batch["end_heading"]), pin(batch["n_points"])
+    h_out = torch.zeros(total * STATE_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
+    h_frenet = torch.zeros(total * 3, dtype=torch.float64).pin_memory()
+    h_status = torch.zeros(B, dtype=torch.int32).pin_memory()
+    h_iters = torch.zeros(B, dtype=torch.int32).pin_memory()
+    stats = Stats()
+
+    def e2e_step():
+        rc = L.pqp_solve_batch(solver._h, 0, B, h_n.data_ptr(), h_ref.data_ptr(), h_bounds.data_ptr(),
+                               h_x0.data_ptr(), h_end.data_ptr(), None, None, h_out.data_ptr(),
+                               h_frenet.data_ptr(), h_status.data_ptr(), h_iters.data_ptr(), C.byref(stats))
+        assert rc == 0, _lib.last_error()
+
+    for _ in range(args.warmup):
+        e2e_step()
+    barrier()
+    e2e_ms = 0.0
+    h2d = d2h = 0
+    kern_ms = 0.0
+    for _ in range(args.steps):
+        flush.fill_(1)
+        torch.cuda.synchronize()
+        e2e_step()  # synchronous; its own CUDA events bracket H2D + kernel + D2H on the handle's stream
+        e2e_ms += stats.h2d_ms + stats.kernel_ms + stats.d2h_ms
+        kern_ms += stats.kernel_ms
+        h2d, d2h = stats.h2d_bytes, stats.d2h_bytes
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+
+    # max over ranks
+    t = torch.tensor([dev_ms, e2e_ms, wall * 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms, wall_ms = [float(x) for x in t.cpu()]
+    solved = torch.tensor([int((status == 1).sum())], device=dev)
+    if world > 1:
+        dist.all_reduce(solved)
+    if rank == 0:
+        total_solves = world * B * args.steps
+        value = total_solves / (dev_ms * 1e-3)
+        e2e_value = total_solves / (e2e_ms * 1e-3)
+        peak, peak_src = measured_peak_gbs()
+        avg_launch_s = (kern_ms / args.steps) * 1e-3 if world == 1 else (dev_ms / args.steps) * 1e-3
+        achieved = B * io_bytes_per_solve(N) / avg_launch_s / 1e9
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+                traffic = json.load(f).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"BASELINE config 2: {B} paths x {N} stations per GPU, straight corridors, KP, "
+                                   f"OSQP defaults (eps 1e-3, adaptive rho every 25 it)",
+                       "paths_per_gpu": B, "n_points": N, "l2": "flushed between timed steps (256 MiB fill)",
+                       "multi_gpu": "independent shards + one NCCL all-gather of Frenet states per step" if world > 1 else "single GPU",
+                       "iters_per_solve_mean": float(iters.mean()), "iters_per_solve_max": int(iters.max())},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": args.steps,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "peak_source": peak_src,
+                         "kernel": "pqp_kp_solve_kernel", "algorithmic_bytes_per_launch": B * io_bytes_per_solve(N),
+                         "note": "state is SM-resident by design: compulsory HBM traffic is I/O only (SURVEY 8d); "
+                                 "the kernel is bound by FP64 issue / dependent-chain latency, see DESIGN.md"},
+            "clocks": clocks, "solved_fraction": int(solved.item()) / (world * B), "wall_ms_per_step": wall_ms / args.steps,
+        }
+        if world == 1:
+            # CPU baseline, bounded sample: the oracle on all host cores, then on one core
+            from oracle import oracle
+            cores = cpu_threads()
+            sample = synth.slice_batch(batch, 0, min(B, max(64, 16 * cores)))
+            r = oracle.solve_batch(oracle.default_params(), 0, sample, threads=cores)
+            one = synth.slice_batch(batch, 0, 32)
+            r1 = oracle.solve_batch(oracle.default_params(), 0, one, threads=1)
+            line["cpu_baseline"] = {"value": len(sample["n_points"]) / r["seconds"], "unit": UNIT, "cores": cores,
+                                    "kind": "port", "sample": f"first {len(sample['n_points'])} paths of the same batch, all cores",
+                                    "single_thread_value": 32 / r1["seconds"],
+                                    "reference_logged_ms_per_qp": "7.09-12.79 ms at N=188-244 (BASELINE.md)"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

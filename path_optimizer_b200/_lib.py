@@ -1,0 +1,47 @@
+"""ctypes binding of libpqp.so (include/pqp.h).  Fails loudly when the library is missing: the
+product has no CPU fallback."""
+import ctypes as C
+import os
+
+from .abi import Params, Stats
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpqp.so")
+
+# every symbol include/pqp.h declares
+SYMBOLS = ["pqp_params_default", "pqp_params_update_config", "pqp_keep_control_steps", "pqp_problem_size",
+           "pqp_create", "pqp_destroy", "pqp_set_params", "pqp_solve_batch", "pqp_solve_batch_device",
+           "pqp_last_error", "pqp_version", "pqp_max_points"]
+
+_lib = None
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `python -m path_optimizer_b200.build` "
+            "(nvcc, sm_100a).  There is no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    vp = C.c_void_p
+    L.pqp_params_default.argtypes = [C.POINTER(Params)]
+    L.pqp_params_update_config.argtypes = [C.POINTER(Params)]
+    L.pqp_keep_control_steps.argtypes = [C.c_int, vp, C.c_int]
+    L.pqp_problem_size.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.pqp_create.argtypes = [C.POINTER(vp), C.POINTER(Params), C.c_int, C.c_int, C.c_int]
+    L.pqp_destroy.argtypes = [vp]
+    L.pqp_destroy.restype = None
+    L.pqp_set_params.argtypes = [vp, C.POINTER(Params)]
+    L.pqp_solve_batch.argtypes = [vp, C.c_int, C.c_int] + [vp] * 11 + [C.POINTER(Stats)]
+    L.pqp_solve_batch_device.argtypes = [vp, C.c_int, C.c_int, C.c_int] + [vp] * 13 + [C.POINTER(Stats)]
+    L.pqp_last_error.restype = C.c_char_p
+    L.pqp_version.restype = C.c_char_p
+    L.pqp_max_points.argtypes = [vp, C.c_int]
+    _lib = L
+    return L
+
+
+def last_error():
+    return load().pqp_last_error().decode()

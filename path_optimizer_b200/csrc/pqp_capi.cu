@@ -1,0 +1,365 @@
+// pqp_capi.cu -- extern "C" boundary of libpqp.so (declared in include/pqp.h) and the kernel
+// launchers.  Host orchestration only: all numerics run in the sm_100a kernels; there is no CPU
+// fallback (pqp_create fails when no CUDA device / kernel image is usable).
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+#include <vector>
+
+#include "pqp_kp_core.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+void set_err(const char *fmt, const char *a = "", const char *b = "") {
+    snprintf(g_err, sizeof(g_err), fmt, a, b);
+}
+
+#define PQP_CUDA(call)                                                       \
+    do {                                                                     \
+        cudaError_t e_ = (call);                                             \
+        if (e_ != cudaSuccess) {                                             \
+            set_err("%s failed: %s", #call, cudaGetErrorString(e_));         \
+            return PQP_ERR_CUDA;                                             \
+        }                                                                    \
+    } while (0)
+
+// One warp (= one CTA) per path.  Shared memory holds the whole ADMM state and the KKT factor.
+__global__ void __launch_bounds__(32)
+pqp_kp_solve_kernel(const __grid_constant__ pqp::DevParams prm, const __grid_constant__ pqp::BatchView bv,
+                    const int32_t *__restrict__ order, int smem_doubles) {
+    extern __shared__ double pqp_smem[];
+    int prob = blockIdx.x;
+    if (order) prob = order[prob];
+    pqp::Warp w;
+    pqp::kp_solve_path(w, prm, bv, prob, pqp_smem, (size_t)smem_doubles);
+}
+
+}  // namespace
+
+struct pqp_handle {
+    int device = 0;
+    int max_batch = 0, max_total = 0;
+    int smem_optin = 0;
+    int num_sms = 0;
+    pqp_params params;
+    pqp::DevParams dprm;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    // device buffers for the host-pointer entry point
+    int32_t *d_n = nullptr, *d_off = nullptr, *d_order = nullptr, *d_status = nullptr, *d_iters = nullptr;
+    pqp_state *d_ref = nullptr, *d_out = nullptr;
+    pqp_station_bounds *d_bounds = nullptr;
+    double *d_x0 = nullptr, *d_end = nullptr, *d_frenet = nullptr;
+    // pinned host scratch for the small per-batch arrays
+    int32_t *h_off = nullptr, *h_order = nullptr;
+};
+
+extern "C" {
+
+const char *pqp_last_error(void) { return g_err; }
+
+const char *pqp_version(void) { return "pqp abi 1 / sm_100a / fp64 warp-per-path ADMM"; }
+
+int pqp_params_update_config(pqp_params *p) {
+    if (!p) return PQP_ERR_ARG;
+    // updateConfig(), planning_flags.cpp:8-14
+    p->circle_radius = sqrt(pow(p->car_length / 8, 2) + pow(p->car_width / 2, 2)) + p->safety_margin;
+    p->d1 = -3.0 / 8.0 * p->car_length + p->rear_axle_to_center;
+    p->d2 = -1.0 / 8.0 * p->car_length + p->rear_axle_to_center;
+    p->d3 = 1.0 / 8.0 * p->car_length + p->rear_axle_to_center;
+    p->d4 = 3.0 / 8.0 * p->car_length + p->rear_axle_to_center;
+    return PQP_OK;
+}
+
+int pqp_params_default(pqp_params *p) {
+    if (!p) return PQP_ERR_ARG;
+    memset(p, 0, sizeof(*p));
+    // planning_flags.cpp:18-43
+    p->car_width = 2.0;
+    p->car_length = 4.9;
+    p->safety_margin = 0.0;
+    p->wheel_base = 2.85;
+    p->rear_axle_to_center = 1.45;
+    p->max_steering_angle = 30.0 * M_PI / 180.0;
+    p->mu = 0.4;
+    p->max_curvature_rate = 0.1;
+    // planning_flags.cpp:102-119
+    p->K_curvature_weight = 50;
+    p->K_curvature_rate_weight = 200;
+    p->K_deviation_weight = 0;
+    p->KP_curvature_weight = 10;
+    p->KP_curvature_rate_weight = 200;
+    p->KP_deviation_weight = 0;
+    p->KP_slack_weight = 3;
+    p->expected_safety_margin = 1.3;
+    p->constraint_end_heading = 1;
+    // OSQP 0.6.x defaults (the reference only touches verbosity / warm start, solver.cpp:48-49)
+    p->rho = 0.1;
+    p->sigma = 1e-6;
+    p->alpha = 1.6;
+    p->eps_abs = 1e-3;
+    p->eps_rel = 1e-3;
+    p->eps_prim_inf = 1e-4;
+    p->eps_dual_inf = 1e-4;
+    p->max_iter = 4000;
+    p->scaling = 10;
+    p->check_termination = 25;
+    p->adaptive_rho = 1;
+    p->adaptive_rho_interval = 25;
+    p->adaptive_rho_tolerance = 5;
+    return pqp_params_update_config(p);
+}
+
+int pqp_keep_control_steps(int formulation, const pqp_state *ref, int n_points) {
+    if (formulation == PQP_FORM_K) return 1;
+    if (formulation == PQP_FORM_KPC) return 4;  // solver_kp_as_input_constrained.cpp:17
+    if (!ref || n_points < 2) return 1;
+    double interval = 0;                        // solver.cpp:21-27
+    for (int i = 1; i < n_points && i < 10; ++i) interval = std::max(interval, ref[i].s - ref[i - 1].s);
+    const double q = 1.2 / interval;            // solver_kp_as_input.cpp:17
+    int keep = (q == q && q < 2147483647.0) ? (int)q : (q == q ? 2147483647 : 0);
+    return std::max(keep, 1);
+}
+
+int pqp_problem_size(int formulation, int n, int keep, int *n_var, int *n_con) {
+    if (n < 2 || keep < 1 || !n_var || !n_con) return PQP_ERR_ARG;
+    const int ch = (n + keep - 2) / keep;
+    switch (formulation) {
+    case PQP_FORM_KP: *n_var = 5 * n + ch; *n_con = 11 * n + ch + 2; return PQP_OK;       // :18-23
+    case PQP_FORM_K: *n_var = 4 * n - 1; *n_con = 11 * n - 1; return PQP_OK;              // :18-19
+    case PQP_FORM_KPC: *n_var = 6 * n + ch; *n_con = 12 * n + 3 * ch + 2; return PQP_OK;  // :18-24
+    default: return PQP_ERR_ARG;
+    }
+}
+
+void pqp_destroy(pqp_handle *h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaFree(h->d_n); cudaFree(h->d_off); cudaFree(h->d_order); cudaFree(h->d_status); cudaFree(h->d_iters);
+    cudaFree(h->d_ref); cudaFree(h->d_out); cudaFree(h->d_bounds);
+    cudaFree(h->d_x0); cudaFree(h->d_end); cudaFree(h->d_frenet);
+    cudaFreeHost(h->h_off); cudaFreeHost(h->h_order);
+    for (auto &e : h->ev) if (e) cudaEventDestroy(e);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+int pqp_set_params(pqp_handle *h, const pqp_params *params) {
+    if (!h || !params) return PQP_ERR_ARG;
+    h->params = *params;
+    h->dprm = pqp::dev_params_from(*params);
+    return PQP_OK;
+}
+
+int pqp_create(pqp_handle **out, const pqp_params *params, int device, int max_batch, int max_total_points) {
+    if (!out || !params || max_batch < 1 || max_total_points < 2) {
+        set_err("pqp_create: bad argument");
+        return PQP_ERR_ARG;
+    }
+    *out = nullptr;
+    int ndev = 0;
+    PQP_CUDA(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) {
+        set_err("pqp_create: no such CUDA device");
+        return PQP_ERR_CUDA;
+    }
+    PQP_CUDA(cudaSetDevice(device));
+    pqp_handle *h = new (std::nothrow) pqp_handle;
+    if (!h) return PQP_ERR_ARG;
+    h->device = device;
+    h->max_batch = max_batch;
+    h->max_total = max_total_points;
+    pqp_set_params(h, params);
+    int rc = PQP_OK;
+    auto fail = [&](int code) { pqp_destroy(h); return code; };
+#define PQP_TRY(call)                                                      \
+    do {                                                                   \
+        cudaError_t e_ = (call);                                           \
+        if (e_ != cudaSuccess) {                                           \
+            set_err("%s failed: %s", #call, cudaGetErrorString(e_));       \
+            return fail(PQP_ERR_CUDA);                                     \
+        }                                                                  \
+    } while (0)
+    PQP_TRY(cudaDeviceGetAttribute(&h->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    PQP_TRY(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device));
+    // fails with cudaErrorNoKernelImageForDevice / InvalidDeviceFunction on anything but sm_100
+    PQP_TRY(cudaFuncSetAttribute(pqp_kp_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin));
+    PQP_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    for (auto &e : h->ev) PQP_TRY(cudaEventCreate(&e));
+    const size_t B = (size_t)max_batch, T = (size_t)max_total_points;
+    PQP_TRY(cudaMalloc(&h->d_n, B * sizeof(int32_t)));
+    PQP_TRY(cudaMalloc(&h->d_off, (B + 1) * sizeof(int32_t)));
+    PQP_TRY(cudaMalloc(&h->d_order, B * sizeof(int32_t)));
+    PQP_TRY(cudaMalloc(&h->d_status, B * sizeof(int32_t)));
+    PQP_TRY(cudaMalloc(&h->d_iters, B * sizeof(int32_t)));
+    PQP_TRY(cudaMalloc(&h->d_ref, T * sizeof(pqp_state)));
+    PQP_TRY(cudaMalloc(&h->d_out, T * sizeof(pqp_state)));
+    PQP_TRY(cudaMalloc(&h->d_bounds, T * sizeof(pqp_station_bounds)));
+    PQP_TRY(cudaMalloc(&h->d_x0, B * 3 * sizeof(double)));
+    PQP_TRY(cudaMalloc(&h->d_end, B * sizeof(double)));
+    PQP_TRY(cudaMalloc(&h->d_frenet, T * 3 * sizeof(double)));
+    PQP_TRY(cudaMallocHost(&h->h_off, (B + 1) * sizeof(int32_t)));
+    PQP_TRY(cudaMallocHost(&h->h_order, B * sizeof(int32_t)));
+#undef PQP_TRY
+    (void)rc;
+    *out = h;
+    return PQP_OK;
+}
+
+int pqp_max_points(pqp_handle *h, int formulation) {
+    if (!h || formulation != PQP_FORM_KP) return 0;
+    int best = 0;
+    for (int n = 2; n <= 4096; ++n) {
+        // keep = 4 (ds = 0.3 m stations give 3, the reference's dense 0.25 m spacing gives 4)
+        if (pqp::kp_smem_doubles(pqp::kp_dims(n, 4)) * sizeof(double) <= (size_t)h->smem_optin) best = n;
+        else break;
+    }
+    return best;
+}
+
+static int launch_kp(pqp_handle *h, const pqp::BatchView &bv, const int32_t *d_order, size_t smem_bytes,
+                     cudaStream_t st) {
+    if (smem_bytes > (size_t)h->smem_optin) {
+        set_err("path too long for one SM's shared memory");
+        return PQP_ERR_UNSUPPORTED;
+    }
+    pqp_kp_solve_kernel<<<bv.batch, 32, smem_bytes, st>>>(h->dprm, bv, d_order, (int)(smem_bytes / sizeof(double)));
+    PQP_CUDA(cudaGetLastError());
+    return PQP_OK;
+}
+
+int pqp_solve_batch_device(pqp_handle *h, int formulation, int batch, int total_points,
+                           const int32_t *d_n_points, const int32_t *d_offsets, const pqp_state *d_ref,
+                           const pqp_station_bounds *d_bounds, const double *d_x0, const double *d_end_heading,
+                           const double *d_max_k, const double *d_max_kp, pqp_state *d_out_states,
+                           double *d_out_frenet, int32_t *d_status, int32_t *d_iters, void *stream,
+                           pqp_stats *stats) {
+    (void)d_max_k; (void)d_max_kp; (void)total_points;
+    if (!h || batch < 0 || !d_n_points || !d_offsets || !d_ref || !d_bounds || !d_x0 || !d_end_heading ||
+        !d_out_states || !d_status) {
+        set_err("pqp_solve_batch_device: bad argument");
+        return PQP_ERR_ARG;
+    }
+    if (formulation != PQP_FORM_KP) {
+        set_err("formulation not implemented on the device yet (KP only)");
+        return PQP_ERR_UNSUPPORTED;
+    }
+    if (batch == 0) return PQP_OK;
+    PQP_CUDA(cudaSetDevice(h->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    pqp::BatchView bv;
+    bv.batch = batch; bv.n_points = d_n_points; bv.offsets = d_offsets; bv.ref = d_ref; bv.bounds = d_bounds;
+    bv.x0 = d_x0; bv.end_heading = d_end_heading; bv.out_states = d_out_states; bv.out_frenet = d_out_frenet;
+    bv.status = d_status; bv.iters = d_iters;
+    // The host does not see n_points here: size shared memory for the largest path the handle was
+    // created for (max_total_points bounds any single path) capped at the device limit; a path that
+    // does not fit reports PQP_INVALID_PROBLEM in its status.
+    int nmax = std::min(h->max_total, pqp_max_points(h, formulation));
+    size_t smem = pqp::kp_smem_doubles(pqp::kp_dims(nmax, 4)) * sizeof(double);
+    smem = std::min(smem, (size_t)h->smem_optin);
+    if (stats) PQP_CUDA(cudaEventRecord(h->ev[0], st));
+    int rc = launch_kp(h, bv, nullptr, smem, st);
+    if (rc != PQP_OK) return rc;
+    if (stats) {
+        memset(stats, 0, sizeof(*stats));
+        PQP_CUDA(cudaEventRecord(h->ev[1], st));
+        PQP_CUDA(cudaEventSynchronize(h->ev[1]));
+        PQP_CUDA(cudaEventElapsedTime(&stats->kernel_ms, h->ev[0], h->ev[1]));
+        stats->kernel_launches = 1;
+    }
+    return PQP_OK;
+}
+
+int pqp_solve_batch(pqp_handle *h, int formulation, int batch, const int32_t *n_points, const pqp_state *ref,
+                    const pqp_station_bounds *bounds, const double *x0, const double *end_heading,
+                    const double *max_k, const double *max_kp, pqp_state *out_states, double *out_frenet,
+                    int32_t *status, int32_t *iters, pqp_stats *stats) {
+    (void)max_k; (void)max_kp;
+    if (!h || batch < 0 || (batch > 0 && (!n_points || !ref || !bounds || !x0 || !end_heading || !out_states || !status))) {
+        set_err("pqp_solve_batch: bad argument");
+        return PQP_ERR_ARG;
+    }
+    if (formulation != PQP_FORM_KP) {
+        set_err("formulation not implemented on the device yet (KP only)");
+        return PQP_ERR_UNSUPPORTED;
+    }
+    if (stats) memset(stats, 0, sizeof(*stats));
+    if (batch == 0) return PQP_OK;
+    if (batch > h->max_batch) {
+        set_err("batch exceeds the handle's max_batch");
+        return PQP_ERR_CAPACITY;
+    }
+    // offsets, per-path shared memory need, longest-first order
+    long long total = 0;
+    size_t smem = 0;
+    h->h_off[0] = 0;
+    for (int b = 0; b < batch; ++b) {
+        const int n = n_points[b];
+        if (n < 0) { set_err("negative n_points"); return PQP_ERR_ARG; }
+        total += n;
+        if (total > h->max_total) { set_err("station count exceeds the handle's max_total_points"); return PQP_ERR_CAPACITY; }
+        h->h_off[b + 1] = (int32_t)total;
+        if (n >= 2) {
+            const int keep = pqp_keep_control_steps(formulation, ref + h->h_off[b], n);
+            if (keep <= 10) smem = std::max(smem, pqp::kp_smem_doubles(pqp::kp_dims(n, keep)) * sizeof(double));
+        }
+        h->h_order[b] = b;
+    }
+    if (smem == 0) smem = pqp::kp_smem_doubles(pqp::kp_dims(2, 1)) * sizeof(double);
+    if (smem > (size_t)h->smem_optin) {
+        set_err("a path is too long for one SM's shared memory");
+        return PQP_ERR_UNSUPPORTED;
+    }
+    std::stable_sort(h->h_order, h->h_order + batch, [&](int a, int b) { return n_points[a] > n_points[b]; });
+    PQP_CUDA(cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    const size_t T = (size_t)total, B = (size_t)batch;
+    PQP_CUDA(cudaEventRecord(h->ev[0], st));
+    PQP_CUDA(cudaMemcpyAsync(h->d_n, n_points, B * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    PQP_CUDA(cudaMemcpyAsync(h->d_off, h->h_off, (B + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    PQP_CUDA(cudaMemcpyAsync(h->d_order, h->h_order, B * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    PQP_CUDA(cudaMemcpyAsync(h->d_ref, ref, T * sizeof(pqp_state), cudaMemcpyHostToDevice, st));
+    PQP_CUDA(cudaMemcpyAsync(h->d_bounds, bounds, T * sizeof(pqp_station_bounds), cudaMemcpyHostToDevice, st));
+    PQP_CUDA(cudaMemcpyAsync(h->d_x0, x0, B * 3 * sizeof(double), cudaMemcpyHostToDevice, st));
+    PQP_CUDA(cudaMemcpyAsync(h->d_end, end_heading, B * sizeof(double), cudaMemcpyHostToDevice, st));
+    PQP_CUDA(cudaEventRecord(h->ev[1], st));
+    pqp::BatchView bv;
+    bv.batch = batch; bv.n_points = h->d_n; bv.offsets = h->d_off; bv.ref = h->d_ref; bv.bounds = h->d_bounds;
+    bv.x0 = h->d_x0; bv.end_heading = h->d_end; bv.out_states = h->d_out;
+    bv.out_frenet = out_frenet ? h->d_frenet : nullptr;
+    bv.status = h->d_status; bv.iters = h->d_iters;
+    int rc = launch_kp(h, bv, h->d_order, smem, st);
+    if (rc != PQP_OK) return rc;
+    PQP_CUDA(cudaEventRecord(h->ev[2], st));
+    PQP_CUDA(cudaMemcpyAsync(out_states, h->d_out, T * sizeof(pqp_state), cudaMemcpyDeviceToHost, st));
+    if (out_frenet) PQP_CUDA(cudaMemcpyAsync(out_frenet, h->d_frenet, T * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    PQP_CUDA(cudaMemcpyAsync(status, h->d_status, B * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    std::vector<int32_t> iters_local;
+    int32_t *it_dst = iters;
+    if (!it_dst && stats) { iters_local.resize(B); it_dst = iters_local.data(); }
+    if (it_dst) PQP_CUDA(cudaMemcpyAsync(it_dst, h->d_iters, B * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    PQP_CUDA(cudaEventRecord(h->ev[3], st));
+    PQP_CUDA(cudaStreamSynchronize(st));
+    if (stats) {
+        PQP_CUDA(cudaEventElapsedTime(&stats->h2d_ms, h->ev[0], h->ev[1]));
+        PQP_CUDA(cudaEventElapsedTime(&stats->kernel_ms, h->ev[1], h->ev[2]));
+        PQP_CUDA(cudaEventElapsedTime(&stats->d2h_ms, h->ev[2], h->ev[3]));
+        stats->h2d_bytes = (int64_t)(B * sizeof(int32_t) * 3 + sizeof(int32_t) + T * (sizeof(pqp_state) + sizeof(pqp_station_bounds)) + B * 4 * sizeof(double));
+        stats->d2h_bytes = (int64_t)(T * sizeof(pqp_state) + (out_frenet ? T * 3 * sizeof(double) : 0) + B * sizeof(int32_t) * 2);
+        stats->kernel_launches = 1;
+        for (size_t b = 0; b < B; ++b) {
+            stats->total_iters += it_dst[b];
+            stats->max_iters = std::max(stats->max_iters, it_dst[b]);
+            stats->n_solved += (status[b] == PQP_SOLVED);
+        }
+    }
+    return PQP_OK;
+}
+
+}  // extern "C"

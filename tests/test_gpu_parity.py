@@ -1,0 +1,143 @@
+"""GPU parity tests (run with -m gpu on the B200 box): the CUDA path, called through the C ABI
+(libpqp.so), against the CPU oracle on the same seeded inputs, against the committed golden fixtures,
+and -- at BASELINE.json's full sizes -- through size-independent properties.
+
+Tolerances.  north_star asks for <= 1e-4 on lateral offset and heading states.  The kernels run the
+same recurrence as the oracle in fp64, so the tests hold them to a much tighter bar:
+  FRENET_TOL = 1e-8 on (e_y, e_phi, kappa) and on the Cartesian states, identical status and
+  identical ADMM iteration count per path."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle
+from path_optimizer_b200 import synth
+from path_optimizer_b200.abi import SOLVED
+
+pytestmark = pytest.mark.gpu
+
+FRENET_TOL = 1e-8
+NORTH_STAR_TOL = 1e-4
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "kp_*.npz")))
+
+
+@pytest.fixture(scope="module")
+def solver():
+    from path_optimizer_b200.solver import BatchPathSolver
+    s = BatchPathSolver(max_batch=8192, max_total_points=8192 * 200)
+    yield s
+    s.close()
+
+
+def _compare(res, ref, tol=FRENET_TOL):
+    assert np.array_equal(res["status"], ref["status"])
+    assert np.array_equal(res["iters"], ref["iters"])
+    np.testing.assert_allclose(res["frenet"], ref["frenet"], rtol=0, atol=tol)
+    for f in "xyzks":
+        np.testing.assert_allclose(res["states"][f], ref["states"][f], rtol=0, atol=tol)
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p) for p in GOLDEN])
+def test_golden_fixtures(solver, path):
+    g = np.load(path)
+    batch = dict(n_points=g["n_points"], ref=g["ref"], bounds=g["bounds"], x0=g["x0"], end_heading=g["end_heading"])
+    res = solver.solve(batch)
+    _compare(res, dict(status=g["status"], iters=g["iters"], frenet=g["frenet"], states=g["states"]))
+    # and the north-star bound against the independent twin
+    assert np.nanmax(np.abs(res["frenet"][:, :2] - g["twin_frenet"][:, :2])) <= NORTH_STAR_TOL
+
+
+def test_config2_sample_vs_oracle(solver, oracle_params):
+    """BASELINE config 2 (1024 x 100 straight corridors): a 64-path sample against the oracle."""
+    batch = synth.straight_corridors(64, 100)
+    _compare(solver.solve(batch), oracle.solve_batch(oracle_params, 0, batch, threads=8))
+
+
+def test_curvy_and_mixed_lengths_vs_oracle(solver, oracle_params):
+    rng = np.random.default_rng(7)
+    n_points = rng.integers(2, 260, size=48)
+    n_points[:4] = [2, 3, 4, 5]
+    batch = synth.curvy_corridors(48, n_points=n_points)
+    _compare(solver.solve(batch), oracle.solve_batch(oracle_params, 0, batch, threads=8))
+
+
+@pytest.mark.parametrize("ds", [0.15, 0.25, 0.5, 1.0])
+def test_other_keep_control_steps(solver, oracle_params, ds):
+    b = synth.curvy_corridors(4, 80)
+    for k in range(4):
+        sl = slice(k * 80, (k + 1) * 80)
+        b["ref"]["s"][sl] = np.arange(80) * ds
+    _compare(solver.solve(b), oracle.solve_batch(oracle_params, 0, b, threads=4))
+
+
+def test_edge_cases(solver, oracle_params):
+    b = synth.straight_corridors(6, 40)
+    b["bounds"]["c0_lb"][10] = 3.0                    # path 0: lb > ub -> invalid
+    b["end_heading"][1] = 2.5                         # path 1: end heading unconstrained (> 70 deg)
+    b["bounds"]["c3_ub"][2 * 40:3 * 40] = 4.0         # path 2: wide corridor (ill-conditioned regime)
+    b["bounds"]["c3_lb"][2 * 40:3 * 40] = -4.0
+    b["x0"][3] = [0.0, 0.0, 0.0]                      # path 3: already on the reference
+    b["bounds"]["c2_lb"][4 * 40 + 7] = b["bounds"]["c2_ub"][4 * 40 + 7] = 0.1  # path 4: collapsed corridor row
+    res = solver.solve(b)
+    ref = oracle.solve_batch(oracle_params, 0, b)
+    assert res["status"][0] == -100 and np.all(np.isnan(res["frenet"][:40]))
+    assert np.array_equal(res["status"], ref["status"])
+    assert np.array_equal(res["iters"], ref["iters"])
+    np.testing.assert_allclose(res["frenet"][40:], ref["frenet"][40:], rtol=0, atol=FRENET_TOL)
+    # empty batch is a no-op
+    empty = dict(n_points=np.zeros(0, np.int32), ref=b["ref"][:0], bounds=b["bounds"][:0],
+                 x0=np.zeros((0, 3)), end_heading=np.zeros(0))
+    assert len(solver.solve(empty)["status"]) == 0
+
+
+def test_max_iter_status(oracle_params):
+    from path_optimizer_b200.solver import BatchPathSolver
+    p = oracle_params.copy()
+    p.max_iter = 75
+    s = BatchPathSolver(params=p, max_batch=4, max_total_points=400)
+    b = synth.curvy_corridors(4, 60)
+    _compare(s.solve(b), oracle.solve_batch(p, 0, b))
+    s.close()
+
+
+def test_full_size_config2_properties(solver):
+    """1024 x 100 at full size: every path solves; the solution satisfies the QP's own constraints to
+    the solver tolerance; permuting the batch permutes the result bit for bit (paths are independent
+    and the kernel is deterministic); a second run is bit-identical."""
+    batch = synth.straight_corridors(1024, 100)
+    res = solver.solve(batch)
+    assert (res["status"] == SOLVED).all()
+    fr = res["frenet"].reshape(1024, 100, 3)
+    p = solver.params
+    w = batch["bounds"]["c0_ub"].reshape(1024, 100)
+    for d in (p.d1, p.d3):  # hard circles stay inside the corridor (to eps 1e-3 of OSQP + slack)
+        off = fr[:, :, 0] + d * fr[:, :, 1]
+        assert np.all(np.abs(off) <= w + 5e-3)
+    assert np.all(np.abs(fr[:, :, 2]) <= np.tan(p.max_steering_angle) / p.wheel_base + 5e-3)
+    np.testing.assert_allclose(fr[:, 0, 0], batch["x0"][:, 0], atol=5e-3)   # initial state row
+    np.testing.assert_allclose(fr[:, 0, 1], batch["x0"][:, 1], atol=5e-3)
+    again = solver.solve(batch)
+    assert np.array_equal(again["frenet"], res["frenet"]) and np.array_equal(again["iters"], res["iters"])
+    perm = np.random.default_rng(3).permutation(1024)
+    pb = dict(n_points=batch["n_points"][perm], ref=batch["ref"].reshape(1024, 100)[perm].reshape(-1),
+              bounds=batch["bounds"].reshape(1024, 100)[perm].reshape(-1), x0=batch["x0"][perm],
+              end_heading=batch["end_heading"][perm])
+    pres = solver.solve(pb)
+    assert np.array_equal(pres["frenet"].reshape(1024, 100, 3), fr[perm])
+    assert np.array_equal(pres["iters"], res["iters"][perm])
+
+
+def test_osqp_solver_adaptor(solver, oracle_params):
+    """Single-path adaptor with the reference's call shape (solver.hpp:31-36)."""
+    from path_optimizer_b200.solver import OsqpSolver
+    b = synth.curvy_corridors(1, 70)
+    s = OsqpSolver.create("KP", b["ref"], b["bounds"], (b["x0"][0, 0], b["x0"][0, 1]), b["x0"][0, 2],
+                          b["end_heading"][0], 70)
+    path = []
+    assert s.solve(path) is True
+    assert len(path) == 70
+    ref = oracle.solve_batch(oracle_params, 0, b)
+    np.testing.assert_allclose([q["x"] for q in path], ref["states"]["x"], rtol=0, atol=FRENET_TOL)
+    assert OsqpSolver.create("XYZ", b["ref"], b["bounds"], (0, 0), 0, 0, 70) is None
