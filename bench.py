@@ -163,10 +163,11 @@ def run_ours(args, rank, world, local_rank):
     d_iters = torch.zeros(B, dtype=torch.int32, device=dev)
     gathered = torch.zeros(world * total * 3, dtype=torch.float64, device=dev) if world > 1 else None
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream(device=dev)  # non-default: the ABI treats a NULL stream as 'the handle's own'
+    torch.cuda.set_stream(stream)
 
     def device_step():
-        rc = L.pqp_solve_batch_device(solver._h, 0, B, total, d_n.data_ptr(), d_off.data_ptr(), d_ref.data_ptr(),
+        rc = L.pqp_solve_batch_device(solver._h, 0, B, total, N, 4, d_n.data_ptr(), d_off.data_ptr(), d_ref.data_ptr(),
                                       d_bounds.data_ptr(), d_x0.data_ptr(), d_end.data_ptr(), None, None,
                                       d_out.data_ptr(), d_frenet.data_ptr(), d_status.data_ptr(),
                                       d_iters.data_ptr(), C.c_void_p(stream.cuda_stream), None)

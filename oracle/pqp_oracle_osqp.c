@@ -172,6 +172,7 @@ static void symbolic_free(symbolic *S) {
     free(S);
 }
 static int symbolic_matches(const symbolic *S, const oqp_problem *qp) {
+    if (!S) return 0;
     return S && S->n == qp->n && S->m == qp->m && S->p_nnz == qp->p_nnz && S->a_nnz == qp->a_nnz &&
            !memcmp(S->p_i, qp->p_i, sizeof(int) * (size_t)qp->p_nnz) &&
            !memcmp(S->p_j, qp->p_j, sizeof(int) * (size_t)qp->p_nnz) &&
@@ -361,8 +362,33 @@ static void ldl_solve(ldl *F, const double *b, double *sol) {
     for (int k = 0; k < nn; ++k) sol[S->perm[k]] = w[k];
 }
 
-/* per-thread cache: paths of one batch share (formulation, N, keep) and hence the pattern */
-static __thread symbolic *tls_sym = NULL;
+/* Symbolic cache.  Paths of one batch share (formulation, N, keep) and hence the sparsity pattern;
+ * the analysis (ordering + elimination tree) is immutable once built, so one copy is shared by all
+ * threads.  (OSQP redoes AMD + symbolic factorisation in every osqp_setup; sharing it only makes
+ * the CPU baseline faster, i.e. errs on the generous side.)  Entries are never freed. */
+#include <pthread.h>
+#define SYM_CACHE 16
+static symbolic *g_sym[SYM_CACHE];
+static int g_sym_n = 0;
+static pthread_mutex_t g_sym_mu = PTHREAD_MUTEX_INITIALIZER;
+static __thread const symbolic *tls_sym = NULL;
+
+static const symbolic *symbolic_get(const oqp_problem *qp) {
+    if (symbolic_matches(tls_sym, qp)) return tls_sym;
+    pthread_mutex_lock(&g_sym_mu);
+    const symbolic *found = NULL;
+    for (int k = 0; k < g_sym_n; ++k)
+        if (symbolic_matches(g_sym[k], qp)) { found = g_sym[k]; break; }
+    if (!found) {
+        symbolic *S = symbolic_build(qp);
+        if (g_sym_n < SYM_CACHE) g_sym[g_sym_n++] = S;
+        else { g_sym[g_sym_n - 1] = S; } /* cache full: replace the last slot (old entry leaks; bounded use) */
+        found = S;
+    }
+    pthread_mutex_unlock(&g_sym_mu);
+    tls_sym = found;
+    return found;
+}
 
 /* ---- the solver ----------------------------------------------------------------------------- */
 typedef struct {
@@ -634,13 +660,10 @@ int oracle_osqp_solve(const pqp_params *prm, const oqp_problem *qp, double *x_ou
     w->rho = prm->rho;
     set_rho_vec(w);
 
-    if (!symbolic_matches(tls_sym, qp)) {
-        symbolic_free(tls_sym);
-        tls_sym = symbolic_build(qp);
-    }
-    ldl *F = ldl_alloc(tls_sym);
-    info->kkt_n = tls_sym->nn;
-    info->kkt_lnz = tls_sym->lnz;
+    const symbolic *sym = symbolic_get(qp);
+    ldl *F = ldl_alloc(sym);
+    info->kkt_n = sym->nn;
+    info->kkt_lnz = sym->lnz;
     kkt_fill(w, qp, F, prm->sigma, p_map, a_map);
     int status = PQP_UNSOLVED;
     int iter = 0;

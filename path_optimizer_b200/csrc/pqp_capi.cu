@@ -10,10 +10,11 @@
 #include <new>
 #include <vector>
 
-#include "pqp_kp_core.cuh"
+#include "pqp_kp_core2.cuh"
 
 namespace {
 
+constexpr int kMaxBandGeneric = pqp::kMaxBand;
 thread_local char g_err[512] = "";
 
 void set_err(const char *fmt, const char *a = "", const char *b = "") {
@@ -40,6 +41,48 @@ pqp_kp_solve_kernel(const __grid_constant__ pqp::DevParams prm, const __grid_con
     pqp::kp_solve_path(w, prm, bv, prob, pqp_smem, (size_t)smem_doubles);
 }
 
+// Production kernels: one instantiation per (max interior size, half-bandwidth) shape class.
+template <int IMAX, int BW>
+__global__ void __launch_bounds__(32)
+pqp_kp2_solve_kernel(const __grid_constant__ pqp::DevParams prm, const __grid_constant__ pqp::BatchView bv,
+                     const int32_t *__restrict__ order, int smem_doubles) {
+    extern __shared__ double pqp_smem[];
+    int prob = blockIdx.x;
+    if (order) prob = order[prob];
+    pqp::Warp w;
+    pqp::Kp2<IMAX, BW>::solve_path(w, prm, bv, prob, pqp_smem, (size_t)smem_doubles);
+}
+
+// Shape classes.  keep_control_steps <= 4 (station spacing >= 0.24 m) maps onto one of the Kp2
+// instantiations; anything else runs on the generic kernel.
+struct Variant {
+    int imax, bw;
+    const void *fn;
+    size_t (*smem)(int n, int keep);
+    bool (*fits)(int n, int keep);
+};
+template <int IMAX, int BW> size_t v_smem(int n, int keep) {
+    return pqp::Kp2<IMAX, BW>::smem_doubles(pqp::Kp2<IMAX, BW>::dims(n, keep)) * sizeof(double);
+}
+template <int IMAX, int BW> bool v_fits(int n, int keep) {
+    return keep <= 10 && pqp::Kp2<IMAX, BW>::fits(pqp::kp2_dims(n, keep));
+}
+size_t g_smem(int n, int keep) { return pqp::kp_smem_doubles(pqp::kp_dims(n, keep)) * sizeof(double); }
+bool g_fits(int, int keep) { return keep <= 10; }
+#define PQP_VARIANT(I, B) {I, B, (const void *)pqp_kp2_solve_kernel<I, B>, v_smem<I, B>, v_fits<I, B>}
+const Variant kVariants[] = {
+    PQP_VARIANT(17, 6), PQP_VARIANT(10, 7), PQP_VARIANT(17, 7), PQP_VARIANT(27, 7), PQP_VARIANT(37, 7),
+    PQP_VARIANT(49, 7),
+    {0, kMaxBandGeneric, (const void *)pqp_kp_solve_kernel, g_smem, g_fits},  // generic fallback (last)
+};
+constexpr int kNumVariants = (int)(sizeof(kVariants) / sizeof(kVariants[0]));
+
+int pick_variant(int n, int keep) {
+    for (int v = 0; v < kNumVariants; ++v)
+        if (kVariants[v].fits(n, keep)) return v;
+    return -1;
+}
+
 }  // namespace
 
 struct pqp_handle {
@@ -55,7 +98,7 @@ struct pqp_handle {
     int32_t *d_n = nullptr, *d_off = nullptr, *d_order = nullptr, *d_status = nullptr, *d_iters = nullptr;
     pqp_state *d_ref = nullptr, *d_out = nullptr;
     pqp_station_bounds *d_bounds = nullptr;
-    double *d_x0 = nullptr, *d_end = nullptr, *d_frenet = nullptr;
+    double *d_x0 = nullptr, *d_end = nullptr, *d_frenet = nullptr, *d_ws = nullptr;
     // pinned host scratch for the small per-batch arrays
     int32_t *h_off = nullptr, *h_order = nullptr;
 };
@@ -143,7 +186,7 @@ void pqp_destroy(pqp_handle *h) {
     cudaSetDevice(h->device);
     cudaFree(h->d_n); cudaFree(h->d_off); cudaFree(h->d_order); cudaFree(h->d_status); cudaFree(h->d_iters);
     cudaFree(h->d_ref); cudaFree(h->d_out); cudaFree(h->d_bounds);
-    cudaFree(h->d_x0); cudaFree(h->d_end); cudaFree(h->d_frenet);
+    cudaFree(h->d_x0); cudaFree(h->d_end); cudaFree(h->d_frenet); cudaFree(h->d_ws);
     cudaFreeHost(h->h_off); cudaFreeHost(h->h_order);
     for (auto &e : h->ev) if (e) cudaEventDestroy(e);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -189,7 +232,8 @@ int pqp_create(pqp_handle **out, const pqp_params *params, int device, int max_b
     PQP_TRY(cudaDeviceGetAttribute(&h->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
     PQP_TRY(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device));
     // fails with cudaErrorNoKernelImageForDevice / InvalidDeviceFunction on anything but sm_100
-    PQP_TRY(cudaFuncSetAttribute(pqp_kp_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin));
+    for (int v = 0; v < kNumVariants; ++v)
+        PQP_TRY(cudaFuncSetAttribute(kVariants[v].fn, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin));
     PQP_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     for (auto &e : h->ev) PQP_TRY(cudaEventCreate(&e));
     const size_t B = (size_t)max_batch, T = (size_t)max_total_points;
@@ -204,6 +248,7 @@ int pqp_create(pqp_handle **out, const pqp_params *params, int device, int max_b
     PQP_TRY(cudaMalloc(&h->d_x0, B * 3 * sizeof(double)));
     PQP_TRY(cudaMalloc(&h->d_end, B * sizeof(double)));
     PQP_TRY(cudaMalloc(&h->d_frenet, T * 3 * sizeof(double)));
+    PQP_TRY(cudaMalloc(&h->d_ws, pqp::kp2_ws_doubles(T, B) * sizeof(double)));
     PQP_TRY(cudaMallocHost(&h->h_off, (B + 1) * sizeof(int32_t)));
     PQP_TRY(cudaMallocHost(&h->h_order, B * sizeof(int32_t)));
 #undef PQP_TRY
@@ -217,25 +262,27 @@ int pqp_max_points(pqp_handle *h, int formulation) {
     int best = 0;
     for (int n = 2; n <= 4096; ++n) {
         // keep = 4 (ds = 0.3 m stations give 3, the reference's dense 0.25 m spacing gives 4)
-        if (pqp::kp_smem_doubles(pqp::kp_dims(n, 4)) * sizeof(double) <= (size_t)h->smem_optin) best = n;
+        const int v = pick_variant(n, 4);
+        if (v >= 0 && kVariants[v].smem(n, 4) <= (size_t)h->smem_optin) best = n;
         else break;
     }
     return best;
 }
 
-static int launch_kp(pqp_handle *h, const pqp::BatchView &bv, const int32_t *d_order, size_t smem_bytes,
-                     cudaStream_t st) {
+static int launch_variant(pqp_handle *h, int v, const pqp::BatchView &bv, int count, const int32_t *d_order,
+                          size_t smem_bytes, cudaStream_t st) {
     if (smem_bytes > (size_t)h->smem_optin) {
         set_err("path too long for one SM's shared memory");
         return PQP_ERR_UNSUPPORTED;
     }
-    pqp_kp_solve_kernel<<<bv.batch, 32, smem_bytes, st>>>(h->dprm, bv, d_order, (int)(smem_bytes / sizeof(double)));
-    PQP_CUDA(cudaGetLastError());
+    int smem_doubles = (int)(smem_bytes / sizeof(double));
+    void *args[] = {(void *)&h->dprm, (void *)&bv, (void *)&d_order, (void *)&smem_doubles};
+    PQP_CUDA(cudaLaunchKernel(kVariants[v].fn, dim3(count), dim3(32), args, smem_bytes, st));
     return PQP_OK;
 }
 
 int pqp_solve_batch_device(pqp_handle *h, int formulation, int batch, int total_points,
-                           const int32_t *d_n_points, const int32_t *d_offsets, const pqp_state *d_ref,
+                           int max_n_points, int max_keep, const int32_t *d_n_points, const int32_t *d_offsets, const pqp_state *d_ref,
                            const pqp_station_bounds *d_bounds, const double *d_x0, const double *d_end_heading,
                            const double *d_max_k, const double *d_max_kp, pqp_state *d_out_states,
                            double *d_out_frenet, int32_t *d_status, int32_t *d_iters, void *stream,
@@ -257,14 +304,32 @@ int pqp_solve_batch_device(pqp_handle *h, int formulation, int batch, int total_
     bv.batch = batch; bv.n_points = d_n_points; bv.offsets = d_offsets; bv.ref = d_ref; bv.bounds = d_bounds;
     bv.x0 = d_x0; bv.end_heading = d_end_heading; bv.out_states = d_out_states; bv.out_frenet = d_out_frenet;
     bv.status = d_status; bv.iters = d_iters;
-    // The host does not see n_points here: size shared memory for the largest path the handle was
-    // created for (max_total_points bounds any single path) capped at the device limit; a path that
-    // does not fit reports PQP_INVALID_PROBLEM in its status.
-    int nmax = std::min(h->max_total, pqp_max_points(h, formulation));
-    size_t smem = pqp::kp_smem_doubles(pqp::kp_dims(nmax, 4)) * sizeof(double);
-    smem = std::min(smem, (size_t)h->smem_optin);
+    // The host does not see n_points / keep here: the kernel shape class and the shared memory are
+    // chosen from the caller's bounds; a path that does not fit reports PQP_INVALID_PROBLEM.
+    bv.workspace = h->d_ws;
+    if (batch > h->max_batch || total_points > h->max_total) {
+        set_err("batch / total_points exceed what the handle was created for (workspace size)");
+        return PQP_ERR_CAPACITY;
+    }
+    const int nmax = max_n_points >= 2 ? max_n_points : std::min(h->max_total, 400);
+    const int k_hi = (max_keep >= 1) ? std::min(max_keep, 10) : 4;
+    int v = -1;
+    size_t smem = 0;
+    for (int cand = 0; cand < kNumVariants && v < 0; ++cand) {
+        bool all = true;
+        size_t need = 0;
+        for (int k = 1; k <= k_hi; ++k) {
+            if (!kVariants[cand].fits(nmax, k)) { all = false; break; }
+            need = std::max(need, kVariants[cand].smem(nmax, k));
+        }
+        if (all && need <= (size_t)h->smem_optin) { v = cand; smem = need; }
+    }
+    if (v < 0) {
+        set_err("no kernel shape class fits (max_n_points, max_keep)");
+        return PQP_ERR_UNSUPPORTED;
+    }
     if (stats) PQP_CUDA(cudaEventRecord(h->ev[0], st));
-    int rc = launch_kp(h, bv, nullptr, smem, st);
+    int rc = launch_variant(h, v, bv, batch, nullptr, smem, st);
     if (rc != PQP_OK) return rc;
     if (stats) {
         memset(stats, 0, sizeof(*stats));
@@ -295,28 +360,46 @@ int pqp_solve_batch(pqp_handle *h, int formulation, int batch, const int32_t *n_
         set_err("batch exceeds the handle's max_batch");
         return PQP_ERR_CAPACITY;
     }
-    // offsets, per-path shared memory need, longest-first order
+    // offsets; shape class and shared-memory need per path; per-class longest-first order
     long long total = 0;
-    size_t smem = 0;
     h->h_off[0] = 0;
+    std::vector<int> cls((size_t)batch);
+    size_t smem_v[kNumVariants] = {0};
+    int count_v[kNumVariants] = {0};
     for (int b = 0; b < batch; ++b) {
         const int n = n_points[b];
         if (n < 0) { set_err("negative n_points"); return PQP_ERR_ARG; }
         total += n;
         if (total > h->max_total) { set_err("station count exceeds the handle's max_total_points"); return PQP_ERR_CAPACITY; }
         h->h_off[b + 1] = (int32_t)total;
+        int v = kNumVariants - 1, keep = 1;
         if (n >= 2) {
-            const int keep = pqp_keep_control_steps(formulation, ref + h->h_off[b], n);
-            if (keep <= 10) smem = std::max(smem, pqp::kp_smem_doubles(pqp::kp_dims(n, keep)) * sizeof(double));
+            keep = pqp_keep_control_steps(formulation, ref + h->h_off[b], n);
+            const int pv = pick_variant(n, keep);
+            if (pv >= 0) v = pv;
         }
-        h->h_order[b] = b;
+        const int ke = std::min(std::max(keep, 1), 10), ne = std::max(n, 2);
+        size_t need = kVariants[v].smem(ne, ke);
+        if (need > (size_t)h->smem_optin) {
+            // too long for this class: the generic kernel reports PQP_INVALID_PROBLEM for it
+            v = kNumVariants - 1;
+            need = kVariants[v].smem(2, 1);
+        }
+        cls[b] = v;
+        smem_v[v] = std::max(smem_v[v], need);
+        count_v[v]++;
     }
-    if (smem == 0) smem = pqp::kp_smem_doubles(pqp::kp_dims(2, 1)) * sizeof(double);
-    if (smem > (size_t)h->smem_optin) {
-        set_err("a path is too long for one SM's shared memory");
-        return PQP_ERR_UNSUPPORTED;
+    int start_v[kNumVariants + 1];
+    start_v[0] = 0;
+    for (int v = 0; v < kNumVariants; ++v) start_v[v + 1] = start_v[v] + count_v[v];
+    {
+        int fill[kNumVariants];
+        for (int v = 0; v < kNumVariants; ++v) fill[v] = start_v[v];
+        for (int b = 0; b < batch; ++b) h->h_order[fill[cls[b]]++] = b;
+        for (int v = 0; v < kNumVariants; ++v)
+            std::stable_sort(h->h_order + start_v[v], h->h_order + start_v[v + 1],
+                             [&](int a, int b) { return n_points[a] > n_points[b]; });
     }
-    std::stable_sort(h->h_order, h->h_order + batch, [&](int a, int b) { return n_points[a] > n_points[b]; });
     PQP_CUDA(cudaSetDevice(h->device));
     cudaStream_t st = h->stream;
     const size_t T = (size_t)total, B = (size_t)batch;
@@ -334,8 +417,14 @@ int pqp_solve_batch(pqp_handle *h, int formulation, int batch, const int32_t *n_
     bv.x0 = h->d_x0; bv.end_heading = h->d_end; bv.out_states = h->d_out;
     bv.out_frenet = out_frenet ? h->d_frenet : nullptr;
     bv.status = h->d_status; bv.iters = h->d_iters;
-    int rc = launch_kp(h, bv, h->d_order, smem, st);
-    if (rc != PQP_OK) return rc;
+    bv.workspace = h->d_ws;
+    int launches = 0;
+    for (int v = 0; v < kNumVariants; ++v) {
+        if (!count_v[v]) continue;
+        int rc = launch_variant(h, v, bv, count_v[v], h->d_order + start_v[v], smem_v[v], st);
+        if (rc != PQP_OK) return rc;
+        ++launches;
+    }
     PQP_CUDA(cudaEventRecord(h->ev[2], st));
     PQP_CUDA(cudaMemcpyAsync(out_states, h->d_out, T * sizeof(pqp_state), cudaMemcpyDeviceToHost, st));
     if (out_frenet) PQP_CUDA(cudaMemcpyAsync(out_frenet, h->d_frenet, T * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -352,7 +441,7 @@ int pqp_solve_batch(pqp_handle *h, int formulation, int batch, const int32_t *n_
         PQP_CUDA(cudaEventElapsedTime(&stats->d2h_ms, h->ev[2], h->ev[3]));
         stats->h2d_bytes = (int64_t)(B * sizeof(int32_t) * 3 + sizeof(int32_t) + T * (sizeof(pqp_state) + sizeof(pqp_station_bounds)) + B * 4 * sizeof(double));
         stats->d2h_bytes = (int64_t)(T * sizeof(pqp_state) + (out_frenet ? T * 3 * sizeof(double) : 0) + B * sizeof(int32_t) * 2);
-        stats->kernel_launches = 1;
+        stats->kernel_launches = launches;
         for (size_t b = 0; b < B; ++b) {
             stats->total_iters += it_dst[b];
             stats->max_iters = std::max(stats->max_iters, it_dst[b]);

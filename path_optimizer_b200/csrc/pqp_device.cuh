@@ -48,6 +48,7 @@ struct BatchView {
     double *out_frenet;                // [sum N][3] or nullptr
     int32_t *status;                   // [B]
     int32_t *iters;                    // [B] or nullptr
+    double *workspace;                 // global scratch: 16*sum(N) + 128*B doubles (v2 kernels)
 };
 
 

@@ -12,8 +12,22 @@ from tests.emu import emu
 TOL = 1e-9  # same recurrence in fp64: agreement is ~1e-13 in practice
 
 
-def _check(batch, params):
-    e = emu.solve_batch(params, batch)
+def _variant_for(batch):
+    """Pick the kernel shape class the library would pick (mirrors pick_variant in pqp_capi.cu)."""
+    keeps = [oracle.keep_control_steps(0, batch["ref"][batch["offsets"][b]:batch["offsets"][b + 1]])
+             for b in range(len(batch["n_points"]))]
+    nmax, kmax = int(batch["n_points"].max()), max(keeps)
+    if kmax > 4:
+        return 0
+    if kmax <= 3 and nmax <= 187:
+        return 1          # Kp2<17,6>
+    if kmax == 4 and nmax <= 125 and min(keeps) == 4:
+        return 2          # Kp2<10,7>
+    return 4              # Kp2<49,7>
+
+
+def _check(batch, params, variant=None):
+    e = emu.solve_batch(params, batch, variant=_variant_for(batch) if variant is None else variant)
     o = oracle.solve_batch(params, 0, batch)
     assert np.array_equal(e["status"], o["status"])
     assert np.array_equal(e["iters"], o["iters"])
@@ -45,7 +59,7 @@ def test_emu_invalid_and_unconstrained_end(oracle_params):
     b["bounds"]["c2_lb"][5] = 1.0
     b["bounds"]["c2_ub"][5] = -1.0      # path 0 invalid (l > u)
     b["end_heading"][1] = 2.0           # path 1: end_psi > 70 deg -> end heading row is free
-    e = emu.solve_batch(oracle_params, b)
+    e = emu.solve_batch(oracle_params, b, variant=1)
     o = oracle.solve_batch(oracle_params, 0, b)
     assert e["status"][0] == o["status"][0] == -100
     assert np.all(np.isnan(e["frenet"][:20]))
@@ -57,8 +71,21 @@ def test_emu_max_iter_status(oracle_params):
     p = oracle_params.copy()
     p.max_iter = 50
     b = synth.straight_corridors(1, 30)
-    e = emu.solve_batch(p, b)
+    e = emu.solve_batch(p, b, variant=1)
     o = oracle.solve_batch(p, 0, b)
     assert e["status"][0] == o["status"][0]
     assert e["iters"][0] == o["iters"][0] == 50
     np.testing.assert_allclose(e["frenet"], o["frenet"], rtol=0, atol=TOL)
+
+
+def test_emu_generic_core_still_matches(oracle_params):
+    """The generic fallback kernel source (pqp_kp_core.cuh, used for keep_control_steps > 4)."""
+    _check(synth.curvy_corridors(2, n_points=[33, 70]), oracle_params, variant=0)
+
+
+@pytest.mark.parametrize("variant,n,ds", [(1, 187, 0.3), (2, 125, 0.25), (3, 200, 0.3), (4, 300, 0.3)])
+def test_emu_shape_classes(oracle_params, variant, n, ds):
+    b = synth.curvy_corridors(1, n)
+    if ds != 0.3:
+        b["ref"]["s"] = np.arange(n) * ds
+    _check(b, oracle_params, variant=variant)

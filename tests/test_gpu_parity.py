@@ -141,3 +141,37 @@ def test_osqp_solver_adaptor(solver, oracle_params):
     ref = oracle.solve_batch(oracle_params, 0, b)
     np.testing.assert_allclose([q["x"] for q in path], ref["states"]["x"], rtol=0, atol=FRENET_TOL)
     assert OsqpSolver.create("XYZ", b["ref"], b["bounds"], (0, 0), 0, 0, 70) is None
+
+
+def test_cpp_host_mirror(oracle_params, tmp_path):
+    """The C++ host side (include/pqp_solver.hpp: BatchPathSolver + GpuOsqpSolver with the reference's
+    create()/solve() shape) through a small compiled driver."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "tests", "cpp", "host_driver")
+    src = exe + ".cpp"
+    if not os.path.exists(exe) or os.path.getmtime(src) > os.path.getmtime(exe):
+        subprocess.run(["g++", "-O2", "-std=c++17", src, "-o", exe, "-L" + os.path.join(root, "path_optimizer_b200"),
+                        "-lpqp", "-Wl,-rpath," + os.path.join(root, "path_optimizer_b200")], check=True)
+    b = synth.curvy_corridors(5, n_points=[60, 33, 100, 7, 81])
+    veh = np.column_stack([b["x0"], b["end_heading"]])
+    fin, fout = tmp_path / "in.bin", tmp_path / "out.bin"
+    with open(fin, "wb") as f:
+        f.write(np.int32(5).tobytes()); f.write(b["n_points"].tobytes()); f.write(b["ref"].tobytes())
+        f.write(b["bounds"].tobytes()); f.write(np.ascontiguousarray(veh).tobytes())
+    subprocess.run([exe, str(fin), str(fout)], check=True)
+    raw = open(fout, "rb").read()
+    total = int(b["n_points"].sum())
+    frenet = np.frombuffer(raw, dtype=np.float64, count=3 * total).reshape(total, 3)
+    o = 24 * total
+    status = np.frombuffer(raw, dtype=np.int32, count=5, offset=o)
+    iters = np.frombuffer(raw, dtype=np.int32, count=5, offset=o + 20)
+    ok = np.frombuffer(raw, dtype=np.int32, count=1, offset=o + 40)[0]
+    from path_optimizer_b200.abi import STATE_DTYPE
+    path0 = np.frombuffer(raw, dtype=STATE_DTYPE, count=60, offset=o + 44)
+    ref = oracle.solve_batch(oracle_params, 0, b)
+    assert np.array_equal(status, ref["status"]) and np.array_equal(iters, ref["iters"])
+    np.testing.assert_allclose(frenet, ref["frenet"], rtol=0, atol=FRENET_TOL)
+    assert ok == 1
+    np.testing.assert_allclose(path0["x"], ref["states"]["x"][:60], rtol=0, atol=FRENET_TOL)
+    np.testing.assert_allclose(path0["s"], ref["states"]["s"][:60], rtol=0, atol=FRENET_TOL)
