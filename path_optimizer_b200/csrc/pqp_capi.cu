@@ -42,38 +42,40 @@ pqp_kp_solve_kernel(const __grid_constant__ pqp::DevParams prm, const __grid_con
 }
 
 // Production kernels: one instantiation per (max interior size, half-bandwidth) shape class.
+// A CTA of kNW warps solves one path: all warps share the per-station phases, warp 0 runs the KKT solve.
+constexpr int kNW = 4;
 template <int IMAX, int BW>
-__global__ void __launch_bounds__(32)
+__global__ void __launch_bounds__(kNW * 32, 3)
 pqp_kp2_solve_kernel(const __grid_constant__ pqp::DevParams prm, const __grid_constant__ pqp::BatchView bv,
                      const int32_t *__restrict__ order, int smem_doubles) {
     extern __shared__ double pqp_smem[];
     int prob = blockIdx.x;
     if (order) prob = order[prob];
-    pqp::Warp w;
-    pqp::Kp2<IMAX, BW>::solve_path(w, prm, bv, prob, pqp_smem, (size_t)smem_doubles);
+    pqp::Cta c{pqp::Warp(), pqp::CtaSync(), (int)(threadIdx.x >> 5), kNW, pqp_smem};
+    pqp::Kp2<IMAX, BW>::solve_path(c, prm, bv, prob, pqp_smem + 32, (size_t)smem_doubles - 32);
 }
 
 // Shape classes.  keep_control_steps <= 4 (station spacing >= 0.24 m) maps onto one of the Kp2
 // instantiations; anything else runs on the generic kernel.
 struct Variant {
-    int imax, bw;
+    int imax, bw, threads;
     const void *fn;
     size_t (*smem)(int n, int keep);
     bool (*fits)(int n, int keep);
 };
 template <int IMAX, int BW> size_t v_smem(int n, int keep) {
-    return pqp::Kp2<IMAX, BW>::smem_doubles(pqp::Kp2<IMAX, BW>::dims(n, keep)) * sizeof(double);
+    return (32 + pqp::Kp2<IMAX, BW>::smem_doubles(pqp::Kp2<IMAX, BW>::dims(n, keep))) * sizeof(double);
 }
 template <int IMAX, int BW> bool v_fits(int n, int keep) {
     return keep <= 10 && pqp::Kp2<IMAX, BW>::fits(pqp::kp2_dims(n, keep));
 }
 size_t g_smem(int n, int keep) { return pqp::kp_smem_doubles(pqp::kp_dims(n, keep)) * sizeof(double); }
 bool g_fits(int, int keep) { return keep <= 10; }
-#define PQP_VARIANT(I, B) {I, B, (const void *)pqp_kp2_solve_kernel<I, B>, v_smem<I, B>, v_fits<I, B>}
+#define PQP_VARIANT(I, B) {I, B, kNW * 32, (const void *)pqp_kp2_solve_kernel<I, B>, v_smem<I, B>, v_fits<I, B>}
 const Variant kVariants[] = {
     PQP_VARIANT(17, 6), PQP_VARIANT(10, 7), PQP_VARIANT(17, 7), PQP_VARIANT(27, 7), PQP_VARIANT(37, 7),
     PQP_VARIANT(49, 7),
-    {0, kMaxBandGeneric, (const void *)pqp_kp_solve_kernel, g_smem, g_fits},  // generic fallback (last)
+    {0, kMaxBandGeneric, 32, (const void *)pqp_kp_solve_kernel, g_smem, g_fits},  // generic fallback (last)
 };
 constexpr int kNumVariants = (int)(sizeof(kVariants) / sizeof(kVariants[0]));
 
@@ -277,7 +279,7 @@ static int launch_variant(pqp_handle *h, int v, const pqp::BatchView &bv, int co
     }
     int smem_doubles = (int)(smem_bytes / sizeof(double));
     void *args[] = {(void *)&h->dprm, (void *)&bv, (void *)&d_order, (void *)&smem_doubles};
-    PQP_CUDA(cudaLaunchKernel(kVariants[v].fn, dim3(count), dim3(32), args, smem_bytes, st));
+    PQP_CUDA(cudaLaunchKernel(kVariants[v].fn, dim3(count), dim3(kVariants[v].threads), args, smem_bytes, st));
     return PQP_OK;
 }
 

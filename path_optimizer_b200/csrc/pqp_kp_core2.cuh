@@ -52,61 +52,73 @@ PQP_HD size_t kp2_ws_doubles(size_t total_points, size_t batch) { return 16 * to
 template <int IMAX, int BW>
 struct Kp2 {
     // ---- shared-memory layout -----------------------------------------------------------------
+    // Per-station fields are tiled: station i = 32*r + l lives at st[(r*kNF + f)*32 + l].  For a lane
+    // walking its stations (l = lane) every field is then a compile-time offset from ONE base
+    // register, and consecutive lanes hit consecutive banks.
+    struct Fld {
+        double *p;
+        PQP_DEV double &operator[](int i) const { return p[(i >> 5) * (kNF * 32) + (i & 31)]; }
+    };
+    struct FldI {
+        double *p;
+        PQP_DEV int &operator[](int i) const { return *(int *)&p[(i >> 5) * (kNF * 32) + (i & 31)]; }
+    };
+    static constexpr int kNF = 39;
     struct Smem {
         double *base;
-        int N, ch, nv, M;
+        int N, ch, nv, M, R;   // R = number of 32-station tiles
         // region A (persistent)
         PQP_DEV double *xr() const { return base; }
         PQP_DEV double *tr() const { return base + nv; }
         PQP_DEV double *sgr() const { return base + 2 * nv; }
-        PQP_DEV double *nA(int k) const { return base + 3 * nv + k * N; }
-        PQP_DEV double *xs() const { return nA(0); }
-        PQP_DEV double *ts() const { return nA(1); }
-        PQP_DEV double *sgs() const { return nA(2); }
-        PQP_DEV double *ksinv() const { return nA(3); }
-        PQP_DEV double *ds() const { return nA(4); }
-        PQP_DEV double *q10() const { return nA(5); }
-        PQP_DEV double *kds() const { return nA(6); }
-        PQP_DEV double *lH1() const { return nA(7); }
-        PQP_DEV double *uH1() const { return nA(8); }
-        PQP_DEV double *lH3() const { return nA(9); }
-        PQP_DEV double *uH3() const { return nA(10); }
-        PQP_DEV double *uS4m() const { return nA(11); }
-        PQP_DEV double *lS4p() const { return nA(12); }
-        PQP_DEV double *uS2m() const { return nA(13); }
-        PQP_DEV double *lS2p() const { return nA(14); }
-        PQP_DEV double *WD() const { return nA(15); }   // [3][N]
-        PQP_DEV double *WKB() const { return nA(18); }
-        PQP_DEV double *WSB() const { return nA(19); }
-        PQP_DEV double *WH1() const { return nA(20); }
-        PQP_DEV double *WH3() const { return nA(21); }
-        PQP_DEV double *WS4() const { return nA(22); }
-        PQP_DEV double *WS2() const { return nA(23); }
-        static constexpr int kNA = 24;
-        PQP_DEV double *tailA() const { return nA(kNA); }
+        PQP_DEV double *st() const { return base + 3 * nv; }
+        PQP_DEV Fld fld(int f) const { return Fld{st() + f * 32}; }
+        PQP_DEV Fld xs() const { return fld(0); }
+        PQP_DEV Fld ts() const { return fld(1); }
+        PQP_DEV Fld sgs() const { return fld(2); }
+        PQP_DEV Fld ksinv() const { return fld(3); }
+        PQP_DEV Fld ds() const { return fld(4); }
+        PQP_DEV Fld q10() const { return fld(5); }
+        PQP_DEV Fld kds() const { return fld(6); }
+        PQP_DEV Fld lH1() const { return fld(7); }
+        PQP_DEV Fld uH1() const { return fld(8); }
+        PQP_DEV Fld lH3() const { return fld(9); }
+        PQP_DEV Fld uH3() const { return fld(10); }
+        PQP_DEV Fld uS4m() const { return fld(11); }
+        PQP_DEV Fld lS4p() const { return fld(12); }
+        PQP_DEV Fld uS2m() const { return fld(13); }
+        PQP_DEV Fld lS2p() const { return fld(14); }
+        PQP_DEV Fld WD(int k) const { return fld(15 + k); }   // k = 0..2
+        PQP_DEV Fld WKB() const { return fld(18); }
+        PQP_DEV Fld WSB() const { return fld(19); }
+        PQP_DEV Fld WH1() const { return fld(20); }
+        PQP_DEV Fld WH3() const { return fld(21); }
+        PQP_DEV Fld WS4() const { return fld(22); }
+        PQP_DEV Fld WS2() const { return fld(23); }
+        PQP_DEV Fld vD(int k) const { return fld(24 + k); }   // k = 0..2
+        PQP_DEV Fld vKB() const { return fld(27); }
+        PQP_DEV Fld vSB() const { return fld(28); }
+        PQP_DEV Fld vH1() const { return fld(29); }
+        PQP_DEV Fld vH3() const { return fld(30); }
+        PQP_DEV Fld vS4m() const { return fld(31); }
+        PQP_DEV Fld vS4p() const { return fld(32); }
+        PQP_DEV Fld vS2m() const { return fld(33); }
+        PQP_DEV Fld vS2p() const { return fld(34); }
+        PQP_DEV Fld gD(int k) const { return fld(35 + k); }   // k = 0..2
+        PQP_DEV FldI gxi() const { return FldI{st() + 38 * 32}; }
+        PQP_DEV double *tailA() const { return st() + R * kNF * 32; }
         PQP_DEV double *WUB() const { return tailA(); }
         PQP_DEV double *vUB() const { return tailA() + ch; }
         PQP_DEV double *WEnd() const { return tailA() + 2 * ch; }
         PQP_DEV double *vEnd() const { return tailA() + 2 * ch + 2; }
-        PQP_DEV int *gxi() const { return (int *)(tailA() + 2 * ch + 4); }
-        PQP_DEV int *gui() const { return gxi() + N; }
-        PQP_DEV double *regB() const { return tailA() + 2 * ch + 4 + (N + ch + 1) / 2; }
-        // region B (per-iteration state + factor; aliased by the scaling scratch)
-        PQP_DEV double *vD() const { return regB(); }       // [3][N]
-        PQP_DEV double *vN(int k) const { return regB() + (3 + k) * N; }
-        PQP_DEV double *vKB() const { return vN(0); }
-        PQP_DEV double *vSB() const { return vN(1); }
-        PQP_DEV double *vH1() const { return vN(2); }
-        PQP_DEV double *vH3() const { return vN(3); }
-        PQP_DEV double *vS4m() const { return vN(4); }
-        PQP_DEV double *vS4p() const { return vN(5); }
-        PQP_DEV double *vS2m() const { return vN(6); }
-        PQP_DEV double *vS2p() const { return vN(7); }
-        PQP_DEV double *fac() const { return regB() + 11 * N; }
+        PQP_DEV int *gui() const { return (int *)(tailA() + 2 * ch + 4); }
+        PQP_DEV double *regB() const { return tailA() + 2 * ch + 4 + (ch + 1) / 2; }
+        // region B: factor, separator system, lane scratch (aliased by the scaling scratch)
+        PQP_DEV double *fac() const { return regB(); }
         PQP_DEV double *red() const { return fac() + IMAX * (BW + 1) * M; }
-        PQP_DEV double *lsc() const { return red() + kRed2 * M; }   // max(IMAX*M, 3N): lane scratch / gD
-        PQP_DEV double *gD() const { return lsc(); }
-        // scaling scratch over region B
+        PQP_DEV double *lsc() const { return red() + kRed2 * M; }   // IMAX*M lane scratch
+        // scaling scratch: region B plus the (not yet live) v / gD fields is too scattered, so the
+        // scratch simply extends past region B; smem_doubles() accounts for it.
         PQP_DEV double *sDr() const { return regB(); }
         PQP_DEV double *sDsl() const { return regB() + nv; }
         PQP_DEV double *sE() const { return regB() + nv + N; }                    // 9N + ch + 2
@@ -116,10 +128,9 @@ struct Kp2 {
     };
     PQP_HD static size_t smem_doubles(const Kp2Dims &d) {
         const size_t N = (size_t)d.N, ch = (size_t)d.ch, nv = (size_t)d.nv, M = (size_t)d.M;
-        const size_t A = 3 * nv + (size_t)Smem::kNA * N + 2 * ch + 4 + (N + ch + 1) / 2;
-        size_t lsc = (size_t)IMAX * M;
-        if (lsc < 3 * N) lsc = 3 * N;
-        size_t B = 11 * N + (size_t)IMAX * (BW + 1) * M + (size_t)kRed2 * M + lsc;
+        const size_t R = (N + 31) / 32;
+        const size_t A = 3 * nv + R * kNF * 32 + 2 * ch + 4 + (ch + 1) / 2;
+        size_t B = (size_t)IMAX * (BW + 1) * M + (size_t)kRed2 * M + (size_t)IMAX * M;
         const size_t S = 2 * nv + 20 * N + 2 * ch + 4;
         if (B < S) B = S;
         return A + B;
@@ -213,17 +224,17 @@ struct Kp2 {
     }
 
     // ---- row weights for the current rho, from the workspace E ----------------------------------
-    PQP_DEV static void weights(Warp &w, Ctx &cx) {
+    PQP_DEV static void weights(const Cta &c, Ctx &cx) {
         const Smem &s = cx.s;
         const Kp2Dims &d = cx.d;
         const DevParams &pm = *cx.pm;
-        const int N = d.N, ch = d.ch, lane = w.lane();
+        const int N = d.N, ch = d.ch, tid = c.tid(), nt = c.nthreads();
         const double rho = cx.rho;
         const double *E = wsE(cx);
-        for (int i = lane; i < N; i += 32) {
-            s.WD()[i] = kp_w_eq(E[i], rho);
-            s.WD()[N + i] = kp_w_eq(E[N + i], rho);
-            s.WD()[2 * N + i] = kp_w_eq(E[2 * N + i], rho);
+        for (int i = tid; i < N; i += nt) {
+            s.WD(0)[i] = kp_w_eq(E[i], rho);
+            s.WD(1)[i] = kp_w_eq(E[N + i], rho);
+            s.WD(2)[i] = kp_w_eq(E[2 * N + i], rho);
             s.WKB()[i] = kp_w_box(E[3 * N + i], -pm.kmax, pm.kmax, rho);
             s.WSB()[i] = kp_w_box(E[4 * N + i], 0.0, pm.margin, rho);
             s.WH1()[i] = kp_w_box(E[5 * N + i], s.lH1()[i], s.uH1()[i], rho);
@@ -231,32 +242,33 @@ struct Kp2 {
             s.WS4()[i] = kp_w_box(E[7 * N + i], -kOsqpInfty, s.uS4m()[i], rho);
             s.WS2()[i] = kp_w_box(E[8 * N + i], -kOsqpInfty, s.uS2m()[i], rho);
         }
-        for (int j = lane; j < ch; j += 32) s.WUB()[j] = kp_w_box(E[9 * N + j], -kOsqpInfty, kOsqpInfty, rho);
-        if (lane == 0) {
+        for (int j = tid; j < ch; j += nt) s.WUB()[j] = kp_w_box(E[9 * N + j], -kOsqpInfty, kOsqpInfty, rho);
+        if (tid == 0) {
             s.WEnd()[0] = kp_w_box(E[9 * N + ch], -1.0, 1.0, rho);
             s.WEnd()[1] = kp_w_box(E[9 * N + ch + 1], cx.lEH, cx.uEH, rho);
         }
-        w.sync();
+        c.sync();
     }
 
     // ---- Ruiz equilibration (same arithmetic as kp_scale in pqp_kp_core.cuh, new layout) ---------
-    PQP_DEV static void scale(Warp &w, Ctx &cx) {
+    PQP_DEV static void scale(const Cta &c, Ctx &cx) {
         const Smem &s = cx.s;
         const Kp2Dims &d = cx.d;
-        const int N = d.N, ch = d.ch, keep = d.keep, lane = w.lane();
+        const int N = d.N, ch = d.ch, keep = d.keep, tid = c.tid(), nt = c.nthreads();
         const DevParams &pm = *cx.pm;
         double *Dr = s.sDr(), *Dsl = s.sDsl(), *E = s.sE(), *fDr = s.sfDr(), *fDs = s.sfDs(), *fE = s.sfE();
-        const int *gxi = s.gxi(), *gui = s.gui();
-        for (int g = lane; g < d.nv; g += 32) Dr[g] = 1.0;
-        for (int i = lane; i < N; i += 32) Dsl[i] = 1.0;
-        for (int k = lane; k < 9 * N + ch + 2; k += 32) E[k] = 1.0;
+        const auto gxi = s.gxi();
+        const int *gui = s.gui();
+        for (int g = tid; g < d.nv; g += nt) Dr[g] = 1.0;
+        for (int i = tid; i < N; i += nt) Dsl[i] = 1.0;
+        for (int k = tid; k < 9 * N + ch + 2; k += nt) E[k] = 1.0;
         cx.c = 1.0;
         cx.Dt = 1.0;
-        w.sync();
+        c.sync();
         const double ad1 = fabs(pm.d1), ad2 = fabs(pm.d2), ad3 = fabs(pm.d3), ad4 = fabs(pm.d4);
         for (int sweep = 0; sweep < pm.scaling; ++sweep) {
-            const double c = cx.c;
-            for (int i = lane; i < N; i += 32) {
+            const double cst = cx.c;
+            for (int i = tid; i < N; i += nt) {
                 const int ga = gxi[i];
                 const double Da = Dr[ga], Db = Dr[ga + 1], Dc = Dr[ga + 2], Dsv = Dsl[i];
                 const double e0 = E[i], e1 = E[N + i], e2 = E[2 * N + i];
@@ -277,10 +289,10 @@ struct Kp2 {
                     Ab = fmax(Ab, E[9 * N + ch + 1]);
                 }
                 const double As = fmax(eSB, fmax(eS4, eS2));
-                fDr[ga] = 1.0 / sqrt(limit_scaling(fmax(c * pm.w_pq * Da * Da, Aa * Da)));
+                fDr[ga] = 1.0 / sqrt(limit_scaling(fmax(cst * pm.w_pq * Da * Da, Aa * Da)));
                 fDr[ga + 1] = 1.0 / sqrt(limit_scaling(Ab * Db));
-                fDr[ga + 2] = 1.0 / sqrt(limit_scaling(fmax(c * pm.w_c * Dc * Dc, Ac * Dc)));
-                fDs[i] = 1.0 / sqrt(limit_scaling(fmax(c * pm.w_s * Dsv * Dsv, As * Dsv)));
+                fDr[ga + 2] = 1.0 / sqrt(limit_scaling(fmax(cst * pm.w_c * Dc * Dc, Ac * Dc)));
+                fDs[i] = 1.0 / sqrt(limit_scaling(fmax(cst * pm.w_s * Dsv * Dsv, As * Dsv)));
                 double r0, r1, r2;
                 if (i == 0) {
                     r0 = e0 * Da; r1 = e1 * Db; r2 = e2 * Dc;
@@ -306,74 +318,82 @@ struct Kp2 {
                     fE[9 * N + ch + 1] = 1.0 / sqrt(limit_scaling(E[9 * N + ch + 1] * Db));
                 }
             }
-            for (int j = lane; j < ch; j += 32) {
+            for (int j = tid; j < ch; j += nt) {
                 const int gu = gui[j];
                 const double Du = Dr[gu];
                 double Au = E[9 * N + j];
                 int t1 = j * keep + keep - 1;
                 if (t1 > N - 2) t1 = N - 2;
                 for (int t = j * keep; t <= t1; ++t) Au = fmax(Au, E[2 * N + t + 1] * s.ds()[t]);
-                fDr[gu] = 1.0 / sqrt(limit_scaling(fmax(c * (keep * pm.w_cr) * Du * Du, Au * Du)));
+                fDr[gu] = 1.0 / sqrt(limit_scaling(fmax(cst * (keep * pm.w_cr) * Du * Du, Au * Du)));
                 fE[9 * N + j] = 1.0 / sqrt(limit_scaling(E[9 * N + j] * Du));
             }
-            const double fDt = 1.0 / sqrt(limit_scaling(c * pm.w_s * cx.Dt * cx.Dt));
-            w.sync();
-            for (int i = lane; i < N; i += 32) {
+            const double fDt = 1.0 / sqrt(limit_scaling(cst * pm.w_s * cx.Dt * cx.Dt));
+            c.sync();
+            for (int i = tid; i < N; i += nt) {
                 const int ga = gxi[i];
                 Dr[ga] *= fDr[ga]; Dr[ga + 1] *= fDr[ga + 1]; Dr[ga + 2] *= fDr[ga + 2];
                 Dsl[i] *= fDs[i];
             }
-            for (int j = lane; j < ch; j += 32) Dr[gui[j]] *= fDr[gui[j]];
-            for (int k = lane; k < 9 * N + ch + 2; k += 32) E[k] *= fE[k];
+            for (int j = tid; j < ch; j += nt) Dr[gui[j]] *= fDr[gui[j]];
+            for (int k = tid; k < 9 * N + ch + 2; k += nt) E[k] *= fE[k];
             cx.Dt *= fDt;
-            w.sync();
+            c.sync();
             double part = 0.0;
-            for (int i = lane; i < N; i += 32) {
+            for (int i = tid; i < N; i += nt) {
                 const int ga = gxi[i];
                 const double Da = Dr[ga], Dc = Dr[ga + 2], Dsv = Dsl[i];
-                part += c * pm.w_pq * Da * Da + c * pm.w_c * Dc * Dc + c * pm.w_s * Dsv * Dsv +
-                        c * pm.w_s * cx.Dt * cx.Dt;
+                part += cst * pm.w_pq * Da * Da + cst * pm.w_c * Dc * Dc + cst * pm.w_s * Dsv * Dsv +
+                        cst * pm.w_s * cx.Dt * cx.Dt;
             }
-            for (int j = lane; j < ch; j += 32) {
+            for (int j = tid; j < ch; j += nt) {
                 const double Du = Dr[gui[j]];
-                part += c * (keep * pm.w_cr) * Du * Du;
+                part += cst * (keep * pm.w_cr) * Du * Du;
             }
-            const double mean = w.sum(part) / (double)(5 * N + ch);
+            const double mean = c.sum(part) / (double)(5 * N + ch);
             double ct = fmax(mean, 1.0);
             ct = limit_scaling(ct);
-            cx.c = c * (1.0 / ct);
-            w.sync();
+            cx.c = cst * (1.0 / ct);
+            c.sync();
         }
         // publish: sigma_v = sigma / D_v^2 into shared memory; E, D into the global workspace
-        for (int g = lane; g < d.nv; g += 32) {
+        for (int g = tid; g < d.nv; g += nt) {
             const double D = Dr[g];
             s.sgr()[g] = pm.sigma / (D * D);
             wsDr(cx)[g] = D;
         }
-        for (int i = lane; i < N; i += 32) {
+        for (int i = tid; i < N; i += nt) {
             const double D = Dsl[i];
             s.sgs()[i] = pm.sigma / (D * D);
             wsDsl(cx)[i] = D;
         }
-        for (int k = lane; k < 9 * N + ch + 2; k += 32) wsE(cx)[k] = E[k];
-        w.sync();
+        for (int k = tid; k < 9 * N + ch + 2; k += nt) wsE(cx)[k] = E[k];
+        c.sync();
     }
 
     // ---- assembly + factorisation ---------------------------------------------------------------
-    PQP_DEV static int factor(Warp &w, Ctx &cx) {
+    PQP_DEV static int factor(const Cta &c, Ctx &cx) {
+        const Smem &s = cx.s;
+        const DevParams &pm = *cx.pm;
+        // K_ss^-1 of the (exactly decoupled) slack unknowns: all threads
+        for (int i = c.tid(); i < cx.d.N; i += c.nthreads())
+            s.ksinv()[i] = 1.0 / (cx.c * pm.w_s + s.sgs()[i] + s.WSB()[i] + 2.0 * s.WS4()[i] + 2.0 * s.WS2()[i]);
+        int ok = 1;
+        if (c.wid == 0) ok = factor_w0(c.w, cx);   // partitioned KKT factorisation: warp 0
+        return !c.any(!ok);
+    }
+    PQP_DEV static int factor_w0(const Warp &w, Ctx &cx) {
         const Smem &s = cx.s;
         const Kp2Dims &d = cx.d;
         const DevParams &pm = *cx.pm;
         const int N = d.N, keep = d.keep, L = d.L, M = d.M, lane = w.lane();
         const double c = cx.c;
-        const int *gxi = s.gxi(), *gui = s.gui();
+        const auto gxi = s.gxi();
+        const int *gui = s.gui();
         const bool act = lane < M;
         const int Mst = M;
         double *fcol = s.fac() + lane;
         int ok = 1;
-        // K_ss^-1 of the (exactly decoupled) slack unknowns
-        for (int i = lane; i < N; i += 32)
-            s.ksinv()[i] = 1.0 / (c * pm.w_s + s.sgs()[i] + s.WSB()[i] + 2.0 * s.WS4()[i] + 2.0 * s.WS2()[i]);
         const int e = lane * L;                  // separator station of this lane
         const int lo = cx.lo, cnt = cx.cnt;
         if (act) {
@@ -388,10 +408,10 @@ struct Kp2 {
             for (int i = e + 1; i <= i1; ++i) {
                 const int ka = gxi[i] - lo;
                 const bool last = (i == N - 1);
-                const double W0 = s.WD()[i], W1 = s.WD()[N + i], W2 = s.WD()[2 * N + i];
+                const double W0 = s.WD(0)[i], W1 = s.WD(1)[i], W2 = s.WD(2)[i];
                 double N0 = 0, N1 = 0, N2 = 0, dsi = 0, q = 0;
                 if (!last) {
-                    N0 = s.WD()[i + 1]; N1 = s.WD()[N + i + 1]; N2 = s.WD()[2 * N + i + 1];
+                    N0 = s.WD(0)[i + 1]; N1 = s.WD(1)[i + 1]; N2 = s.WD(2)[i + 1];
                     dsi = s.ds()[i]; q = s.q10()[i];
                 }
                 const double wH1 = s.WH1()[i], wH3 = s.WH3()[i], w4 = s.WS4()[i], w2 = s.WS2()[i];
@@ -434,11 +454,11 @@ struct Kp2 {
                 for (int ii = j * keep; ii <= ii1; ++ii) {
                     double val = 0.0;
                     if (ii >= 1 && (ii - 1) / keep == j) {
-                        const double wv = s.WD()[2 * N + ii], dst = s.ds()[ii - 1];
+                        const double wv = s.WD(2)[ii], dst = s.ds()[ii - 1];
                         val -= wv * dst;
                         du += wv * dst * dst;
                     }
-                    if (ii <= N - 2 && ii / keep == j) val += s.WD()[2 * N + ii + 1] * s.ds()[ii];
+                    if (ii <= N - 2 && ii / keep == j) val += s.WD(2)[ii + 1] * s.ds()[ii];
                     if (ii % L == 0) continue;           // c of a separator station: closed-form coupling
                     const int kc = gxi[ii] + 2 - lo;
                     if (kc < ku) PQP_F(ku, ku - kc) = val;
@@ -462,7 +482,7 @@ struct Kp2 {
             double lN0 = 0, lN1 = 0, lN2 = 0, lds = 0, lq = 0;
             int ka1 = 0, kul = -1;
             if (has_int) {
-                lN0 = s.WD()[e + 1]; lN1 = s.WD()[N + e + 1]; lN2 = s.WD()[2 * N + e + 1];
+                lN0 = s.WD(0)[e + 1]; lN1 = s.WD(1)[e + 1]; lN2 = s.WD(2)[e + 1];
                 lds = s.ds()[e]; lq = s.q10()[e];
                 ka1 = gxi[e + 1] - lo;
                 kul = gui[e / keep] - lo;
@@ -470,7 +490,7 @@ struct Kp2 {
             double rW0 = 0, rW1 = 0, rW2 = 0, rds = 0, rq = 0;
             int kat = 0, kur = -1;
             if (has_right) {
-                rW0 = s.WD()[e2]; rW1 = s.WD()[N + e2]; rW2 = s.WD()[2 * N + e2];
+                rW0 = s.WD(0)[e2]; rW1 = s.WD(1)[e2]; rW2 = s.WD(2)[e2];
                 rds = s.ds()[e2 - 1]; rq = s.q10()[e2 - 1];
                 kat = gxi[e2 - 1] - lo;
                 kur = gui[(e2 - 1) / keep] - lo;
@@ -522,10 +542,10 @@ struct Kp2 {
         if (act) {
             const int i = e;
             const bool last = (i == N - 1);
-            const double W0 = s.WD()[i], W1 = s.WD()[N + i], W2 = s.WD()[2 * N + i];
+            const double W0 = s.WD(0)[i], W1 = s.WD(1)[i], W2 = s.WD(2)[i];
             double N0 = 0, N1 = 0, N2 = 0, dsi = 0, q = 0;
             if (!last) {
-                N0 = s.WD()[i + 1]; N1 = s.WD()[N + i + 1]; N2 = s.WD()[2 * N + i + 1];
+                N0 = s.WD(0)[i + 1]; N1 = s.WD(1)[i + 1]; N2 = s.WD(2)[i + 1];
                 dsi = s.ds()[i]; q = s.q10()[i];
             }
             const double wH1 = s.WH1()[i], wH3 = s.WH3()[i], w4 = s.WS4()[i], w2 = s.WS2()[i];
@@ -545,7 +565,8 @@ struct Kp2 {
             for (int k = 0; k < 9; ++k) { R[k] = Dg[k]; R[9 + k] = Of[k]; }
         }
         w.sync();
-        // ---- block LDL' of the separator system (sequential, lane 0)
+        // ---- block LDL' of the separator system (sequential, lane 0).  Stored per separator:
+        //      Sinv_p | H_p = Sinv_p Off_p | G_p = Off_{p-1}' Sinv_{p-1} | g_p
         if (lane == 0) {
             double Sch[9], Sinv[9];
             for (int k = 0; k < 9; ++k) Sch[k] = s.red()[k];
@@ -553,15 +574,19 @@ struct Kp2 {
                 double *Rp = s.red() + kRed2 * p;
                 if (!(Sch[0] > 0.0)) ok = 0;
                 inv3_spd(Sch, Sinv);
-                for (int k = 0; k < 9; ++k) Rp[k] = Sinv[k];
                 if (p + 1 < M) {
                     double *Rn = Rp + kRed2;
-                    const double *Off = Rp + 9;
+                    double Off[9];
+                    for (int k = 0; k < 9; ++k) Off[k] = Rp[9 + k];
                     for (int r = 0; r < 3; ++r)
                         for (int cc = 0; cc < 3; ++cc) {
-                            double a = 0.0;
-                            for (int k = 0; k < 3; ++k) a += Off[k * 3 + r] * Sinv[k * 3 + cc];
+                            double a = 0.0, hh = 0.0;
+                            for (int k = 0; k < 3; ++k) {
+                                a += Off[k * 3 + r] * Sinv[k * 3 + cc];
+                                hh += Sinv[r * 3 + k] * Off[k * 3 + cc];
+                            }
                             Rn[18 + r * 3 + cc] = a;
+                            Rp[9 + r * 3 + cc] = hh;
                         }
                     for (int r = 0; r < 3; ++r)
                         for (int cc = 0; cc < 3; ++cc) {
@@ -570,6 +595,7 @@ struct Kp2 {
                             Sch[r * 3 + cc] = a;
                         }
                 }
+                for (int k = 0; k < 9; ++k) Rp[k] = Sinv[k];
             }
         }
         ok = !w.any(!ok);
@@ -578,7 +604,11 @@ struct Kp2 {
     }
 
     // ---- K xt = rhs.  rhs in tr (padded order) on entry, xt on exit.  (ts is already final.)
-    PQP_DEV static void solve(Warp &w, Ctx &cx) {
+    PQP_DEV static void solve(const Cta &c, Ctx &cx) {
+        if (c.wid == 0) solve_w0(c.w, cx);
+        c.sync();
+    }
+    PQP_DEV static void solve_w0(const Warp &w, Ctx &cx) {
         const Smem &s = cx.s;
         const Kp2Dims &d = cx.d;
         const int N = d.N, keep = d.keep, L = d.L, M = d.M, lane = w.lane();
@@ -586,7 +616,8 @@ struct Kp2 {
         const int Mst = M;
         double *fcol = s.fac() + lane;
         double *tr = s.tr();
-        const int *gxi = s.gxi(), *gui = s.gui();
+        const auto gxi = s.gxi();
+        const int *gui = s.gui();
         const int e = lane * L, lo = cx.lo, sp = lo - 3;
         const bool has_int = act && cx.cnt > 0 && e < N - 1;
         const bool has_right = act && (lane + 1 < M);
@@ -595,7 +626,7 @@ struct Kp2 {
         double lN0 = 0, lN1 = 0, lN2 = 0, lds = 0, lq = 0;
         int pa1 = 0, pul = 0;
         if (has_int) {
-            lN0 = s.WD()[e + 1]; lN1 = s.WD()[N + e + 1]; lN2 = s.WD()[2 * N + e + 1];
+            lN0 = s.WD(0)[e + 1]; lN1 = s.WD(1)[e + 1]; lN2 = s.WD(2)[e + 1];
             lds = s.ds()[e]; lq = s.q10()[e];
             pa1 = gxi[e + 1]; pul = gui[e / keep];
         }
@@ -603,7 +634,7 @@ struct Kp2 {
             double ga_ = tr[sp], gb_ = tr[sp + 1], gc_ = tr[sp + 2];
             if (lane > 0) {
                 const int t = e - 1;
-                const double W0 = s.WD()[e], W1 = s.WD()[N + e], W2 = s.WD()[2 * N + e];
+                const double W0 = s.WD(0)[e], W1 = s.WD(1)[e], W2 = s.WD(2)[e];
                 const double dst = s.ds()[t], qt = s.q10()[t];
                 const int pt = gxi[t];
                 const double ya = tr[pt], yb = tr[pt + 1], yc = tr[pt + 2], yu = tr[gui[t / keep]];
@@ -621,36 +652,54 @@ struct Kp2 {
             R[27] = ga_; R[28] = gb_; R[29] = gc_;
         }
         w.sync();
+        // separator system: forward sweep (lane 0), g^ = Sinv g' (all lanes), backward sweep (lane 0)
         if (lane == 0) {
             double gp0 = s.red()[27], gp1 = s.red()[28], gp2 = s.red()[29];
-            for (int p = 1; p < M; ++p) {
-                double *Rp = s.red() + kRed2 * p;
-                const double g0 = Rp[27] - (Rp[18] * gp0 + Rp[19] * gp1 + Rp[20] * gp2);
-                const double g1 = Rp[28] - (Rp[21] * gp0 + Rp[22] * gp1 + Rp[23] * gp2);
-                const double g2 = Rp[29] - (Rp[24] * gp0 + Rp[25] * gp1 + Rp[26] * gp2);
-                Rp[27] = g0; Rp[28] = g1; Rp[29] = g2;
+            const double *Rp = s.red() + kRed2;
+#pragma unroll 2
+            for (int p = 1; p < M; ++p, Rp += kRed2) {
+                const double G0 = Rp[18], G1 = Rp[19], G2 = Rp[20], G3 = Rp[21], G4 = Rp[22], G5 = Rp[23],
+                             G6 = Rp[24], G7 = Rp[25], G8 = Rp[26];
+                const double g0 = Rp[27] - (G0 * gp0 + G1 * gp1 + G2 * gp2);
+                const double g1 = Rp[28] - (G3 * gp0 + G4 * gp1 + G5 * gp2);
+                const double g2 = Rp[29] - (G6 * gp0 + G7 * gp1 + G8 * gp2);
+                double *Rw = s.red() + kRed2 * p;
+                Rw[27] = g0; Rw[28] = g1; Rw[29] = g2;
                 gp0 = g0; gp1 = g1; gp2 = g2;
             }
-            double x0 = 0, x1 = 0, x2 = 0;
-            for (int p = M - 1; p >= 0; --p) {
-                const double *Rp = s.red() + kRed2 * p;
-                double t0 = Rp[27], t1 = Rp[28], t2 = Rp[29];
-                if (p + 1 < M) {
-                    t0 -= Rp[9] * x0 + Rp[10] * x1 + Rp[11] * x2;
-                    t1 -= Rp[12] * x0 + Rp[13] * x1 + Rp[14] * x2;
-                    t2 -= Rp[15] * x0 + Rp[16] * x1 + Rp[17] * x2;
-                }
-                x0 = Rp[0] * t0 + Rp[1] * t1 + Rp[2] * t2;
-                x1 = Rp[3] * t0 + Rp[4] * t1 + Rp[5] * t2;
-                x2 = Rp[6] * t0 + Rp[7] * t1 + Rp[8] * t2;
-                const int q = p * d.CS;
-                tr[q] = x0; tr[q + 1] = x1; tr[q + 2] = x2;
+        }
+        w.sync();
+        if (act) {
+            double *R = s.red() + kRed2 * lane;
+            const double t0 = R[27], t1 = R[28], t2 = R[29];
+            const double h0 = R[0] * t0 + R[1] * t1 + R[2] * t2;
+            const double h1 = R[3] * t0 + R[4] * t1 + R[5] * t2;
+            const double h2 = R[6] * t0 + R[7] * t1 + R[8] * t2;
+            R[27] = h0; R[28] = h1; R[29] = h2;
+        }
+        w.sync();
+        if (lane == 0) {
+            const double *Rp = s.red() + kRed2 * (M - 1);
+            double x0 = Rp[27], x1 = Rp[28], x2 = Rp[29];
+            int q = (M - 1) * d.CS;
+            tr[q] = x0; tr[q + 1] = x1; tr[q + 2] = x2;
+#pragma unroll 2
+            for (int p = M - 2; p >= 0; --p) {
+                Rp -= kRed2;
+                q -= d.CS;
+                const double H0 = Rp[9], H1 = Rp[10], H2 = Rp[11], H3 = Rp[12], H4 = Rp[13], H5 = Rp[14],
+                             H6 = Rp[15], H7 = Rp[16], H8 = Rp[17];
+                const double y0 = Rp[27] - (H0 * x0 + H1 * x1 + H2 * x2);
+                const double y1 = Rp[28] - (H3 * x0 + H4 * x1 + H5 * x2);
+                const double y2 = Rp[29] - (H6 * x0 + H7 * x1 + H8 * x2);
+                tr[q] = y0; tr[q + 1] = y1; tr[q + 2] = y2;
+                x0 = y0; x1 = y1; x2 = y2;
             }
         }
         w.sync();
         if (act) {
             double *lcol = s.lsc() + lane;
-#pragma unroll 1
+#pragma unroll
             for (int k = 0; k < IMAX; ++k) lcol[k * Mst] = 0.0;
             if (has_int) {
                 const double xa = tr[sp], xb = tr[sp + 1], xc = tr[sp + 2];
@@ -662,7 +711,7 @@ struct Kp2 {
             }
             if (has_right) {
                 const int e2 = e + L, t = e2 - 1;
-                const double W0 = s.WD()[e2], W1 = s.WD()[N + e2], W2 = s.WD()[2 * N + e2];
+                const double W0 = s.WD(0)[e2], W1 = s.WD(1)[e2], W2 = s.WD(2)[e2];
                 const double dst = s.ds()[t], qt = s.q10()[t];
                 const int sq = sp + d.CS;
                 const double xa = tr[sq], xb = tr[sq + 1], xc = tr[sq + 2];
@@ -673,7 +722,7 @@ struct Kp2 {
                 lcol[kur * Mst] += W2 * dst * xc;
             }
             local_solve(lcol, Mst, fcol, Mst);
-#pragma unroll 4
+#pragma unroll
             for (int k = 0; k < IMAX; ++k) tr[lo + k] += lcol[k * Mst];
         }
         w.sync();
@@ -681,10 +730,10 @@ struct Kp2 {
 #undef PQP_F
 
     // The 11 row values (A x)_r of station i for a vector in padded order (vr) + slack (vs).
-    PQP_DEV static KpRows apply_A(const Ctx &cx, int i, const double *vr, const double *vs) {
+    PQP_DEV static KpRows apply_A(const Ctx &cx, int i, const double *vr, const Fld vs) {
         const Smem &s = cx.s;
         const DevParams &pm = *cx.pm;
-        const int *gxi = s.gxi();
+        const auto gxi = s.gxi();
         const int ga = gxi[i];
         const double a = vr[ga], b = vr[ga + 1], cc = vr[ga + 2], sl = vs[i];
         KpRows r;
@@ -717,7 +766,7 @@ struct Kp2 {
         rc = -o.D2 + o.KB;
         rs = o.SB - o.S4m + o.S4p - o.S2m + o.S2p;
         if (i < N - 1) {
-            const double n0 = s.gD()[i + 1], n1 = s.gD()[N + i + 1], n2 = s.gD()[2 * N + i + 1];
+            const double n0 = s.gD(0)[i + 1], n1 = s.gD(1)[i + 1], n2 = s.gD(2)[i + 1];
             const double dsi = s.ds()[i];
             ra += n0 + s.q10()[i] * n1;
             rb += dsi * n0 + n1;
@@ -733,9 +782,9 @@ struct Kp2 {
     }
 
     // ---- the whole per-path solve ----------------------------------------------------------------
-    PQP_DEV static void solve_path(Warp &w, const DevParams &prm, const BatchView &bv, int prob, double *smem,
+    PQP_DEV static void solve_path(const Cta &c, const DevParams &prm, const BatchView &bv, int prob, double *smem,
                                    size_t smem_cap) {
-        const int lane = w.lane();
+        const int lane = c.lane(), tid = c.tid(), nt = c.nthreads();
         const int N = bv.n_points[prob];
         const int off = bv.offsets[prob];
         const pqp_state *ref = bv.ref + off;
@@ -761,11 +810,11 @@ struct Kp2 {
         if (!bad && (!fits(d) || smem_doubles(d) > smem_cap || !bv.workspace)) bad = 1;
         const double qnan = nan("");
         if (bad) {
-            if (lane == 0) {
+            if (tid == 0) {
                 bv.status[prob] = PQP_INVALID_PROBLEM;
                 if (bv.iters) bv.iters[prob] = 0;
             }
-            for (int i = lane; i < N; i += 32) {
+            for (int i = tid; i < N; i += nt) {
                 out[i].x = out[i].y = out[i].z = out[i].k = out[i].s = qnan;
                 out[i].v = out[i].a = 0.0;
                 if (bv.out_frenet) {
@@ -776,7 +825,7 @@ struct Kp2 {
             return;
         }
         Smem &s = cx.s;
-        s.base = smem; s.N = N; s.ch = d.ch; s.nv = d.nv; s.M = d.M;
+        s.base = smem; s.N = N; s.ch = d.ch; s.nv = d.nv; s.M = d.M; s.R = (N + 31) / 32;
         cx.ws = bv.workspace + (size_t)off * 16 + (size_t)prob * kWsPerPath;
         const int ch = d.ch;
         const DevParams &pm = prm;
@@ -796,11 +845,11 @@ struct Kp2 {
         // ---- index tables (padded chunk order) and this lane's interior
         {
             const KpDims a = kp_dims(N, keep);
-            for (int i = lane; i < N; i += 32) {
+            for (int i = tid; i < N; i += nt) {
                 const int p = i / d.L;
                 s.gxi()[i] = p * d.CS + (kp_gx(a, i) - kp_gx(a, p * d.L));
             }
-            for (int j = lane; j < ch; j += 32) {
+            for (int j = tid; j < ch; j += nt) {
                 int home = j * keep + d.h;
                 if (home > N - 1) home = N - 1;
                 const int p = home / d.L;
@@ -808,7 +857,7 @@ struct Kp2 {
             }
             cx.lo = 3;
             cx.cnt = 0;
-            if (lane < d.M) {
+            if (c.wid == 0 && lane < d.M) {
                 const int g0 = kp_gx(a, lane * d.L);
                 const int g1 = (lane + 1 < d.M) ? kp_gx(a, (lane + 1) * d.L) : a.nred;
                 cx.lo = lane * d.CS + 3;
@@ -817,7 +866,7 @@ struct Kp2 {
         }
         int invalid = (cx.cnt > IMAX);
         // ---- per-station coefficients (setConstraintMatrix :84-98, :166-187)
-        for (int i = lane; i < N; i += 32) {
+        for (int i = tid; i < N; i += nt) {
             const double kap = ref[i].k;
             if (i < N - 1) {
                 const double dsv = ref[i + 1].s - ref[i].s;
@@ -838,47 +887,48 @@ struct Kp2 {
                 invalid = 1;
         }
         if (!(0.0 <= pm.margin) || !(-pm.kmax <= pm.kmax) || !(cx.lEH <= cx.uEH)) invalid = 1;
-        invalid = w.any(invalid);
-        w.sync();
+        invalid = c.any(invalid);
+        c.sync();
 
         int status = PQP_UNSOLVED;
         int iter = 0;
         if (invalid) {
             status = PQP_INVALID_PROBLEM;
         } else {
-            scale(w, cx);
+            scale(c, cx);
             // cold start: OSQP's first iteration from zero leaves x = 0, v = 0 (see pqp_kp_core.cuh)
-            for (int g = lane; g < d.nv; g += 32) { s.xr()[g] = 0.0; s.tr()[g] = 0.0; }
-            for (int i = lane; i < N; i += 32) {
+            for (int g = tid; g < d.nv; g += nt) { s.xr()[g] = 0.0; s.tr()[g] = 0.0; }
+            for (int i = tid; i < N; i += nt) {
                 s.xs()[i] = 0.0;
-                s.vD()[i] = s.vD()[N + i] = s.vD()[2 * N + i] = 0.0;
+                s.vD(0)[i] = s.vD(1)[i] = s.vD(2)[i] = 0.0;
                 s.vKB()[i] = s.vSB()[i] = s.vH1()[i] = s.vH3()[i] = 0.0;
                 s.vS4m()[i] = s.vS4p()[i] = s.vS2m()[i] = s.vS2p()[i] = 0.0;
             }
-            for (int j = lane; j < ch; j += 32) s.vUB()[j] = 0.0;
-            if (lane == 0) s.vEnd()[0] = s.vEnd()[1] = 0.0;
+            for (int j = tid; j < ch; j += nt) s.vUB()[j] = 0.0;
+            if (tid == 0) s.vEnd()[0] = s.vEnd()[1] = 0.0;
             cx.rho = fmin(fmax(pm.rho, kRhoMin), kRhoMax);
-            w.sync();
-            weights(w, cx);
-            if (!factor(w, cx)) status = PQP_NON_CVX;
+            c.sync();
+            weights(c, cx);
+            if (!factor(c, cx)) status = PQP_NON_CVX;
             const double alpha = pm.alpha;
             double pri_res = 0, dua_res = 0, pri_nrm = 0, dua_nrm = 0;
-            const int *gxi = s.gxi(), *gui = s.gui();
+            const auto gxi = s.gxi();
+        const int *gui = s.gui();
             iter = 1;
             while (status == PQP_UNSOLVED && iter < pm.max_iter) {
                 ++iter;
                 // ---- (a) rhs = sigma_v x + A' W (2 clamp(v) - v)
-                for (int i = lane; i < N; i += 32) {
+                for (int i = tid; i < N; i += nt) {
                     double b0, b1, b2;
                     dyn_bounds(cx, i, b0, b1, b2);
-                    s.gD()[i] = s.WD()[i] * (2.0 * b0 - s.vD()[i]);
-                    s.gD()[N + i] = s.WD()[N + i] * (2.0 * b1 - s.vD()[N + i]);
-                    s.gD()[2 * N + i] = s.WD()[2 * N + i] * (2.0 * b2 - s.vD()[2 * N + i]);
+                    s.gD(0)[i] = s.WD(0)[i] * (2.0 * b0 - s.vD(0)[i]);
+                    s.gD(1)[i] = s.WD(1)[i] * (2.0 * b1 - s.vD(1)[i]);
+                    s.gD(2)[i] = s.WD(2)[i] * (2.0 * b2 - s.vD(2)[i]);
                 }
-                w.sync();
-                for (int i = lane; i < N; i += 32) {
+                c.sync();
+                for (int i = tid; i < N; i += nt) {
                     KpRows g;
-                    g.D0 = s.gD()[i]; g.D1 = s.gD()[N + i]; g.D2 = s.gD()[2 * N + i];
+                    g.D0 = s.gD(0)[i]; g.D1 = s.gD(1)[i]; g.D2 = s.gD(2)[i];
                     double v;
                     v = s.vKB()[i]; g.KB = s.WKB()[i] * (2.0 * clampd(v, -pm.kmax, pm.kmax) - v);
                     v = s.vSB()[i]; g.SB = s.WSB()[i] * (2.0 * clampd(v, 0.0, pm.margin) - v);
@@ -902,26 +952,26 @@ struct Kp2 {
                     s.tr()[ga + 2] = s.sgr()[ga + 2] * s.xr()[ga + 2] + rc;
                     s.ts()[i] = (s.sgs()[i] * s.xs()[i] + rs) * s.ksinv()[i];   // slack decouples: final
                 }
-                for (int j = lane; j < ch; j += 32) {
+                for (int j = tid; j < ch; j += nt) {
                     const int gu = gui[j];
                     const double v = s.vUB()[j];
                     double acc = s.sgr()[gu] * s.xr()[gu] + s.WUB()[j] * (2.0 * clampd(v, -kOsqpInfty, kOsqpInfty) - v);
                     int t1 = j * keep + keep - 1;
                     if (t1 > N - 2) t1 = N - 2;
-                    for (int t = j * keep; t <= t1; ++t) acc += s.ds()[t] * s.gD()[2 * N + t + 1];
+                    for (int t = j * keep; t <= t1; ++t) acc += s.ds()[t] * s.gD(2)[t + 1];
                     s.tr()[gu] = acc;
                 }
-                w.sync();
+                c.sync();
                 // ---- (b) reduced KKT solve
-                solve(w, cx);
+                solve(c, cx);
                 // ---- (c) v += alpha (A xt - clamp(v)),  x = alpha xt + (1 - alpha) x
-                for (int i = lane; i < N; i += 32) {
+                for (int i = tid; i < N; i += nt) {
                     const KpRows zt = apply_A(cx, i, s.tr(), s.ts());
                     double b0, b1, b2, v;
                     dyn_bounds(cx, i, b0, b1, b2);
-                    s.vD()[i] += alpha * (zt.D0 - b0);
-                    s.vD()[N + i] += alpha * (zt.D1 - b1);
-                    s.vD()[2 * N + i] += alpha * (zt.D2 - b2);
+                    s.vD(0)[i] += alpha * (zt.D0 - b0);
+                    s.vD(1)[i] += alpha * (zt.D1 - b1);
+                    s.vD(2)[i] += alpha * (zt.D2 - b2);
                     v = s.vKB()[i]; s.vKB()[i] = v + alpha * (zt.KB - clampd(v, -pm.kmax, pm.kmax));
                     v = s.vSB()[i]; s.vSB()[i] = v + alpha * (zt.SB - clampd(v, 0.0, pm.margin));
                     v = s.vH1()[i]; s.vH1()[i] = v + alpha * (zt.H1 - clampd(v, s.lH1()[i], s.uH1()[i]));
@@ -936,14 +986,14 @@ struct Kp2 {
                         v = s.vEnd()[1]; s.vEnd()[1] = v + alpha * (s.tr()[ga + 1] - clampd(v, cx.lEH, cx.uEH));
                     }
                 }
-                for (int j = lane; j < ch; j += 32) {
+                for (int j = tid; j < ch; j += nt) {
                     const double v = s.vUB()[j];
                     s.vUB()[j] = v + alpha * (s.tr()[gui[j]] - clampd(v, -kOsqpInfty, kOsqpInfty));
                 }
-                w.sync();
-                for (int g = lane; g < d.nv; g += 32) s.xr()[g] = alpha * s.tr()[g] + (1.0 - alpha) * s.xr()[g];
-                for (int i = lane; i < N; i += 32) s.xs()[i] = alpha * s.ts()[i] + (1.0 - alpha) * s.xs()[i];
-                w.sync();
+                c.sync();
+                for (int g = tid; g < d.nv; g += nt) s.xr()[g] = alpha * s.tr()[g] + (1.0 - alpha) * s.xr()[g];
+                for (int i = tid; i < N; i += nt) s.xs()[i] = alpha * s.ts()[i] + (1.0 - alpha) * s.xs()[i];
+                c.sync();
                 // ---- (d) residuals, termination, adaptive rho
                 const bool can_check = pm.check_termination && (iter % pm.check_termination == 0);
                 const bool can_adapt = pm.adaptive_rho && pm.adaptive_rho_interval &&
@@ -961,13 +1011,13 @@ struct Kp2 {
         naxs = fmax(naxs, e_ * fabs(ax_));                                           \
     }
 #define PQP_DUAL(V, LO, HI, WW) ((WW) * ((V) - clampd((V), (LO), (HI))) * cinv)
-                    for (int i = lane; i < N; i += 32) {
+                    for (int i = tid; i < N; i += nt) {
                         const KpRows ax = apply_A(cx, i, s.xr(), s.xs());
                         double b0, b1, b2;
                         dyn_bounds(cx, i, b0, b1, b2);
-                        PQP_ROW(ax.D0, s.vD()[i], b0, b0, E[i])
-                        PQP_ROW(ax.D1, s.vD()[N + i], b1, b1, E[N + i])
-                        PQP_ROW(ax.D2, s.vD()[2 * N + i], b2, b2, E[2 * N + i])
+                        PQP_ROW(ax.D0, s.vD(0)[i], b0, b0, E[i])
+                        PQP_ROW(ax.D1, s.vD(1)[i], b1, b1, E[N + i])
+                        PQP_ROW(ax.D2, s.vD(2)[i], b2, b2, E[2 * N + i])
                         PQP_ROW(ax.KB, s.vKB()[i], -pm.kmax, pm.kmax, E[3 * N + i])
                         PQP_ROW(ax.SB, s.vSB()[i], 0.0, pm.margin, E[4 * N + i])
                         PQP_ROW(ax.H1, s.vH1()[i], s.lH1()[i], s.uH1()[i], E[5 * N + i])
@@ -976,18 +1026,18 @@ struct Kp2 {
                         PQP_ROW(ax.S4p, s.vS4p()[i], s.lS4p()[i], kOsqpInfty, E[7 * N + i])
                         PQP_ROW(ax.S2m, s.vS2m()[i], -kOsqpInfty, s.uS2m()[i], E[8 * N + i])
                         PQP_ROW(ax.S2p, s.vS2p()[i], s.lS2p()[i], kOsqpInfty, E[8 * N + i])
-                        s.gD()[i] = PQP_DUAL(s.vD()[i], b0, b0, s.WD()[i]);
-                        s.gD()[N + i] = PQP_DUAL(s.vD()[N + i], b1, b1, s.WD()[N + i]);
-                        s.gD()[2 * N + i] = PQP_DUAL(s.vD()[2 * N + i], b2, b2, s.WD()[2 * N + i]);
+                        s.gD(0)[i] = PQP_DUAL(s.vD(0)[i], b0, b0, s.WD(0)[i]);
+                        s.gD(1)[i] = PQP_DUAL(s.vD(1)[i], b1, b1, s.WD(1)[i]);
+                        s.gD(2)[i] = PQP_DUAL(s.vD(2)[i], b2, b2, s.WD(2)[i]);
                         if (i == N - 1) {
                             const int ga = gxi[i];
                             PQP_ROW(s.xr()[ga], s.vEnd()[0], -1.0, 1.0, E[9 * N + ch])
                             PQP_ROW(s.xr()[ga + 1], s.vEnd()[1], cx.lEH, cx.uEH, E[9 * N + ch + 1])
                         }
                     }
-                    for (int j = lane; j < ch; j += 32)
+                    for (int j = tid; j < ch; j += nt)
                         PQP_ROW(s.xr()[gui[j]], s.vUB()[j], -kOsqpInfty, kOsqpInfty, E[9 * N + j])
-                    w.sync();
+                    c.sync();
                     double dr = 0, npx = 0, naty = 0, drs = 0, npxs = 0, natys = 0;
                     const double cc = cx.c;
 #define PQP_VAR(PX, ATY, DD)                                                          \
@@ -997,10 +1047,10 @@ struct Kp2 {
         drs = fmax(drs, cd_ * fabs(r_)); npxs = fmax(npxs, cd_ * fabs(px_));          \
         natys = fmax(natys, cd_ * fabs(aty_));                                        \
     }
-                    for (int i = lane; i < N; i += 32) {
+                    for (int i = tid; i < N; i += nt) {
                         const int ga = gxi[i];
                         KpRows y;
-                        y.D0 = s.gD()[i]; y.D1 = s.gD()[N + i]; y.D2 = s.gD()[2 * N + i];
+                        y.D0 = s.gD(0)[i]; y.D1 = s.gD(1)[i]; y.D2 = s.gD(2)[i];
                         y.KB = PQP_DUAL(s.vKB()[i], -pm.kmax, pm.kmax, s.WKB()[i]);
                         y.SB = PQP_DUAL(s.vSB()[i], 0.0, pm.margin, s.WSB()[i]);
                         y.H1 = PQP_DUAL(s.vH1()[i], s.lH1()[i], s.uH1()[i], s.WH1()[i]);
@@ -1021,22 +1071,22 @@ struct Kp2 {
                         PQP_VAR(pm.w_c * s.xr()[ga + 2], rc, Dr[ga + 2])
                         PQP_VAR(pm.w_s * s.xs()[i], rs, Dsl[i])
                     }
-                    for (int j = lane; j < ch; j += 32) {
+                    for (int j = tid; j < ch; j += nt) {
                         const int gu = gui[j];
                         double aty = PQP_DUAL(s.vUB()[j], -kOsqpInfty, kOsqpInfty, s.WUB()[j]);
                         int t1 = j * keep + keep - 1;
                         if (t1 > N - 2) t1 = N - 2;
-                        for (int t = j * keep; t <= t1; ++t) aty += s.ds()[t] * s.gD()[2 * N + t + 1];
+                        for (int t = j * keep; t <= t1; ++t) aty += s.ds()[t] * s.gD(2)[t + 1];
                         PQP_VAR((keep * pm.w_cr) * s.xr()[gu], aty, Dr[gu])
                     }
 #undef PQP_ROW
 #undef PQP_DUAL
 #undef PQP_VAR
-                    pr = w.max(pr); nz = w.max(nz); nax = w.max(nax);
-                    prs = w.max(prs); nzs = w.max(nzs); naxs = w.max(naxs);
-                    dr = w.max(dr); npx = w.max(npx); naty = w.max(naty);
-                    drs = w.max(drs); npxs = w.max(npxs); natys = w.max(natys);
-                    w.sync();
+                    pr = c.max(pr); nz = c.max(nz); nax = c.max(nax);
+                    prs = c.max(prs); nzs = c.max(nzs); naxs = c.max(naxs);
+                    dr = c.max(dr); npx = c.max(npx); naty = c.max(naty);
+                    drs = c.max(drs); npxs = c.max(npxs); natys = c.max(natys);
+                    c.sync();
                     pri_res = pr; dua_res = dr;
                     pri_nrm = fmax(nz, nax); dua_nrm = fmax(npx, naty);
                     if (can_check || iter == pm.max_iter) {
@@ -1053,12 +1103,12 @@ struct Kp2 {
                         rho_new = fmin(fmax(rho_new, kRhoMin), kRhoMax);
                         if (rho_new > rho * pm.adaptive_rho_tolerance || rho_new < rho / pm.adaptive_rho_tolerance) {
                             const double ratio = rho / rho_new;
-                            for (int i = lane; i < N; i += 32) {
+                            for (int i = tid; i < N; i += nt) {
                                 double b0, b1, b2, v, z;
                                 dyn_bounds(cx, i, b0, b1, b2);
-                                s.vD()[i] = b0 + (s.vD()[i] - b0) * ratio;
-                                s.vD()[N + i] = b1 + (s.vD()[N + i] - b1) * ratio;
-                                s.vD()[2 * N + i] = b2 + (s.vD()[2 * N + i] - b2) * ratio;
+                                s.vD(0)[i] = b0 + (s.vD(0)[i] - b0) * ratio;
+                                s.vD(1)[i] = b1 + (s.vD(1)[i] - b1) * ratio;
+                                s.vD(2)[i] = b2 + (s.vD(2)[i] - b2) * ratio;
 #define PQP_RESC(V, LO, HI) v = (V); z = clampd(v, (LO), (HI)); (V) = z + (v - z) * ratio;
                                 PQP_RESC(s.vKB()[i], -pm.kmax, pm.kmax)
                                 PQP_RESC(s.vSB()[i], 0.0, pm.margin)
@@ -1075,9 +1125,9 @@ struct Kp2 {
 #undef PQP_RESC
                             }
                             cx.rho = rho_new;
-                            w.sync();
-                            weights(w, cx);
-                            if (!factor(w, cx)) status = PQP_NON_CVX;
+                            c.sync();
+                            weights(c, cx);
+                            if (!factor(c, cx)) status = PQP_NON_CVX;
                         }
                     }
                 }
@@ -1093,9 +1143,9 @@ struct Kp2 {
         // ---- epilogue: getOptimizedPath, solver_kp_as_input.cpp:26-43
         const bool has_sol = (status == PQP_SOLVED || status == PQP_SOLVED_INACCURATE || status == PQP_MAX_ITER_REACHED);
         double *px = s.tr(), *py = s.tr() + N;   // nv >= 3N: room for x and y of every station
-        double *seg = s.ts();
-        w.sync();
-        for (int i = lane; i < N; i += 32) {
+        const Fld seg = s.ts();
+        c.sync();
+        for (int i = tid; i < N; i += nt) {
             double ey = qnan, ephi = qnan, kk = qnan;
             if (has_sol) {
                 const int ga = s.gxi()[i];
@@ -1114,8 +1164,8 @@ struct Kp2 {
                 f[0] = ey; f[1] = ephi; f[2] = kk;
             }
         }
-        w.sync();
-        for (int i = lane; i < N; i += 32) {
+        c.sync();
+        for (int i = tid; i < N; i += nt) {
             double sg = 0.0;
             if (i > 0) {
                 const double dx = px[i] - px[i - 1], dy = py[i] - py[i - 1];
@@ -1123,8 +1173,8 @@ struct Kp2 {
             }
             seg[i] = sg;
         }
-        w.sync();
-        if (lane == 0) {
+        c.sync();
+        if (tid == 0) {
             double acc = 0.0;  // sequential: same association order as the reference's running sum
             for (int i = 0; i < N; ++i) {
                 acc += seg[i];
@@ -1133,7 +1183,7 @@ struct Kp2 {
             bv.status[prob] = status;
             if (bv.iters) bv.iters[prob] = iter;
         }
-        w.sync();
+        c.sync();
     }
 };
 

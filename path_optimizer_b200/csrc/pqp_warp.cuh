@@ -15,10 +15,14 @@
 #include <stdint.h>
 #define PQP_DEV inline
 namespace pqp {
-struct EmuShared {
+struct EmuShared {            // one per emulated warp
     pthread_barrier_t bar;
     double slot_d[32];
     int slot_i[32];
+};
+struct EmuCta {               // one per emulated CTA
+    pthread_barrier_t bar;
+    int nthreads;
 };
 struct Warp {
     int lane_;
@@ -70,6 +74,10 @@ struct Warp {
         return r;
     }
 };
+struct CtaSync {
+    EmuCta *cta;
+    void sync() const { pthread_barrier_wait(&cta->bar); }
+};
 }  // namespace pqp
 #else
 #include <cuda_runtime.h>
@@ -92,5 +100,56 @@ struct Warp {
     }
     PQP_DEV int any(int v) const { return __any_sync(0xffffffffu, v); }
 };
+struct CtaSync {
+    PQP_DEV void sync() const { __syncthreads(); }
+};
 }  // namespace pqp
 #endif
+
+namespace pqp {
+// A CTA of NW warps working on ONE path.  Block-wide reductions go through a small shared scratch
+// (NW doubles) in a fixed order, so results are deterministic and identical on every thread.
+struct Cta {
+    Warp w;
+    CtaSync cs;
+    int wid, nw;
+    double *scratch;   // >= 32 doubles of shared memory
+    PQP_DEV int lane() const { return w.lane(); }
+    PQP_DEV int tid() const { return wid * 32 + w.lane(); }
+    PQP_DEV int nthreads() const { return nw * 32; }
+    PQP_DEV void sync() const {
+        if (nw == 1) w.sync();
+        else cs.sync();
+    }
+    PQP_DEV double max(double v) const {
+        v = w.max(v);
+        if (nw == 1) return v;
+        if (w.lane() == 0) scratch[wid] = v;
+        cs.sync();
+        double r = scratch[0];
+        for (int k = 1; k < nw; ++k) r = fmax(r, scratch[k]);
+        cs.sync();
+        return r;
+    }
+    PQP_DEV double sum(double v) const {
+        v = w.sum(v);
+        if (nw == 1) return v;
+        if (w.lane() == 0) scratch[wid] = v;
+        cs.sync();
+        double r = scratch[0];
+        for (int k = 1; k < nw; ++k) r += scratch[k];
+        cs.sync();
+        return r;
+    }
+    PQP_DEV int any(int v) const {
+        v = w.any(v);
+        if (nw == 1) return v;
+        if (w.lane() == 0) scratch[wid] = v ? 1.0 : 0.0;
+        cs.sync();
+        int r = 0;
+        for (int k = 0; k < nw; ++k) r |= (scratch[k] != 0.0);
+        cs.sync();
+        return r;
+    }
+};
+}  // namespace pqp

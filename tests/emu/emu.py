@@ -33,13 +33,13 @@ def lib():
     global _lib
     if _lib is None:
         _lib = C.CDLL(build())
-        _lib.kp_emu_solve_batch.argtypes = [C.POINTER(Params), C.c_int] + [C.c_void_p] * 10 + [C.c_int, C.c_int]
+        _lib.kp_emu_solve_batch.argtypes = [C.POINTER(Params), C.c_int] + [C.c_void_p] * 10 + [C.c_int, C.c_int, C.c_int]
         _lib.kp_emu_solve_batch.restype = C.c_int
     return _lib
 
 
-def solve_batch(params, batch, smem_bytes=227 * 1024, variant=0):
-    """variant 0 = generic core (pqp_kp_core.cuh); 1..4 = Kp2<17,6>, <10,7>, <27,7>, <48,7>."""
+def solve_batch(params, batch, smem_bytes=227 * 1024, variant=0, nwarps=4):
+    """variant 0 = generic core (pqp_kp_core.cuh); 1..4 = Kp2<17,6>, <10,7>, <27,7>, <49,7> run by a CTA of `nwarps` warps."""
     B = len(batch["n_points"])
     total = int(batch["offsets"][-1])
     ref = np.ascontiguousarray(batch["ref"], dtype=STATE_DTYPE)
@@ -50,5 +50,5 @@ def solve_batch(params, batch, smem_bytes=227 * 1024, variant=0):
     iters = np.zeros(B, dtype=np.int32)
     lib().kp_emu_solve_batch(C.byref(params), B, ptr(batch["n_points"]), ptr(batch["offsets"]), ptr(ref),
                              ptr(bounds), ptr(batch["x0"]), ptr(batch["end_heading"]), ptr(out),
-                             ptr(frenet), ptr(status), ptr(iters), smem_bytes, variant)
+                             ptr(frenet), ptr(status), ptr(iters), smem_bytes, variant, nwarps)
     return dict(states=out, frenet=frenet, status=status, iters=iters)

@@ -12,23 +12,27 @@
 namespace {
 struct LaneArgs {
     pqp::EmuShared *sh;
-    int lane;
+    pqp::EmuCta *cta;
+    int lane, wid, nw;
     const pqp::DevParams *prm;
     const pqp::BatchView *bv;
     int prob;
     double *smem;
     size_t smem_doubles;
-    int variant;  // 0: generic v1 core; 1: v2 <17,6>; 2: v2 <10,7>; 3: v2 <27,7>; 4: v2 <48,7>
+    int variant;  // 0: generic v1 core; 1: v2 <17,6>; 2: v2 <10,7>; 3: v2 <27,7>; 4: v2 <49,7>
 };
 void *lane_main(void *p) {
     LaneArgs *a = (LaneArgs *)p;
     pqp::Warp w{a->lane, a->sh};
+    pqp::Cta c{w, pqp::CtaSync{a->cta}, a->wid, a->nw, a->smem};
+    double *sm = a->smem + 32;                 // first 32 doubles: CTA reduction scratch
+    const size_t cap = a->smem_doubles - 32;
     switch (a->variant) {
-    case 1: pqp::Kp2<17, 6>::solve_path(w, *a->prm, *a->bv, a->prob, a->smem, a->smem_doubles); break;
-    case 2: pqp::Kp2<10, 7>::solve_path(w, *a->prm, *a->bv, a->prob, a->smem, a->smem_doubles); break;
-    case 3: pqp::Kp2<27, 7>::solve_path(w, *a->prm, *a->bv, a->prob, a->smem, a->smem_doubles); break;
-    case 4: pqp::Kp2<48, 7>::solve_path(w, *a->prm, *a->bv, a->prob, a->smem, a->smem_doubles); break;
-    default: pqp::kp_solve_path(w, *a->prm, *a->bv, a->prob, a->smem, a->smem_doubles);
+    case 1: pqp::Kp2<17, 6>::solve_path(c, *a->prm, *a->bv, a->prob, sm, cap); break;
+    case 2: pqp::Kp2<10, 7>::solve_path(c, *a->prm, *a->bv, a->prob, sm, cap); break;
+    case 3: pqp::Kp2<27, 7>::solve_path(c, *a->prm, *a->bv, a->prob, sm, cap); break;
+    case 4: pqp::Kp2<49, 7>::solve_path(c, *a->prm, *a->bv, a->prob, sm, cap); break;
+    default: pqp::kp_solve_path(w, *a->prm, *a->bv, a->prob, sm, cap);   // generic core: one warp
     }
     return nullptr;
 }
@@ -38,7 +42,8 @@ extern "C" int kp_emu_solve_batch(const pqp_params *params, int batch, const int
                                   const int32_t *offsets, const pqp_state *ref,
                                   const pqp_station_bounds *bounds, const double *x0,
                                   const double *end_heading, pqp_state *out_states, double *out_frenet,
-                                  int32_t *status, int32_t *iters, int smem_bytes, int variant) {
+                                  int32_t *status, int32_t *iters, int smem_bytes, int variant, int nwarps) {
+    if (variant == 0 || nwarps < 1) nwarps = 1;
     pqp::DevParams prm = pqp::dev_params_from(*params);
     pqp::BatchView bv;
     bv.batch = batch; bv.n_points = n_points; bv.offsets = offsets; bv.ref = ref; bv.bounds = bounds;
@@ -52,16 +57,21 @@ extern "C" int kp_emu_solve_batch(const pqp_params *params, int batch, const int
     for (int prob = 0; prob < batch; ++prob) {
         // poison the scratch so that reads of uninitialised shared memory show up as NaN
         for (size_t k = 0; k < smem_doubles; ++k) smem[k] = nan("");
-        pqp::EmuShared sh;
-        pthread_barrier_init(&sh.bar, nullptr, 32);
-        pthread_t th[32];
-        LaneArgs args[32];
-        for (int l = 0; l < 32; ++l) {
-            args[l] = LaneArgs{&sh, l, &prm, &bv, prob, smem, smem_doubles, variant};
-            pthread_create(&th[l], nullptr, lane_main, &args[l]);
+        const int nth = 32 * nwarps;
+        pqp::EmuShared sh[8];
+        pqp::EmuCta cta;
+        cta.nthreads = nth;
+        pthread_barrier_init(&cta.bar, nullptr, nth);
+        for (int k = 0; k < nwarps; ++k) pthread_barrier_init(&sh[k].bar, nullptr, 32);
+        pthread_t th[256];
+        LaneArgs args[256];
+        for (int t = 0; t < nth; ++t) {
+            args[t] = LaneArgs{&sh[t / 32], &cta, t % 32, t / 32, nwarps, &prm, &bv, prob, smem, smem_doubles, variant};
+            pthread_create(&th[t], nullptr, lane_main, &args[t]);
         }
-        for (int l = 0; l < 32; ++l) pthread_join(th[l], nullptr);
-        pthread_barrier_destroy(&sh.bar);
+        for (int t = 0; t < nth; ++t) pthread_join(th[t], nullptr);
+        for (int k = 0; k < nwarps; ++k) pthread_barrier_destroy(&sh[k].bar);
+        pthread_barrier_destroy(&cta.bar);
     }
     free(smem);
     free(bv.workspace);
