@@ -10,7 +10,7 @@
 #include <new>
 #include <vector>
 
-#include "pqp_kp_core2.cuh"
+#include "pqp_kp_core3.cuh"
 
 namespace {
 
@@ -55,6 +55,18 @@ pqp_kp2_solve_kernel(const __grid_constant__ pqp::DevParams prm, const __grid_co
     pqp::Kp2<IMAX, BW>::solve_path(c, prm, bv, prob, pqp_smem + 32, (size_t)smem_doubles - 32);
 }
 
+// Thread-per-station kernels (pqp_kp_core3.cuh): NW warps per path, N <= 32*NW stations.
+template <int IMAX, int BW, int NW>
+__global__ void __launch_bounds__(NW * 32, NW <= 4 ? 3 : 1)
+pqp_kp3_solve_kernel(const __grid_constant__ pqp::DevParams prm, const __grid_constant__ pqp::BatchView bv,
+                     const int32_t *__restrict__ order, int smem_doubles) {
+    extern __shared__ double pqp_smem[];
+    int prob = blockIdx.x;
+    if (order) prob = order[prob];
+    pqp::Cta c{pqp::Warp(), pqp::CtaSync(), (int)(threadIdx.x >> 5), NW, pqp_smem};
+    pqp::Kp3<IMAX, BW, NW>::solve_path(c, prm, bv, prob, pqp_smem + 32, (size_t)smem_doubles - 32);
+}
+
 // Shape classes.  keep_control_steps <= 4 (station spacing >= 0.24 m) maps onto one of the Kp2
 // instantiations; anything else runs on the generic kernel.
 struct Variant {
@@ -71,8 +83,14 @@ template <int IMAX, int BW> bool v_fits(int n, int keep) {
 }
 size_t g_smem(int n, int keep) { return pqp::kp_smem_doubles(pqp::kp_dims(n, keep)) * sizeof(double); }
 bool g_fits(int, int keep) { return keep <= 10; }
+template <int IMAX, int BW, int NW> size_t v3_smem(int n, int keep) {
+    return (32 + pqp::Kp3<IMAX, BW, NW>::smem_doubles(pqp::Kp3<IMAX, BW, NW>::dims(n, keep))) * sizeof(double);
+}
+template <int IMAX, int BW, int NW> bool v3_fits(int n, int keep) { return pqp::Kp3<IMAX, BW, NW>::fits(n, keep); }
+#define PQP_VARIANT3(I, B, W) {I, B, W * 32, (const void *)pqp_kp3_solve_kernel<I, B, W>, v3_smem<I, B, W>, v3_fits<I, B, W>}
 #define PQP_VARIANT(I, B) {I, B, kNW * 32, (const void *)pqp_kp2_solve_kernel<I, B>, v_smem<I, B>, v_fits<I, B>}
 const Variant kVariants[] = {
+    PQP_VARIANT3(17, 6, 4), PQP_VARIANT3(23, 7, 4), PQP_VARIANT3(27, 7, 4), PQP_VARIANT3(37, 7, 8),
     PQP_VARIANT(17, 6), PQP_VARIANT(10, 7), PQP_VARIANT(17, 7), PQP_VARIANT(27, 7), PQP_VARIANT(37, 7),
     PQP_VARIANT(49, 7),
     {0, kMaxBandGeneric, 32, (const void *)pqp_kp_solve_kernel, g_smem, g_fits},  // generic fallback (last)

@@ -223,6 +223,31 @@ struct Kp2 {
         for (int k = 0; k < IMAX; ++k) vec[k * vst] = y[k];
     }
 
+    // y = K_I^-1 r with separate input / output vectors (unit stride).
+    PQP_NOINLINE static void local_solve2(const double *in, double *outv, const double *fcol, int Mst) {
+        double y[IMAX];
+#pragma unroll
+        for (int k = 0; k < IMAX; ++k) y[k] = in[k];
+#pragma unroll
+        for (int k = 1; k < IMAX; ++k) {
+            double acc = y[k];
+#pragma unroll
+            for (int dd = BW; dd >= 1; --dd)
+                if (k - dd >= 0) acc -= PQP_F(k, dd) * y[k - dd];
+            y[k] = acc;
+        }
+#pragma unroll
+        for (int k = IMAX - 1; k >= 0; --k) {
+            double acc = y[k] * PQP_F(k, 0);
+#pragma unroll
+            for (int dd = BW; dd >= 1; --dd)
+                if (k + dd < IMAX) acc -= PQP_F(k + dd, dd) * y[k + dd];
+            y[k] = acc;
+        }
+#pragma unroll
+        for (int k = 0; k < IMAX; ++k) outv[k] = y[k];
+    }
+
     // ---- row weights for the current rho, from the workspace E ----------------------------------
     PQP_DEV static void weights(const Cta &c, Ctx &cx) {
         const Smem &s = cx.s;

@@ -1,0 +1,957 @@
+// pqp_kp_core3.cuh -- thread-per-station "KP" solver: the production kernel for N <= 32*NW stations.
+//
+// Same mathematics as pqp_kp_core.cuh / pqp_kp_core2.cuh (read their headers first).  A CTA of NW
+// warps solves one path; what changes is WHERE things live and HOW the reduced KKT is applied:
+//   * thread t owns station t: its 11 row values v, 9 row weights W, 8 bounds, transition
+//     coefficients, proximal terms and its slice (e_y, e_phi, kappa, s) of the iterate stay in
+//     REGISTERS for the whole solve (thread j < ch additionally owns held control u_j);
+//   * shared memory only holds what is exchanged: the rhs / x-tilde vector, the dynamics-row values a
+//     neighbouring station needs, and the factorisation;
+//   * reduced KKT, per (re)factorisation: lane p of warp 0 factors the interior after separator p
+//     (banded LDL'), 6M threads build the spikes T_p = K_I^-1 K[I, S_p | S_p+1], and the M x M
+//     block-tridiagonal Schur complement over the separators is inverted DENSELY (3M threads, one
+//     unit vector each).  Per ADMM iteration:
+//         g   = r_S - T' r_I                (3M threads, no dependency chain)
+//         y   = K_I^-1 r_I                  (warp 0, one banded solve per lane)   } concurrently
+//         x_S = Sinv g                      (3M threads of warps 1.., dense dot)  }
+//         x_I = y - T x_S                   (station threads)
+//     so the only serial chain left in an iteration is ONE interior substitution.
+//
+// Reference being replaced: src/solver/solver_kp_as_input.cpp:26-203 + the OSQP solve at
+// src/solver/solver.cpp:66-74.
+#pragma once
+#include "pqp_kp_core2.cuh"
+
+namespace pqp {
+
+struct Kp3Dims {
+    int N, keep, ch, h, L, M, I, CS, nv, bw, nS;
+};
+
+// separators every L stations with at most 17 of them (the dense separator inverse is (3M)^2)
+PQP_HD Kp3Dims kp3_dims_raw(int N, int keep) {
+    const KpDims a = kp_dims(N, keep);
+    Kp3Dims d;
+    d.N = N; d.keep = keep; d.ch = a.ch; d.h = a.h; d.bw = a.bw;
+    int L = keep * ((N - 1) / (17 * keep) + 1);   // smallest multiple of keep with (N-1)/L < 17
+    if (L < 2) L = 2;
+    d.L = L;
+    d.M = (N - 1) / L + 1;
+    d.I = 3 * (L - 1) + L / keep;
+    d.CS = d.I + 3;
+    d.nv = d.M * d.CS;
+    d.nS = 3 * d.M;
+    return d;
+}
+
+template <int IMAX, int BW, int NW>
+struct Kp3 {
+    static constexpr int kT = NW * 32;     // threads = max stations
+    using K2 = Kp2<IMAX, BW>;              // reuses the unrolled interior factor / solve
+
+    PQP_HD static Kp3Dims dims(int N, int keep) {
+        Kp3Dims d = kp3_dims_raw(N, keep);
+        d.CS = (IMAX + 3) | 1;
+        d.nv = d.M * d.CS;
+        return d;
+    }
+    PQP_HD static bool fits(int N, int keep) {
+        if (N < 2 || N > kT || keep < 1 || keep > 10) return false;
+        const Kp3Dims d = kp3_dims_raw(N, keep);
+        return d.I <= IMAX && d.bw <= BW && d.M <= 17;
+    }
+
+    // ---- shared memory (doubles) ---------------------------------------------------------------
+    struct Smem {
+        double *base;
+        int nv, M, nS, ch;
+        PQP_DEV double *tr() const { return base; }                       // rhs, then x-tilde  [nv]
+        PQP_DEV double *yv() const { return base + nv; }                  // K_I^-1 r_I         [nv]
+        PQP_DEV double *ex(int k) const { return base + 2 * nv + k * kT; }  // 6 exchange rows of kT
+        PQP_DEV double *dsS() const { return ex(6); }                     // ds per station     [kT]
+        PQP_DEV double *gS() const { return ex(7); }                      // separator rhs      [nS <= kT]
+        PQP_DEV double *fac() const { return ex(8); }                     // [IMAX*(BW+1)*M]
+        PQP_DEV double *T() const { return fac() + IMAX * (BW + 1) * M; } // spikes [(k*6+c)*M + p]
+        PQP_DEV double *Sinv() const { return T() + IMAX * 6 * M; }       // [nS*nS]
+        PQP_DEV double *red() const { return Sinv() + nS * nS; }          // [kRed2*M] + blocks [27*M]
+        PQP_DEV double *blk() const { return red() + kRed2 * M; }         // A|C|Off per chunk [27*M]
+        PQP_DEV double *cpl() const { return blk() + 27 * M; }            // coupling coefs [12*M]
+    };
+    PQP_HD static size_t smem_doubles(const Kp3Dims &d) {
+        return 2 * (size_t)d.nv + 8 * (size_t)kT + (size_t)IMAX * (BW + 1) * d.M + (size_t)IMAX * 6 * d.M +
+               (size_t)d.nS * d.nS + (size_t)(kRed2 + 27 + 12) * d.M;
+    }
+
+#define PQP_F(k, dd) fcol[((k) * (BW + 1) + (dd)) * Mst]
+
+    // per-thread station state ------------------------------------------------------------------
+    struct St {
+        // row state and data
+        double vD0, vD1, vD2, vKB, vSB, vH1, vH3, vS4m, vS4p, vS2m, vS2p;
+        double WD0, WD1, WD2, WKB, WSB, WH1, WH3, WS4, WS2;
+        double lH1, uH1, lH3, uH3, uS4m, lS4p, uS2m, lS2p;
+        double b0, b1, b2;          // bounds of the dynamics (equality) rows
+        double ds, q10;             // transition i -> i+1
+        double dst, qt;             // transition i-1 -> i
+        double sga, sgb, sgc, sgs, ksinv;
+        double xa, xb, xc, xs;      // iterate
+        int pos, posp, posup;       // padded index of a_i, a_{i-1}, u of transition i-1
+        bool live, first, last, sep;
+    };
+    struct Ub {                     // held control j (thread j < ch)
+        double v, W, x, sg;
+        int pos, t0, t1;            // padded index, first / last transition of the block
+        bool live;
+    };
+
+    // ---- the whole per-path solve ----------------------------------------------------------------
+    PQP_DEV static void solve_path(const Cta &c, const DevParams &pm, const BatchView &bv, int prob, double *smem,
+                                   size_t smem_cap) {
+        const int lane = c.lane(), tid = c.tid(), wid = c.wid;
+        const int N = bv.n_points[prob];
+        const int off = bv.offsets[prob];
+        const pqp_state *ref = bv.ref + off;
+        const pqp_station_bounds *bnd = bv.bounds + off;
+        pqp_state *out = bv.out_states + off;
+        int keep = 1;
+        {
+            double interval = 0.0;  // solver.cpp:21-27, solver_kp_as_input.cpp:17
+            for (int i = 1; i < N && i < 10; ++i) {
+                const double dd = ref[i].s - ref[i - 1].s;
+                interval = interval > dd ? interval : dd;
+            }
+            const double q = 1.2 / interval;
+            keep = (q < 2147483647.0) ? (int)q : 2147483647;
+            if (!(q == q)) keep = 0;
+            if (keep < 1) keep = 1;
+        }
+        const double qnan = nan("");
+        const bool shape_ok = fits(N, keep);
+        const Kp3Dims d = dims(shape_ok ? N : 2, shape_ok ? keep : 1);
+        if (!shape_ok || smem_doubles(d) > smem_cap || !bv.workspace) {
+            if (tid == 0) {
+                bv.status[prob] = PQP_INVALID_PROBLEM;
+                if (bv.iters) bv.iters[prob] = 0;
+            }
+            for (int i = tid; i < N; i += kT) {
+                out[i].x = out[i].y = out[i].z = out[i].k = out[i].s = qnan;
+                out[i].v = out[i].a = 0.0;
+                if (bv.out_frenet) {
+                    double *f = bv.out_frenet + 3 * (size_t)(off + i);
+                    f[0] = f[1] = f[2] = qnan;
+                }
+            }
+            return;
+        }
+        Smem s;
+        s.base = smem; s.nv = d.nv; s.M = d.M; s.nS = d.nS; s.ch = d.ch;
+        const int M = d.M, L = d.L, ch = d.ch, nS = d.nS, Mst = d.M;
+        double *ws = bv.workspace + (size_t)off * 16 + (size_t)prob * kWsPerPath;  // E[9] per station, [9N..] EUB, EEnd; then D
+        const KpDims ka = kp_dims(N, keep);
+        // ---- station / control ownership and padded positions
+        St st;
+        const int i = tid;
+        st.live = i < N;
+        st.first = (i == 0);
+        st.last = (i == N - 1);
+        st.sep = st.live && (i % L == 0);
+        st.pos = st.posp = st.posup = 0;
+        if (st.live) {
+            const int p = i / L;
+            st.pos = p * d.CS + (kp_gx(ka, i) - kp_gx(ka, p * L));
+            if (i > 0) {
+                const int t = i - 1, pt = t / L;
+                st.posp = pt * d.CS + (kp_gx(ka, t) - kp_gx(ka, pt * L));
+                const int j = t / keep;
+                int home = j * keep + d.h;
+                if (home > N - 1) home = N - 1;
+                const int pu = home / L;
+                st.posup = pu * d.CS + (kp_gu(ka, j) - kp_gx(ka, pu * L));
+            }
+        }
+        Ub ub;
+        ub.live = tid < ch;
+        ub.pos = 0; ub.t0 = 0; ub.t1 = -1;
+        if (ub.live) {
+            const int j = tid;
+            int home = j * keep + d.h;
+            if (home > N - 1) home = N - 1;
+            const int pu = home / L;
+            ub.pos = pu * d.CS + (kp_gu(ka, j) - kp_gx(ka, pu * L));
+            ub.t0 = j * keep;
+            ub.t1 = j * keep + keep - 1;
+            if (ub.t1 > N - 2) ub.t1 = N - 2;
+        }
+        // partition lanes (warp 0): interior after separator p
+        int lo = 3, cnt = 0;
+        if (wid == 0 && lane < M) {
+            const int g0 = kp_gx(ka, lane * L);
+            const int g1 = (lane + 1 < M) ? kp_gx(ka, (lane + 1) * L) : ka.nred;
+            lo = lane * d.CS + 3;
+            cnt = g1 - g0 - 3;
+        }
+        // end-heading window, solver_kp_as_input.cpp:193-201
+        double lEH = -kOsqpInfty, uEH = kOsqpInfty;
+        if (pm.constraint_end_heading) {
+            const double pi = 3.14159265358979323846;
+            const double end_psi = constraint_angle(bv.end_heading[prob] - ref[N - 1].z);
+            if (end_psi < 70 * pi / 180) {
+                lEH = end_psi - 5 * pi / 180;
+                uEH = end_psi + 5 * pi / 180;
+            }
+        }
+        // ---- per-station coefficients (setConstraintMatrix :84-98, :143-151, :166-187)
+        int invalid = (cnt > IMAX);
+        st.ds = st.q10 = st.dst = st.qt = 0.0;
+        st.b0 = st.b1 = st.b2 = 0.0;
+        st.lH1 = st.lH3 = -1.0; st.uH1 = st.uH3 = 1.0;
+        st.uS4m = st.uS2m = 0.0; st.lS4p = st.lS2p = 0.0;
+        if (st.live) {
+            const double kap = ref[i].k;
+            if (!st.last) {
+                st.ds = ref[i + 1].s - ref[i].s;
+                st.q10 = -(kap * kap) * st.ds;
+            }
+            if (st.first) {
+                st.b0 = -bv.x0[3 * (size_t)prob];
+                st.b1 = -bv.x0[3 * (size_t)prob + 1];
+                st.b2 = -bv.x0[3 * (size_t)prob + 2];
+            } else {
+                const double kp_ = ref[i - 1].k;
+                st.dst = ref[i].s - ref[i - 1].s;
+                st.qt = -(kp_ * kp_) * st.dst;
+                st.b1 = st.dst * kp_;
+            }
+            const pqp_station_bounds bb = bnd[i];
+            st.lH1 = bb.c0_lb; st.uH1 = bb.c0_ub;
+            st.lH3 = bb.c2_lb; st.uH3 = bb.c2_ub;
+            st.uS4m = bb.c3_ub - pm.margin; st.lS4p = bb.c3_lb + pm.margin;
+            st.uS2m = bb.c1_ub - pm.margin; st.lS2p = bb.c1_lb + pm.margin;
+            if (!(bb.c0_lb <= bb.c0_ub) || !(bb.c2_lb <= bb.c2_ub)) invalid = 1;
+            if (!(-kOsqpInfty <= st.uS4m) || !(st.lS4p <= kOsqpInfty) || !(-kOsqpInfty <= st.uS2m) ||
+                !(st.lS2p <= kOsqpInfty))
+                invalid = 1;
+            s.dsS()[i] = st.ds;
+        }
+        if (!(0.0 <= pm.margin) || !(-pm.kmax <= pm.kmax) || !(lEH <= uEH)) invalid = 1;
+        invalid = c.any(invalid);
+
+        int status = PQP_UNSOLVED;
+        int iter = 0;
+        double vEY = 0, vEH = 0, WEY = 0, WEH = 0;   // end rows (thread of station N-1)
+        st.xa = st.xb = st.xc = st.xs = 0.0;
+        ub.x = 0.0; ub.v = 0.0; ub.W = 0.0; ub.sg = 0.0;
+        double cost_c = 1.0;
+        if (invalid) {
+            status = PQP_INVALID_PROBLEM;
+        } else {
+            // ================= Ruiz equilibration + cost scaling (OSQP scale_data) =================
+            double Da = 1, Db = 1, Dc = 1, Dsv = 1, Du = 1, Dt = 1;
+            double e0 = 1, e1 = 1, e2 = 1, eKB = 1, eSB = 1, eH1 = 1, eH3 = 1, eS4 = 1, eS2 = 1, eUB = 1, eEY = 1, eEH = 1;
+            const double ad1 = fabs(pm.d1), ad2 = fabs(pm.d2), ad3 = fabs(pm.d3), ad4 = fabs(pm.d4);
+            for (int sweep = 0; sweep < pm.scaling; ++sweep) {
+                // publish what neighbours need: D of this station, E of its dynamics rows, Du
+                if (st.live) {
+                    s.ex(0)[i] = Da; s.ex(1)[i] = Db; s.ex(2)[i] = Dc;
+                    s.ex(3)[i] = e0; s.ex(4)[i] = e1; s.ex(5)[i] = e2;
+                }
+                if (ub.live) s.tr()[tid] = Du;       // Du per control (tr is free during scaling; ch <= kT <= nv)
+                c.sync();
+                double fDa = 1, fDb = 1, fDc = 1, fDs = 1, fDu = 1;
+                double f0 = 1, f1 = 1, f2 = 1, fKB = 1, fSB = 1, fH1 = 1, fH3 = 1, fS4 = 1, fS2 = 1, fUB = 1, fEY = 1, fEH = 1;
+                if (st.live) {
+                    double Aa = fmax(fmax(e0, eH1), fmax(eH3, fmax(eS4, eS2)));
+                    double Ab = fmax(fmax(e1, eH1 * ad1), fmax(eH3 * ad3, fmax(eS4 * ad4, eS2 * ad2)));
+                    double Ac = fmax(e2, eKB);
+                    if (!st.last) {
+                        const double e0n = s.ex(3)[i + 1], e1n = s.ex(4)[i + 1], e2n = s.ex(5)[i + 1];
+                        const double aq = fabs(st.q10);
+                        Aa = fmax(Aa, fmax(e0n, e1n * aq));
+                        Ab = fmax(Ab, fmax(e0n * st.ds, e1n));
+                        Ac = fmax(Ac, fmax(e1n * st.ds, e2n));
+                    } else {
+                        Aa = fmax(Aa, eEY);
+                        Ab = fmax(Ab, eEH);
+                    }
+                    const double As = fmax(eSB, fmax(eS4, eS2));
+                    fDa = 1.0 / sqrt(limit_scaling(fmax(cost_c * pm.w_pq * Da * Da, Aa * Da)));
+                    fDb = 1.0 / sqrt(limit_scaling(Ab * Db));
+                    fDc = 1.0 / sqrt(limit_scaling(fmax(cost_c * pm.w_c * Dc * Dc, Ac * Dc)));
+                    fDs = 1.0 / sqrt(limit_scaling(fmax(cost_c * pm.w_s * Dsv * Dsv, As * Dsv)));
+                    double r0, r1, r2;
+                    if (st.first) {
+                        r0 = e0 * Da; r1 = e1 * Db; r2 = e2 * Dc;
+                    } else {
+                        const double Dat = s.ex(0)[i - 1], Dbt = s.ex(1)[i - 1], Dct = s.ex(2)[i - 1];
+                        const double Dut = s.tr()[(i - 1) / keep];
+                        const double aqt = fabs(st.qt);
+                        r0 = e0 * fmax(Da, fmax(Dat, st.dst * Dbt));
+                        r1 = e1 * fmax(fmax(Db, aqt * Dat), fmax(Dbt, st.dst * Dct));
+                        r2 = e2 * fmax(Dc, fmax(Dct, st.dst * Dut));
+                    }
+                    f0 = 1.0 / sqrt(limit_scaling(r0));
+                    f1 = 1.0 / sqrt(limit_scaling(r1));
+                    f2 = 1.0 / sqrt(limit_scaling(r2));
+                    fKB = 1.0 / sqrt(limit_scaling(eKB * Dc));
+                    fSB = 1.0 / sqrt(limit_scaling(eSB * Dsv));
+                    fH1 = 1.0 / sqrt(limit_scaling(eH1 * fmax(Da, ad1 * Db)));
+                    fH3 = 1.0 / sqrt(limit_scaling(eH3 * fmax(Da, ad3 * Db)));
+                    fS4 = 1.0 / sqrt(limit_scaling(eS4 * fmax(Da, fmax(ad4 * Db, Dsv))));
+                    fS2 = 1.0 / sqrt(limit_scaling(eS2 * fmax(Da, fmax(ad2 * Db, Dsv))));
+                    if (st.last) {
+                        fEY = 1.0 / sqrt(limit_scaling(eEY * Da));
+                        fEH = 1.0 / sqrt(limit_scaling(eEH * Db));
+                    }
+                }
+                if (ub.live) {
+                    double Au = eUB;
+                    for (int t = ub.t0; t <= ub.t1; ++t) Au = fmax(Au, s.ex(5)[t + 1] * s.dsS()[t]);
+                    fDu = 1.0 / sqrt(limit_scaling(fmax(cost_c * (keep * pm.w_cr) * Du * Du, Au * Du)));
+                    fUB = 1.0 / sqrt(limit_scaling(eUB * Du));
+                }
+                const double fDt = 1.0 / sqrt(limit_scaling(cost_c * pm.w_s * Dt * Dt));
+                Da *= fDa; Db *= fDb; Dc *= fDc; Dsv *= fDs; Du *= fDu; Dt *= fDt;
+                e0 *= f0; e1 *= f1; e2 *= f2; eKB *= fKB; eSB *= fSB; eH1 *= fH1; eH3 *= fH3; eS4 *= fS4; eS2 *= fS2;
+                eUB *= fUB; eEY *= fEY; eEH *= fEH;
+                double part = 0.0;
+                if (st.live)
+                    part += cost_c * pm.w_pq * Da * Da + cost_c * pm.w_c * Dc * Dc + cost_c * pm.w_s * Dsv * Dsv +
+                            cost_c * pm.w_s * Dt * Dt;
+                if (ub.live) part += cost_c * (keep * pm.w_cr) * Du * Du;
+                const double mean = c.sum(part) / (double)(5 * N + ch);   // (contains CTA barriers)
+                double ct = fmax(mean, 1.0);
+                ct = limit_scaling(ct);
+                cost_c = cost_c * (1.0 / ct);
+            }
+            // publish E, D to the workspace (read back at residual checks / refactorisations)
+            if (st.live) {
+                double *w9 = ws + 9 * (size_t)i;
+                w9[0] = e0; w9[1] = e1; w9[2] = e2; w9[3] = eKB; w9[4] = eSB; w9[5] = eH1; w9[6] = eH3; w9[7] = eS4; w9[8] = eS2;
+                double *wD = ws + 9 * (size_t)N + ch + 2 + 4 * (size_t)i;
+                wD[0] = Da; wD[1] = Db; wD[2] = Dc; wD[3] = Dsv;
+                st.sga = pm.sigma / (Da * Da); st.sgb = pm.sigma / (Db * Db);
+                st.sgc = pm.sigma / (Dc * Dc); st.sgs = pm.sigma / (Dsv * Dsv);
+                if (st.last) { ws[9 * (size_t)N + ch] = eEY; ws[9 * (size_t)N + ch + 1] = eEH; }
+            }
+            if (ub.live) {
+                ws[9 * (size_t)N + tid] = eUB;
+                ws[13 * (size_t)N + ch + 2 + tid] = Du;
+                ub.sg = pm.sigma / (Du * Du);
+            }
+            // cold start: OSQP's first iteration from zero leaves x = 0, v = 0 (see pqp_kp_core.cuh)
+            st.vD0 = st.vD1 = st.vD2 = st.vKB = st.vSB = st.vH1 = st.vH3 = 0.0;
+            st.vS4m = st.vS4p = st.vS2m = st.vS2p = 0.0;
+            for (int g = tid; g < d.nv; g += kT) { s.tr()[g] = 0.0; s.yv()[g] = 0.0; }
+            double rho = fmin(fmax(pm.rho, kRhoMin), kRhoMax);
+            c.sync();
+
+            // ================= (re)factorisation =====================================================
+            auto refactor = [&]() -> int {
+                // ---- row weights W = rho_row E^2 from the workspace E
+                if (st.live) {
+                    const double *w9 = ws + 9 * (size_t)i;
+                    st.WD0 = kp_w_eq(w9[0], rho); st.WD1 = kp_w_eq(w9[1], rho); st.WD2 = kp_w_eq(w9[2], rho);
+                    st.WKB = kp_w_box(w9[3], -pm.kmax, pm.kmax, rho);
+                    st.WSB = kp_w_box(w9[4], 0.0, pm.margin, rho);
+                    st.WH1 = kp_w_box(w9[5], st.lH1, st.uH1, rho);
+                    st.WH3 = kp_w_box(w9[6], st.lH3, st.uH3, rho);
+                    st.WS4 = kp_w_box(w9[7], -kOsqpInfty, st.uS4m, rho);
+                    st.WS2 = kp_w_box(w9[8], -kOsqpInfty, st.uS2m, rho);
+                    if (st.last) {
+                        WEY = kp_w_box(ws[9 * (size_t)N + ch], -1.0, 1.0, rho);
+                        WEH = kp_w_box(ws[9 * (size_t)N + ch + 1], lEH, uEH, rho);
+                    }
+                    st.ksinv = 1.0 / (cost_c * pm.w_s + st.sgs + st.WSB + 2.0 * st.WS4 + 2.0 * st.WS2);
+                    s.ex(0)[i] = st.WD0; s.ex(1)[i] = st.WD1; s.ex(2)[i] = st.WD2;   // neighbours need these
+                }
+                if (ub.live) ub.W = kp_w_box(ws[9 * (size_t)N + tid], -kOsqpInfty, kOsqpInfty, rho);
+                // zero the factor storage (identity on padded rows)
+                for (int k = tid; k < IMAX * (BW + 1) * M; k += kT) {
+                    const int p = k % M, kd = k / M, dd = kd % (BW + 1), kk = kd / (BW + 1);
+                    int cp = 0;
+                    {   // interior size of chunk p
+                        const int g0 = kp_gx(ka, p * L);
+                        const int g1 = (p + 1 < M) ? kp_gx(ka, (p + 1) * L) : ka.nred;
+                        cp = g1 - g0 - 3;
+                    }
+                    s.fac()[k] = (dd == 0 && kk >= cp) ? 1.0 : 0.0;
+                }
+                c.sync();
+                // ---- assembly: every station / control thread writes its own band rows
+                double N0 = 0, N1 = 0, N2 = 0;
+                if (st.live && !st.last) { N0 = s.ex(0)[i + 1]; N1 = s.ex(1)[i + 1]; N2 = s.ex(2)[i + 1]; }
+                const double d1 = pm.d1, d2 = pm.d2, d3 = pm.d3, d4 = pm.d4;
+                double da = 0, db = 0, dc = 0, kba = 0, kca = 0, kcb = 0;
+                if (st.live) {
+                    da = cost_c * pm.w_pq + st.sga + st.WD0 + N0 + N1 * st.q10 * st.q10 + st.WH1 + st.WH3 + 2.0 * st.WS4 + 2.0 * st.WS2;
+                    db = st.sgb + st.WD1 + N0 * st.ds * st.ds + N1 + st.WH1 * d1 * d1 + st.WH3 * d3 * d3 +
+                         2.0 * st.WS4 * d4 * d4 + 2.0 * st.WS2 * d2 * d2;
+                    dc = cost_c * pm.w_c + st.sgc + st.WD2 + N1 * st.ds * st.ds + N2 + st.WKB;
+                    if (st.last) { da += WEY; db += WEH; }
+                    kba = N0 * st.ds + N1 * st.q10 + st.WH1 * d1 + st.WH3 * d3 + 2.0 * st.WS4 * d4 + 2.0 * st.WS2 * d2;
+                    kca = N1 * st.q10 * st.ds;
+                    kcb = N1 * st.ds;
+                    if (!st.sep) {
+                        const int p = i / L;
+                        double *fcol = s.fac() + p;
+                        const int k0 = st.pos - (p * d.CS + 3);
+                        PQP_F(k0, 0) = da; PQP_F(k0 + 1, 0) = db; PQP_F(k0 + 2, 0) = dc;
+                        PQP_F(k0 + 1, 1) = kba; PQP_F(k0 + 2, 2) = kca; PQP_F(k0 + 2, 1) = kcb;
+                        if ((i - 1) % L != 0) {   // previous station is interior as well
+                            const int o = st.pos - st.posp;
+                            PQP_F(k0, o) = -st.WD0;
+                            PQP_F(k0, o - 1) = -st.WD0 * st.dst;
+                            PQP_F(k0 + 1, o + 1) = -st.WD1 * st.qt;
+                            PQP_F(k0 + 1, o) = -st.WD1;
+                            PQP_F(k0 + 1, o - 1) = -st.WD1 * st.dst;
+                            PQP_F(k0 + 2, o) = -st.WD2;
+                        }
+                    }
+                }
+                if (ub.live) {
+                    const int p = ub.pos / d.CS;
+                    double *fcol = s.fac() + p;
+                    const int ku = ub.pos - (p * d.CS + 3);
+                    double du = cost_c * (keep * pm.w_cr) + ub.sg + ub.W;
+                    int ii1 = tid * keep + keep;
+                    if (ii1 > N - 1) ii1 = N - 1;
+                    for (int ii = tid * keep; ii <= ii1; ++ii) {
+                        double val = 0.0;
+                        if (ii >= 1 && (ii - 1) / keep == tid) {
+                            const double wv = s.ex(2)[ii], dst = s.dsS()[ii - 1];
+                            val -= wv * dst;
+                            du += wv * dst * dst;
+                        }
+                        if (ii <= N - 2 && ii / keep == tid) val += s.ex(2)[ii + 1] * s.dsS()[ii];
+                        if (ii % L == 0) continue;   // c of a separator station: handled through the spikes
+                        const int pi = ii / L;
+                        const int kc = pi * d.CS + (kp_gx(ka, ii) - kp_gx(ka, pi * L)) + 2 - (p * d.CS + 3);
+                        if (kc < ku) PQP_F(ku, ku - kc) = val;
+                        else PQP_F(kc, kc - ku) = val;
+                    }
+                    PQP_F(ku, 0) = du;
+                }
+                c.sync();
+                // ---- interior LDL' (warp 0, lane p) and coupling coefficients per chunk:
+                //      cpl[p] = left  (transition e -> e+1):  N0 N1 N2 ds q
+                //               right (transition e2-1 -> e2): W0 W1 W2 ds q ; + flags
+                int ok = 1;
+                if (wid == 0 && lane < M) ok = K2::local_factor(s.fac() + lane, Mst);
+                if (st.live && i >= 1) {
+                    if ((i - 1) % L == 0) {          // first interior station of chunk p: owns the LEFT coupling
+                        double *cp = s.cpl() + 12 * ((i - 1) / L);
+                        cp[0] = st.WD0; cp[1] = st.WD1; cp[2] = st.WD2; cp[3] = st.dst; cp[4] = st.qt;
+                    }
+                    if (st.sep) {                   // separator p: owns the RIGHT coupling of chunk p-1
+                        double *cp = s.cpl() + 12 * (i / L - 1);
+                        cp[5] = st.WD0; cp[6] = st.WD1; cp[7] = st.WD2; cp[8] = st.dst; cp[9] = st.qt;
+                    }
+                }
+                c.sync();
+                // ---- spikes: thread (p, col) solves K_I t = K[I, s_col]  (col 0..2 left, 3..5 right separator)
+                const int sp_p = tid / 6, sp_c = tid % 6;
+                bool sp_act = tid < 6 * M;
+                int ka1 = 0, kul = 0, kat = 0, kur = 0;
+                bool has_int = false, has_right = false;
+                double lN0 = 0, lN1 = 0, lN2 = 0, lds = 0, lq = 0, rW0 = 0, rW1 = 0, rW2 = 0, rds = 0, rq = 0;
+                double *tcol = s.T() + sp_p;   // element (k, col) at tcol[(k*6+col)*Mst]
+                if (sp_act) {
+                    const int e = sp_p * L, e2 = e + L;
+                    const int g0 = kp_gx(ka, e);
+                    const int g1 = (sp_p + 1 < M) ? kp_gx(ka, e2) : ka.nred;
+                    const int cn = g1 - g0 - 3;
+                    has_int = cn > 0 && e < N - 1;
+                    has_right = sp_p + 1 < M;
+                    const double *cp = s.cpl() + 12 * sp_p;
+                    const int lo_p = sp_p * d.CS + 3;
+                    if (has_int) {
+                        lN0 = cp[0]; lN1 = cp[1]; lN2 = cp[2]; lds = cp[3]; lq = cp[4];
+                        ka1 = (kp_gx(ka, e + 1) - g0) - 3;
+                        int home = (e / keep) * keep + d.h;
+                        if (home > N - 1) home = N - 1;
+                        kul = (home / L) * d.CS + (kp_gu(ka, e / keep) - kp_gx(ka, (home / L) * L)) - lo_p;
+                    }
+                    if (has_right) {
+                        rW0 = cp[5]; rW1 = cp[6]; rW2 = cp[7]; rds = cp[8]; rq = cp[9];
+                        kat = (kp_gx(ka, e2 - 1) - g0) - 3;
+                        const int j = (e2 - 1) / keep;
+                        int home = j * keep + d.h;
+                        if (home > N - 1) home = N - 1;
+                        kur = (home / L) * d.CS + (kp_gu(ka, j) - kp_gx(ka, (home / L) * L)) - lo_p;
+                    }
+#pragma unroll 1
+                    for (int k = 0; k < IMAX; ++k) tcol[(k * 6 + sp_c) * Mst] = 0.0;
+                    const bool colok = (sp_c < 3) ? has_int : has_right;
+                    if (colok) {
+#define PQP_TC(k) tcol[((k) * 6 + sp_c) * Mst]
+                        if (sp_c == 0) { PQP_TC(ka1) += -lN0; PQP_TC(ka1 + 1) += -lN1 * lq; }
+                        else if (sp_c == 1) { PQP_TC(ka1) += -lN0 * lds; PQP_TC(ka1 + 1) += -lN1; }
+                        else if (sp_c == 2) { PQP_TC(ka1 + 1) += -lN1 * lds; PQP_TC(ka1 + 2) += -lN2; PQP_TC(kul) += lN2 * lds; }
+                        else if (sp_c == 3) { PQP_TC(kat) += -rW0; PQP_TC(kat + 1) += -rW0 * rds; }
+                        else if (sp_c == 4) { PQP_TC(kat) += -rW1 * rq; PQP_TC(kat + 1) += -rW1; PQP_TC(kat + 2) += -rW1 * rds; }
+                        else { PQP_TC(kat + 2) += -rW2; PQP_TC(kur) += -rW2 * rds; }
+#undef PQP_TC
+                        K2::local_solve(tcol + sp_c * Mst, 6 * Mst, s.fac() + sp_p, Mst);
+                    }
+                }
+                c.sync();
+                // ---- Schur blocks: A_p = K[S_p,I] T_left, Off_p = -(K[S_q,I] T_left)', C_p = K[S_q,I] T_right
+                if (sp_act) {
+                    double tl0 = 0, tl1 = 0, tl2 = 0, tr0 = 0, tr1 = 0, tr2 = 0;
+                    const bool colok = (sp_c < 3) ? has_int : has_right;
+                    if (colok) {
+#define PQP_TC(k) tcol[((k) * 6 + sp_c) * Mst]
+                        if (has_int) {
+                            const double wa = PQP_TC(ka1), wb = PQP_TC(ka1 + 1), wc = PQP_TC(ka1 + 2), wu = PQP_TC(kul);
+                            tl0 = -lN0 * wa - lN1 * lq * wb;
+                            tl1 = -lN0 * lds * wa - lN1 * wb;
+                            tl2 = -lN1 * lds * wb - lN2 * wc + lN2 * lds * wu;
+                        }
+                        if (has_right) {
+                            const double wa = PQP_TC(kat), wb = PQP_TC(kat + 1), wc = PQP_TC(kat + 2), wu = PQP_TC(kur);
+                            tr0 = -rW0 * wa - rW0 * rds * wb;
+                            tr1 = -rW1 * rq * wa - rW1 * wb - rW1 * rds * wc;
+                            tr2 = -rW2 * wc - rW2 * rds * wu;
+                        }
+#undef PQP_TC
+                    }
+                    double *B = s.blk() + 27 * sp_p;   // A[9] | C[9] | Off[9]
+                    if (sp_c < 3) {
+                        B[0 * 3 + sp_c] = tl0; B[1 * 3 + sp_c] = tl1; B[2 * 3 + sp_c] = tl2;                 // A[r][col]
+                        B[18 + sp_c * 3 + 0] = -tr0; B[18 + sp_c * 3 + 1] = -tr1; B[18 + sp_c * 3 + 2] = -tr2;  // Off[col][r]
+                    } else {
+                        const int cc = sp_c - 3;
+                        B[9 + 0 * 3 + cc] = tr0; B[9 + 1 * 3 + cc] = tr1; B[9 + 2 * 3 + cc] = tr2;          // C[r][col]
+                    }
+                }
+                c.sync();
+                // ---- Dg_p = K[S_p,S_p] - A_p - C_{p-1}  (separator station threads), Off_p -> red
+                if (st.sep) {
+                    const int p = i / L;
+                    const double *B = s.blk() + 27 * p;
+                    double *R = s.red() + kRed2 * p;
+                    double Dg[9];
+#pragma unroll
+                    for (int k = 0; k < 9; ++k) {
+                        Dg[k] = -B[k];
+                        if (p > 0) Dg[k] -= B[k - 27 + 9];
+                    }
+                    Dg[0] += da; Dg[4] += db; Dg[8] += dc;
+                    Dg[1] += kba; Dg[3] += kba; Dg[2] += kca; Dg[6] += kca; Dg[5] += kcb; Dg[7] += kcb;
+#pragma unroll
+                    for (int k = 0; k < 9; ++k) { R[k] = Dg[k]; R[9 + k] = B[18 + k]; }
+                }
+                c.sync();
+                // ---- block LDL' of the separator system (one thread), as in pqp_kp_core2.cuh:
+                //      red[p] = Sinv_p | H_p = Sinv_p Off_p | G_p = Off_{p-1}' Sinv_{p-1}
+                if (tid == 0) {
+                    double Sch[9], Sinv[9];
+                    for (int k = 0; k < 9; ++k) Sch[k] = s.red()[k];
+                    for (int p = 0; p < M; ++p) {
+                        double *Rp = s.red() + kRed2 * p;
+                        if (!(Sch[0] > 0.0)) ok = 0;
+                        inv3_spd(Sch, Sinv);
+                        if (p + 1 < M) {
+                            double *Rn = Rp + kRed2;
+                            double Off[9];
+                            for (int k = 0; k < 9; ++k) Off[k] = Rp[9 + k];
+                            for (int r = 0; r < 3; ++r)
+                                for (int cc = 0; cc < 3; ++cc) {
+                                    double a = 0.0, hh = 0.0;
+                                    for (int k = 0; k < 3; ++k) {
+                                        a += Off[k * 3 + r] * Sinv[k * 3 + cc];
+                                        hh += Sinv[r * 3 + k] * Off[k * 3 + cc];
+                                    }
+                                    Rn[18 + r * 3 + cc] = a;
+                                    Rp[9 + r * 3 + cc] = hh;
+                                }
+                            for (int r = 0; r < 3; ++r)
+                                for (int cc = 0; cc < 3; ++cc) {
+                                    double a = Rn[r * 3 + cc];
+                                    for (int k = 0; k < 3; ++k) a -= Rn[18 + r * 3 + k] * Off[k * 3 + cc];
+                                    Sch[r * 3 + cc] = a;
+                                }
+                        }
+                        for (int k = 0; k < 9; ++k) Rp[k] = Sinv[k];
+                    }
+                }
+                c.sync();
+                // ---- dense inverse of the separator system: thread t solves for unit vector e_t and
+                //      stores column t (= row t, the matrix is symmetric) as Sinv[k*nS + t]
+                if (tid < nS) {
+                    const int pt = tid / 3, rt = tid % 3;
+                    double *col = s.Sinv() + tid;
+                    // forward: g'_p = g_p - G_p g'_{p-1}; g is e_t  -> zero before block pt
+                    double g0 = 0, g1 = 0, g2 = 0;
+                    for (int p = 0; p < M; ++p) {
+                        const double *Rp = s.red() + kRed2 * p;
+                        double n0 = (p == pt && rt == 0) ? 1.0 : 0.0, n1 = (p == pt && rt == 1) ? 1.0 : 0.0,
+                               n2 = (p == pt && rt == 2) ? 1.0 : 0.0;
+                        if (p > pt) {
+                            n0 -= Rp[18] * g0 + Rp[19] * g1 + Rp[20] * g2;
+                            n1 -= Rp[21] * g0 + Rp[22] * g1 + Rp[23] * g2;
+                            n2 -= Rp[24] * g0 + Rp[25] * g1 + Rp[26] * g2;
+                        }
+                        g0 = n0; g1 = n1; g2 = n2;
+                        // g^ = Sinv_p g' parked in the output column
+                        col[(3 * p) * nS] = Rp[0] * g0 + Rp[1] * g1 + Rp[2] * g2;
+                        col[(3 * p + 1) * nS] = Rp[3] * g0 + Rp[4] * g1 + Rp[5] * g2;
+                        col[(3 * p + 2) * nS] = Rp[6] * g0 + Rp[7] * g1 + Rp[8] * g2;
+                    }
+                    double x0 = col[(3 * (M - 1)) * nS], x1 = col[(3 * (M - 1) + 1) * nS], x2 = col[(3 * (M - 1) + 2) * nS];
+                    for (int p = M - 2; p >= 0; --p) {
+                        const double *Rp = s.red() + kRed2 * p;
+                        const double y0 = col[(3 * p) * nS] - (Rp[9] * x0 + Rp[10] * x1 + Rp[11] * x2);
+                        const double y1 = col[(3 * p + 1) * nS] - (Rp[12] * x0 + Rp[13] * x1 + Rp[14] * x2);
+                        const double y2 = col[(3 * p + 2) * nS] - (Rp[15] * x0 + Rp[16] * x1 + Rp[17] * x2);
+                        col[(3 * p) * nS] = y0; col[(3 * p + 1) * nS] = y1; col[(3 * p + 2) * nS] = y2;
+                        x0 = y0; x1 = y1; x2 = y2;
+                    }
+                }
+                return !c.any(!ok);   // (contains CTA barriers)
+            };
+
+            if (!refactor()) status = PQP_NON_CVX;
+            const double alpha = pm.alpha;
+            double pri_res = 0, dua_res = 0, pri_nrm = 0, dua_nrm = 0;
+            const double d1 = pm.d1, d2 = pm.d2, d3 = pm.d3, d4 = pm.d4;
+            iter = 1;
+            while (status == PQP_UNSOLVED && iter < pm.max_iter) {
+                ++iter;
+                // ---- (a) g = W (2 clamp(v) - v) per row; rhs = sigma x + A' g
+                const double gD0 = st.WD0 * (2.0 * st.b0 - st.vD0);
+                const double gD1 = st.WD1 * (2.0 * st.b1 - st.vD1);
+                const double gD2 = st.WD2 * (2.0 * st.b2 - st.vD2);
+                if (st.live) { s.ex(0)[i] = gD0; s.ex(1)[i] = gD1; s.ex(2)[i] = gD2; }
+                c.sync();
+                double tsl = 0.0;   // x-tilde of the slack (decouples exactly)
+                if (st.live) {
+                    const double gKB = st.WKB * (2.0 * clampd(st.vKB, -pm.kmax, pm.kmax) - st.vKB);
+                    const double gSB = st.WSB * (2.0 * clampd(st.vSB, 0.0, pm.margin) - st.vSB);
+                    const double gH1 = st.WH1 * (2.0 * clampd(st.vH1, st.lH1, st.uH1) - st.vH1);
+                    const double gH3 = st.WH3 * (2.0 * clampd(st.vH3, st.lH3, st.uH3) - st.vH3);
+                    const double g4m = st.WS4 * (2.0 * fmin(st.vS4m, st.uS4m) - st.vS4m);
+                    const double g4p = st.WS4 * (2.0 * fmax(st.vS4p, st.lS4p) - st.vS4p);
+                    const double g2m = st.WS2 * (2.0 * fmin(st.vS2m, st.uS2m) - st.vS2m);
+                    const double g2p = st.WS2 * (2.0 * fmax(st.vS2p, st.lS2p) - st.vS2p);
+                    const double s4 = g4m + g4p, s2 = g2m + g2p;
+                    double ra = -gD0 + gH1 + gH3 + s4 + s2;
+                    double rb = -gD1 + d1 * gH1 + d3 * gH3 + d4 * s4 + d2 * s2;
+                    double rc = -gD2 + gKB;
+                    const double rs = gSB - g4m + g4p - g2m + g2p;
+                    if (!st.last) {
+                        const double n0 = s.ex(0)[i + 1], n1 = s.ex(1)[i + 1], n2 = s.ex(2)[i + 1];
+                        ra += n0 + st.q10 * n1;
+                        rb += st.ds * n0 + n1;
+                        rc += st.ds * n1 + n2;
+                    } else {
+                        ra += WEY * (2.0 * clampd(vEY, -1.0, 1.0) - vEY);
+                        rb += WEH * (2.0 * clampd(vEH, lEH, uEH) - vEH);
+                    }
+                    s.tr()[st.pos] = st.sga * st.xa + ra;
+                    s.tr()[st.pos + 1] = st.sgb * st.xb + rb;
+                    s.tr()[st.pos + 2] = st.sgc * st.xc + rc;
+                    tsl = (st.sgs * st.xs + rs) * st.ksinv;
+                }
+                if (ub.live) {
+                    double acc = ub.sg * ub.x + ub.W * (2.0 * clampd(ub.v, -kOsqpInfty, kOsqpInfty) - ub.v);
+                    for (int t = ub.t0; t <= ub.t1; ++t) acc += s.dsS()[t] * s.ex(2)[t + 1];
+                    s.tr()[ub.pos] = acc;
+                }
+                c.sync();
+                // ---- (b1) separator rhs g = r_S - T' r_I  (threads 0..3M-1)
+                if (tid < nS) {
+                    const int p = tid / 3, r = tid % 3;
+                    double acc = s.tr()[p * d.CS + r];
+                    const double *Tl = s.T() + p;
+                    const double *rI = s.tr() + p * d.CS + 3;
+#pragma unroll
+                    for (int k = 0; k < IMAX; ++k) acc -= Tl[(k * 6 + r) * Mst] * rI[k];
+                    if (p > 0) {
+                        const double *Tr = s.T() + (p - 1);
+                        const double *rJ = s.tr() + (p - 1) * d.CS + 3;
+#pragma unroll
+                        for (int k = 0; k < IMAX; ++k) acc -= Tr[(k * 6 + 3 + r) * Mst] * rJ[k];
+                    }
+                    s.gS()[tid] = acc;
+                }
+                c.sync();
+                // ---- (b2) y = K_I^-1 r_I on warp 0  ||  x_S = Sinv g on the following warps
+                if (wid == 0) {
+                    if (lane < M) K2::local_solve2(s.tr() + lo, s.yv() + lo, s.fac() + lane, Mst);
+                } else {
+                    const int t = tid - 32;
+                    if (t < nS) {
+                        const double *row = s.Sinv() + t;
+                        const double *gS = s.gS();
+                        double a0 = 0, a1 = 0, a2 = 0;
+                        for (int k = 0; k < nS; k += 3) {     // nS = 3M
+                            a0 += row[k * nS] * gS[k];
+                            a1 += row[(k + 1) * nS] * gS[k + 1];
+                            a2 += row[(k + 2) * nS] * gS[k + 2];
+                        }
+                        s.ex(3)[t] = (a0 + a1) + a2;
+                    }
+                }
+                c.sync();
+                // ---- (b3) x-tilde: separators take x_S, interiors y - T [x_Sp ; x_Sq]
+                double ta = 0, tb = 0, tc = 0, tu = 0;
+#define PQP_TX(k) ((s.yv()[p * d.CS + 3 + (k)] - (Tp[((k) * 6 + 0) * Mst] * xl0 + Tp[((k) * 6 + 1) * Mst] * xl1 + Tp[((k) * 6 + 2) * Mst] * xl2)) \
+                   - (Tp[((k) * 6 + 3) * Mst] * xr0 + Tp[((k) * 6 + 4) * Mst] * xr1 + Tp[((k) * 6 + 5) * Mst] * xr2))
+                if (st.live) {
+                    const int p = i / L;
+                    if (st.sep) {
+                        ta = s.ex(3)[3 * p]; tb = s.ex(3)[3 * p + 1]; tc = s.ex(3)[3 * p + 2];
+                    } else {
+                        const int k0 = st.pos - (p * d.CS + 3);
+                        const double *Tp = s.T() + p;
+                        const double xl0 = s.ex(3)[3 * p], xl1 = s.ex(3)[3 * p + 1], xl2 = s.ex(3)[3 * p + 2];
+                        double xr0 = 0, xr1 = 0, xr2 = 0;
+                        if (p + 1 < M) { xr0 = s.ex(3)[3 * p + 3]; xr1 = s.ex(3)[3 * p + 4]; xr2 = s.ex(3)[3 * p + 5]; }
+                        ta = PQP_TX(k0); tb = PQP_TX(k0 + 1); tc = PQP_TX(k0 + 2);
+                    }
+                }
+                if (ub.live) {
+                    const int p = ub.pos / d.CS;
+                    const int k0 = ub.pos - (p * d.CS + 3);
+                    const double *Tp = s.T() + p;
+                    const double xl0 = s.ex(3)[3 * p], xl1 = s.ex(3)[3 * p + 1], xl2 = s.ex(3)[3 * p + 2];
+                    double xr0 = 0, xr1 = 0, xr2 = 0;
+                    if (p + 1 < M) { xr0 = s.ex(3)[3 * p + 3]; xr1 = s.ex(3)[3 * p + 4]; xr2 = s.ex(3)[3 * p + 5]; }
+                    tu = PQP_TX(k0);
+                }
+#undef PQP_TX
+                c.sync();   // everyone has consumed tr (rhs): publish x-tilde there for the neighbours
+                if (st.live) { s.tr()[st.pos] = ta; s.tr()[st.pos + 1] = tb; s.tr()[st.pos + 2] = tc; }
+                if (ub.live) s.tr()[ub.pos] = tu;
+                c.sync();
+                // ---- (c) v += alpha (A xt - clamp(v)),  x = alpha xt + (1 - alpha) x
+                if (st.live) {
+                    double zD0 = -ta, zD1 = -tb, zD2 = -tc;
+                    if (!st.first) {
+                        const double at = s.tr()[st.posp], bt = s.tr()[st.posp + 1], ct = s.tr()[st.posp + 2];
+                        const double ut = s.tr()[st.posup];
+                        zD0 += at + st.dst * bt;
+                        zD1 += st.qt * at + bt + st.dst * ct;
+                        zD2 += ct + st.dst * ut;
+                    }
+                    const double e4 = ta + d4 * tb, e2 = ta + d2 * tb;
+                    st.vD0 += alpha * (zD0 - st.b0);
+                    st.vD1 += alpha * (zD1 - st.b1);
+                    st.vD2 += alpha * (zD2 - st.b2);
+                    st.vKB += alpha * (tc - clampd(st.vKB, -pm.kmax, pm.kmax));
+                    st.vSB += alpha * (tsl - clampd(st.vSB, 0.0, pm.margin));
+                    st.vH1 += alpha * ((ta + d1 * tb) - clampd(st.vH1, st.lH1, st.uH1));
+                    st.vH3 += alpha * ((ta + d3 * tb) - clampd(st.vH3, st.lH3, st.uH3));
+                    st.vS4m += alpha * ((e4 - tsl) - fmin(st.vS4m, st.uS4m));
+                    st.vS4p += alpha * ((e4 + tsl) - fmax(st.vS4p, st.lS4p));
+                    st.vS2m += alpha * ((e2 - tsl) - fmin(st.vS2m, st.uS2m));
+                    st.vS2p += alpha * ((e2 + tsl) - fmax(st.vS2p, st.lS2p));
+                    if (st.last) {
+                        vEY += alpha * (ta - clampd(vEY, -1.0, 1.0));
+                        vEH += alpha * (tb - clampd(vEH, lEH, uEH));
+                    }
+                    st.xa = alpha * ta + (1.0 - alpha) * st.xa;
+                    st.xb = alpha * tb + (1.0 - alpha) * st.xb;
+                    st.xc = alpha * tc + (1.0 - alpha) * st.xc;
+                    st.xs = alpha * tsl + (1.0 - alpha) * st.xs;
+                }
+                if (ub.live) {
+                    ub.v += alpha * (tu - clampd(ub.v, -kOsqpInfty, kOsqpInfty));
+                    ub.x = alpha * tu + (1.0 - alpha) * ub.x;
+                }
+                // ---- (d) residuals, termination, adaptive rho
+                const bool can_check = pm.check_termination && (iter % pm.check_termination == 0);
+                const bool can_adapt = pm.adaptive_rho && pm.adaptive_rho_interval &&
+                                       (iter % pm.adaptive_rho_interval == 0);
+                if (can_check || can_adapt || iter == pm.max_iter) {
+                    // publish x (neighbours need station i-1 and the control) and read the scalings
+                    c.sync();
+                    if (st.live) { s.tr()[st.pos] = st.xa; s.tr()[st.pos + 1] = st.xb; s.tr()[st.pos + 2] = st.xc; }
+                    if (ub.live) s.tr()[ub.pos] = ub.x;
+                    c.sync();
+                    double pr = 0, nz = 0, nax = 0, prs = 0, nzs = 0, naxs = 0;
+                    double dr = 0, npx = 0, naty = 0, drs = 0, npxs = 0, natys = 0;
+                    const double cinv = 1.0 / cost_c;
+#define PQP_ROW(AX, V, LO, HI, EE)                                                   \
+    {                                                                                \
+        const double ax_ = (AX), v_ = (V), z_ = clampd(v_, (LO), (HI)), r_ = ax_ - z_; \
+        const double e_ = (EE);                                                      \
+        pr = fmax(pr, fabs(r_)); nz = fmax(nz, fabs(z_)); nax = fmax(nax, fabs(ax_)); \
+        prs = fmax(prs, e_ * fabs(r_)); nzs = fmax(nzs, e_ * fabs(z_));              \
+        naxs = fmax(naxs, e_ * fabs(ax_));                                           \
+    }
+#define PQP_DUAL(V, LO, HI, WW) ((WW) * ((V) - clampd((V), (LO), (HI))) * cinv)
+#define PQP_VAR(PX, ATY, DD)                                                          \
+    {                                                                                 \
+        const double px_ = (PX), aty_ = (ATY), r_ = px_ + aty_, cd_ = cost_c * (DD);  \
+        dr = fmax(dr, fabs(r_)); npx = fmax(npx, fabs(px_)); naty = fmax(naty, fabs(aty_)); \
+        drs = fmax(drs, cd_ * fabs(r_)); npxs = fmax(npxs, cd_ * fabs(px_));          \
+        natys = fmax(natys, cd_ * fabs(aty_));                                        \
+    }
+                    double yD0 = 0, yD1 = 0, yD2 = 0;
+                    const double *w9 = ws + 9 * (size_t)(st.live ? i : 0);
+                    if (st.live) {
+                        double aD0 = -st.xa, aD1 = -st.xb, aD2 = -st.xc;
+                        if (!st.first) {
+                            const double at = s.tr()[st.posp], bt = s.tr()[st.posp + 1], ct = s.tr()[st.posp + 2];
+                            const double ut = s.tr()[st.posup];
+                            aD0 += at + st.dst * bt;
+                            aD1 += st.qt * at + bt + st.dst * ct;
+                            aD2 += ct + st.dst * ut;
+                        }
+                        const double e4 = st.xa + d4 * st.xb, e2 = st.xa + d2 * st.xb;
+                        PQP_ROW(aD0, st.vD0, st.b0, st.b0, w9[0])
+                        PQP_ROW(aD1, st.vD1, st.b1, st.b1, w9[1])
+                        PQP_ROW(aD2, st.vD2, st.b2, st.b2, w9[2])
+                        PQP_ROW(st.xc, st.vKB, -pm.kmax, pm.kmax, w9[3])
+                        PQP_ROW(st.xs, st.vSB, 0.0, pm.margin, w9[4])
+                        PQP_ROW(st.xa + d1 * st.xb, st.vH1, st.lH1, st.uH1, w9[5])
+                        PQP_ROW(st.xa + d3 * st.xb, st.vH3, st.lH3, st.uH3, w9[6])
+                        PQP_ROW(e4 - st.xs, st.vS4m, -kOsqpInfty, st.uS4m, w9[7])
+                        PQP_ROW(e4 + st.xs, st.vS4p, st.lS4p, kOsqpInfty, w9[7])
+                        PQP_ROW(e2 - st.xs, st.vS2m, -kOsqpInfty, st.uS2m, w9[8])
+                        PQP_ROW(e2 + st.xs, st.vS2p, st.lS2p, kOsqpInfty, w9[8])
+                        if (st.last) {
+                            PQP_ROW(st.xa, vEY, -1.0, 1.0, ws[9 * (size_t)N + ch])
+                            PQP_ROW(st.xb, vEH, lEH, uEH, ws[9 * (size_t)N + ch + 1])
+                        }
+                        yD0 = PQP_DUAL(st.vD0, st.b0, st.b0, st.WD0);
+                        yD1 = PQP_DUAL(st.vD1, st.b1, st.b1, st.WD1);
+                        yD2 = PQP_DUAL(st.vD2, st.b2, st.b2, st.WD2);
+                        s.ex(0)[i] = yD0; s.ex(1)[i] = yD1; s.ex(2)[i] = yD2;
+                    }
+                    if (ub.live) PQP_ROW(ub.x, ub.v, -kOsqpInfty, kOsqpInfty, ws[9 * (size_t)N + tid])
+                    c.sync();
+                    if (st.live) {
+                        const double yKB = PQP_DUAL(st.vKB, -pm.kmax, pm.kmax, st.WKB);
+                        const double ySB = PQP_DUAL(st.vSB, 0.0, pm.margin, st.WSB);
+                        const double yH1 = PQP_DUAL(st.vH1, st.lH1, st.uH1, st.WH1);
+                        const double yH3 = PQP_DUAL(st.vH3, st.lH3, st.uH3, st.WH3);
+                        const double y4m = PQP_DUAL(st.vS4m, -kOsqpInfty, st.uS4m, st.WS4);
+                        const double y4p = PQP_DUAL(st.vS4p, st.lS4p, kOsqpInfty, st.WS4);
+                        const double y2m = PQP_DUAL(st.vS2m, -kOsqpInfty, st.uS2m, st.WS2);
+                        const double y2p = PQP_DUAL(st.vS2p, st.lS2p, kOsqpInfty, st.WS2);
+                        const double s4 = y4m + y4p, s2 = y2m + y2p;
+                        double ra = -yD0 + yH1 + yH3 + s4 + s2;
+                        double rb = -yD1 + d1 * yH1 + d3 * yH3 + d4 * s4 + d2 * s2;
+                        double rc = -yD2 + yKB;
+                        const double rs = ySB - y4m + y4p - y2m + y2p;
+                        if (!st.last) {
+                            const double n0 = s.ex(0)[i + 1], n1 = s.ex(1)[i + 1], n2 = s.ex(2)[i + 1];
+                            ra += n0 + st.q10 * n1;
+                            rb += st.ds * n0 + n1;
+                            rc += st.ds * n1 + n2;
+                        } else {
+                            ra += PQP_DUAL(vEY, -1.0, 1.0, WEY);
+                            rb += PQP_DUAL(vEH, lEH, uEH, WEH);
+                        }
+                        const double *wD = ws + 9 * (size_t)N + ch + 2 + 4 * (size_t)i;
+                        PQP_VAR(pm.w_pq * st.xa, ra, wD[0])
+                        PQP_VAR(0.0, rb, wD[1])
+                        PQP_VAR(pm.w_c * st.xc, rc, wD[2])
+                        PQP_VAR(pm.w_s * st.xs, rs, wD[3])
+                    }
+                    if (ub.live) {
+                        double aty = PQP_DUAL(ub.v, -kOsqpInfty, kOsqpInfty, ub.W);
+                        for (int t = ub.t0; t <= ub.t1; ++t) aty += s.dsS()[t] * s.ex(2)[t + 1];
+                        PQP_VAR((keep * pm.w_cr) * ub.x, aty, ws[13 * (size_t)N + ch + 2 + tid])
+                    }
+#undef PQP_ROW
+#undef PQP_DUAL
+#undef PQP_VAR
+                    pr = c.max(pr); nz = c.max(nz); nax = c.max(nax);
+                    prs = c.max(prs); nzs = c.max(nzs); naxs = c.max(naxs);
+                    dr = c.max(dr); npx = c.max(npx); naty = c.max(naty);
+                    drs = c.max(drs); npxs = c.max(npxs); natys = c.max(natys);
+                    pri_res = pr; dua_res = dr;
+                    pri_nrm = fmax(nz, nax); dua_nrm = fmax(npx, naty);
+                    if (can_check || iter == pm.max_iter) {
+                        if (pri_res > kOsqpInfty || dua_res > kOsqpInfty) status = PQP_NON_CVX;
+                        else if (pri_res < pm.eps_abs + pm.eps_rel * pri_nrm &&
+                                 dua_res < pm.eps_abs + pm.eps_rel * dua_nrm)
+                            status = PQP_SOLVED;
+                    }
+                    if (status == PQP_UNSOLVED && can_adapt) {
+                        const double pn = prs / (fmax(nzs, naxs) + 1e-10);
+                        const double dn = drs / (fmax(npxs, natys) + 1e-10);
+                        double rho_new = rho * sqrt(pn / (dn + 1e-10));
+                        rho_new = fmin(fmax(rho_new, kRhoMin), kRhoMax);
+                        if (rho_new > rho * pm.adaptive_rho_tolerance || rho_new < rho / pm.adaptive_rho_tolerance) {
+                            const double ratio = rho / rho_new;   // y is kept: w = E^-1 y / rho_row rescales
+                            double v, z;
+#define PQP_RESC(V, LO, HI) v = (V); z = clampd(v, (LO), (HI)); (V) = z + (v - z) * ratio;
+                            st.vD0 = st.b0 + (st.vD0 - st.b0) * ratio;
+                            st.vD1 = st.b1 + (st.vD1 - st.b1) * ratio;
+                            st.vD2 = st.b2 + (st.vD2 - st.b2) * ratio;
+                            PQP_RESC(st.vKB, -pm.kmax, pm.kmax)
+                            PQP_RESC(st.vSB, 0.0, pm.margin)
+                            PQP_RESC(st.vH1, st.lH1, st.uH1)
+                            PQP_RESC(st.vH3, st.lH3, st.uH3)
+                            PQP_RESC(st.vS4m, -kOsqpInfty, st.uS4m)
+                            PQP_RESC(st.vS4p, st.lS4p, kOsqpInfty)
+                            PQP_RESC(st.vS2m, -kOsqpInfty, st.uS2m)
+                            PQP_RESC(st.vS2p, st.lS2p, kOsqpInfty)
+                            PQP_RESC(vEY, -1.0, 1.0)
+                            PQP_RESC(vEH, lEH, uEH)
+#undef PQP_RESC
+                            rho = rho_new;
+                            c.sync();
+                            if (!refactor()) status = PQP_NON_CVX;
+                        }
+                    }
+                }
+            }
+            if (status == PQP_UNSOLVED) {
+                if (pri_res < 10 * pm.eps_abs + 10 * pm.eps_rel * pri_nrm &&
+                    dua_res < 10 * pm.eps_abs + 10 * pm.eps_rel * dua_nrm)
+                    status = PQP_SOLVED_INACCURATE;
+                else
+                    status = PQP_MAX_ITER_REACHED;
+            }
+        }
+        // ---- epilogue: getOptimizedPath, solver_kp_as_input.cpp:26-43
+        const bool has_sol = (status == PQP_SOLVED || status == PQP_SOLVED_INACCURATE || status == PQP_MAX_ITER_REACHED);
+        c.sync();
+        double *px = s.ex(0), *py = s.ex(1), *seg = s.ex(2);
+        if (st.live) {
+            double ey = qnan, ephi = qnan, kk = qnan;
+            if (has_sol) { ey = st.xa; ephi = st.xb; kk = st.xc; }
+            const double angle = ref[i].z;
+            const double new_angle = constraint_angle(angle + 1.57079632679489661923);
+            const double tx = ref[i].x + ey * cos(new_angle);
+            const double ty = ref[i].y + ey * sin(new_angle);
+            out[i].x = tx; out[i].y = ty; out[i].z = angle + ephi; out[i].k = kk;
+            out[i].v = 0.0; out[i].a = 0.0;
+            px[i] = tx;
+            py[i] = ty;
+            if (bv.out_frenet) {
+                double *f = bv.out_frenet + 3 * (size_t)(off + i);
+                f[0] = ey; f[1] = ephi; f[2] = kk;
+            }
+        }
+        c.sync();
+        if (st.live) {
+            double sg = 0.0;
+            if (i > 0) {
+                const double dx = px[i] - px[i - 1], dy = py[i] - py[i - 1];
+                sg = sqrt(dx * dx + dy * dy);
+            }
+            seg[i] = sg;
+        }
+        c.sync();
+        if (tid == 0) {
+            double acc = 0.0;  // sequential: same association order as the reference's running sum
+            for (int k = 0; k < N; ++k) {
+                acc += seg[k];
+                out[k].s = acc;
+            }
+            bv.status[prob] = status;
+            if (bv.iters) bv.iters[prob] = iter;
+        }
+        c.sync();
+    }
+#undef PQP_F
+};
+
+}  // namespace pqp

@@ -7,7 +7,7 @@
 #include <stdlib.h>
 #include <string.h>
 
-#include "../../path_optimizer_b200/csrc/pqp_kp_core2.cuh"
+#include "../../path_optimizer_b200/csrc/pqp_kp_core3.cuh"
 
 namespace {
 struct LaneArgs {
@@ -32,6 +32,9 @@ void *lane_main(void *p) {
     case 2: pqp::Kp2<10, 7>::solve_path(c, *a->prm, *a->bv, a->prob, sm, cap); break;
     case 3: pqp::Kp2<27, 7>::solve_path(c, *a->prm, *a->bv, a->prob, sm, cap); break;
     case 4: pqp::Kp2<49, 7>::solve_path(c, *a->prm, *a->bv, a->prob, sm, cap); break;
+    case 5: pqp::Kp3<17, 6, 4>::solve_path(c, *a->prm, *a->bv, a->prob, sm, cap); break;
+    case 6: pqp::Kp3<23, 7, 4>::solve_path(c, *a->prm, *a->bv, a->prob, sm, cap); break;
+    case 7: pqp::Kp3<27, 7, 8>::solve_path(c, *a->prm, *a->bv, a->prob, sm, cap); break;
     default: pqp::kp_solve_path(w, *a->prm, *a->bv, a->prob, sm, cap);   // generic core: one warp
     }
     return nullptr;
@@ -44,6 +47,8 @@ extern "C" int kp_emu_solve_batch(const pqp_params *params, int batch, const int
                                   const double *end_heading, pqp_state *out_states, double *out_frenet,
                                   int32_t *status, int32_t *iters, int smem_bytes, int variant, int nwarps) {
     if (variant == 0 || nwarps < 1) nwarps = 1;
+    if (variant == 5 || variant == 6) nwarps = 4;
+    if (variant == 7) nwarps = 8;
     pqp::DevParams prm = pqp::dev_params_from(*params);
     pqp::BatchView bv;
     bv.batch = batch; bv.n_points = n_points; bv.offsets = offsets; bv.ref = ref; bv.bounds = bounds;

@@ -19,6 +19,8 @@ def _variant_for(batch):
     nmax, kmax = int(batch["n_points"].max()), max(keeps)
     if kmax > 4:
         return 0
+    if kmax <= 3 and nmax <= 102:
+        return 5          # Kp3<17,6,4>  (thread-per-station production kernel)
     if kmax <= 3 and nmax <= 187:
         return 1          # Kp2<17,6>
     if kmax == 4 and nmax <= 125 and min(keeps) == 4:
@@ -83,7 +85,8 @@ def test_emu_generic_core_still_matches(oracle_params):
     _check(synth.curvy_corridors(2, n_points=[33, 70]), oracle_params, variant=0)
 
 
-@pytest.mark.parametrize("variant,n,ds", [(1, 187, 0.3), (2, 125, 0.25), (3, 200, 0.3), (4, 300, 0.3)])
+@pytest.mark.parametrize("variant,n,ds", [(1, 187, 0.3), (2, 125, 0.25), (3, 200, 0.3), (4, 300, 0.3),
+                                           (5, 102, 0.3), (6, 128, 0.25), (6, 77, 0.5), (7, 128, 0.3), (7, 150, 0.3)])
 def test_emu_shape_classes(oracle_params, variant, n, ds):
     b = synth.curvy_corridors(1, n)
     if ds != 0.3:
