@@ -149,6 +149,7 @@ def run_ours(args, rank, world, local_rank):
     total = B * N
     solver = BatchPathSolver(device=local_rank, max_batch=B, max_total_points=total)
     L = _lib.load()
+    KEEP = int(L.pqp_keep_control_steps(0, np.ascontiguousarray(batch["ref"][:N]).ctypes.data_as(C.c_void_p), N))
 
     def dev_bytes(arr):
         t = torch.from_numpy(np.frombuffer(np.ascontiguousarray(arr).tobytes(), dtype=np.uint8).copy())
@@ -167,7 +168,7 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.set_stream(stream)
 
     def device_step():
-        rc = L.pqp_solve_batch_device(solver._h, 0, B, total, N, 4, d_n.data_ptr(), d_off.data_ptr(), d_ref.data_ptr(),
+        rc = L.pqp_solve_batch_device(solver._h, 0, B, total, N, KEEP, KEEP, d_n.data_ptr(), d_off.data_ptr(), d_ref.data_ptr(),
                                       d_bounds.data_ptr(), d_x0.data_ptr(), d_end.data_ptr(), None, None,
                                       d_out.data_ptr(), d_frenet.data_ptr(), d_status.data_ptr(),
                                       d_iters.data_ptr(), C.c_void_p(stream.cuda_stream), None)
@@ -268,9 +269,9 @@ def run_ours(args, rank, world, local_rank):
             "gpu_launches": args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src,
-                         "kernel": "pqp_kp_solve_kernel", "algorithmic_bytes_per_launch": B * io_bytes_per_solve(N),
-                         "note": "state is SM-resident by design: compulsory HBM traffic is I/O only (SURVEY 8d); "
-                                 "the kernel is bound by FP64 issue / dependent-chain latency, see DESIGN.md"},
+                         "kernel": "pqp_kp3_solve_kernel<17,6,4>", "algorithmic_bytes_per_launch": B * io_bytes_per_solve(N),
+                         "note": "state is SM-resident by design: compulsory HBM traffic is I/O only (SURVEY 8d); the kernel is "
+                                 "bound by dependent-issue latency at 8 warps/SM, see profiles/r01_phase_cycles.md"},
             "clocks": clocks, "solved_fraction": int(solved.item()) / (world * B), "wall_ms_per_step": wall_ms / args.steps,
         }
         if world == 1:

@@ -213,12 +213,12 @@ int pqp_solve_batch(pqp_handle *h, int formulation, int batch,
  * (e.g. produced by the clearance kernel or owned by the host framework).  `offsets` is the
  * exclusive prefix sum of n_points with offsets[batch] = sum.  The host cannot see the device-side
  * n_points, so the caller states upper bounds used to size shared memory: `max_n_points` >= every
- * n_points[b] and `max_keep` >= every path's keep_control_steps (pass 0 for "unknown": the largest
- * the device can take).  A path that exceeds them reports PQP_INVALID_PROBLEM.  Asynchronous on `stream`
+ * n_points[b], and `min_keep` <= keep_control_steps <= `max_keep` for every path (pass 0, 0 for
+ * "unknown": 1..4 is assumed).  A path that exceeds them reports PQP_INVALID_PROBLEM.  Asynchronous on `stream`
  * (a cudaStream_t, or NULL for the handle's own stream); no host synchronisation is done
  * unless `stats` is non-NULL.  No reference counterpart (the reference has no device). */
 int pqp_solve_batch_device(pqp_handle *h, int formulation, int batch, int total_points,
-                           int max_n_points, int max_keep,
+                           int max_n_points, int min_keep, int max_keep,
                            const int32_t *d_n_points, const int32_t *d_offsets,
                            const pqp_state *d_ref,
                            const pqp_station_bounds *d_bounds,

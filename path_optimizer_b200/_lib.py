@@ -35,7 +35,7 @@ def load():
     L.pqp_destroy.restype = None
     L.pqp_set_params.argtypes = [vp, C.POINTER(Params)]
     L.pqp_solve_batch.argtypes = [vp, C.c_int, C.c_int] + [vp] * 11 + [C.POINTER(Stats)]
-    L.pqp_solve_batch_device.argtypes = [vp] + [C.c_int] * 5 + [vp] * 13 + [C.POINTER(Stats)]
+    L.pqp_solve_batch_device.argtypes = [vp] + [C.c_int] * 6 + [vp] * 13 + [C.POINTER(Stats)]
     L.pqp_last_error.restype = C.c_char_p
     L.pqp_version.restype = C.c_char_p
     L.pqp_max_points.argtypes = [vp, C.c_int]

@@ -55,9 +55,12 @@ pqp_kp2_solve_kernel(const __grid_constant__ pqp::DevParams prm, const __grid_co
     pqp::Kp2<IMAX, BW>::solve_path(c, prm, bv, prob, pqp_smem + 32, (size_t)smem_doubles - 32);
 }
 
+#ifndef PQP_KP3_MINBLOCKS
+#define PQP_KP3_MINBLOCKS 2
+#endif
 // Thread-per-station kernels (pqp_kp_core3.cuh): NW warps per path, N <= 32*NW stations.
 template <int IMAX, int BW, int NW>
-__global__ void __launch_bounds__(NW * 32, NW <= 4 ? 3 : 1)
+__global__ void __launch_bounds__(NW * 32, NW <= 4 ? PQP_KP3_MINBLOCKS : 1)
 pqp_kp3_solve_kernel(const __grid_constant__ pqp::DevParams prm, const __grid_constant__ pqp::BatchView bv,
                      const int32_t *__restrict__ order, int smem_doubles) {
     extern __shared__ double pqp_smem[];
@@ -302,7 +305,7 @@ static int launch_variant(pqp_handle *h, int v, const pqp::BatchView &bv, int co
 }
 
 int pqp_solve_batch_device(pqp_handle *h, int formulation, int batch, int total_points,
-                           int max_n_points, int max_keep, const int32_t *d_n_points, const int32_t *d_offsets, const pqp_state *d_ref,
+                           int max_n_points, int min_keep, int max_keep, const int32_t *d_n_points, const int32_t *d_offsets, const pqp_state *d_ref,
                            const pqp_station_bounds *d_bounds, const double *d_x0, const double *d_end_heading,
                            const double *d_max_k, const double *d_max_kp, pqp_state *d_out_states,
                            double *d_out_frenet, int32_t *d_status, int32_t *d_iters, void *stream,
@@ -327,18 +330,20 @@ int pqp_solve_batch_device(pqp_handle *h, int formulation, int batch, int total_
     // The host does not see n_points / keep here: the kernel shape class and the shared memory are
     // chosen from the caller's bounds; a path that does not fit reports PQP_INVALID_PROBLEM.
     bv.workspace = h->d_ws;
+    bv.debug = nullptr;
     if (batch > h->max_batch || total_points > h->max_total) {
         set_err("batch / total_points exceed what the handle was created for (workspace size)");
         return PQP_ERR_CAPACITY;
     }
     const int nmax = max_n_points >= 2 ? max_n_points : std::min(h->max_total, 400);
     const int k_hi = (max_keep >= 1) ? std::min(max_keep, 10) : 4;
+    const int k_lo = (min_keep >= 1) ? std::min(min_keep, k_hi) : 1;
     int v = -1;
     size_t smem = 0;
     for (int cand = 0; cand < kNumVariants && v < 0; ++cand) {
         bool all = true;
         size_t need = 0;
-        for (int k = 1; k <= k_hi; ++k) {
+        for (int k = k_lo; k <= k_hi; ++k) {
             if (!kVariants[cand].fits(nmax, k)) { all = false; break; }
             need = std::max(need, kVariants[cand].smem(nmax, k));
         }
@@ -438,6 +443,13 @@ int pqp_solve_batch(pqp_handle *h, int formulation, int batch, const int32_t *n_
     bv.out_frenet = out_frenet ? h->d_frenet : nullptr;
     bv.status = h->d_status; bv.iters = h->d_iters;
     bv.workspace = h->d_ws;
+    bv.debug = nullptr;
+#ifdef PQP_PHASE_TIMING
+    static long long *d_dbg = nullptr;
+    if (!d_dbg) cudaMalloc(&d_dbg, sizeof(long long) * 32 * 65536);
+    cudaMemsetAsync(d_dbg, 0, sizeof(long long) * 24 * (size_t)batch, st);
+    bv.debug = d_dbg;
+#endif
     int launches = 0;
     for (int v = 0; v < kNumVariants; ++v) {
         if (!count_v[v]) continue;
@@ -455,6 +467,26 @@ int pqp_solve_batch(pqp_handle *h, int formulation, int batch, const int32_t *n_
     if (it_dst) PQP_CUDA(cudaMemcpyAsync(it_dst, h->d_iters, B * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     PQP_CUDA(cudaEventRecord(h->ev[3], st));
     PQP_CUDA(cudaStreamSynchronize(st));
+#ifdef PQP_PHASE_TIMING
+    {
+        std::vector<long long> dbg(24 * (size_t)batch);
+        cudaMemcpy(dbg.data(), bv.debug, dbg.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+        const char *names[10] = {"a1 gD+sync", "a2 rhs+sync", "b1 g+sync", "b2 work", "b2 wait", "b3 xt+2sync", "c update", "-", "-", "d check/rest"};
+        for (int wsel = 0; wsel < 2; ++wsel) {
+            double tot[10] = {0}; double its = 0;
+            for (int b = 0; b < batch; ++b) { for (int k = 0; k < 10; ++k) tot[k] += (double)dbg[(2 * (size_t)b + wsel) * 12 + k]; its += (double)dbg[(2 * (size_t)b + wsel) * 12 + 10]; }
+            fprintf(stderr, "[phase cycles per iteration, warp %d]", wsel);
+            double sum = 0;
+            for (int k = 0; k < 10; ++k) if (names[k][0] != '-') { fprintf(stderr, " %s=%.0f", names[k], tot[k] / its); sum += tot[k] / its; }
+            fprintf(stderr, " | total=%.0f\n", sum);
+        }
+        std::vector<long long> g(8 * (size_t)batch);
+        cudaMemcpy(g.data(), bv.debug + 24 * 65536, g.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+        double tg[8] = {0};
+        for (int b = 0; b < batch; ++b) for (int k = 0; k < 8; ++k) tg[k] += (double)g[8 * (size_t)b + k] / batch;
+        fprintf(stderr, "[cycles per path] setup=%.0f scale=%.0f refactor(all)=%.0f checks(all)=%.0f epilogue=%.0f loop-other=%.0f\n", tg[0], tg[1], tg[2], tg[3], tg[4], tg[5]);
+    }
+#endif
     if (stats) {
         PQP_CUDA(cudaEventElapsedTime(&stats->h2d_ms, h->ev[0], h->ev[1]));
         PQP_CUDA(cudaEventElapsedTime(&stats->kernel_ms, h->ev[1], h->ev[2]));

@@ -53,7 +53,7 @@ extern "C" int kp_emu_solve_batch(const pqp_params *params, int batch, const int
     pqp::BatchView bv;
     bv.batch = batch; bv.n_points = n_points; bv.offsets = offsets; bv.ref = ref; bv.bounds = bounds;
     bv.x0 = x0; bv.end_heading = end_heading; bv.out_states = out_states; bv.out_frenet = out_frenet;
-    bv.status = status; bv.iters = iters;
+    bv.status = status; bv.iters = iters; bv.debug = nullptr;
     const size_t ws_n = pqp::kp2_ws_doubles((size_t)offsets[batch], (size_t)batch);
     bv.workspace = (double *)malloc(ws_n * sizeof(double));
     for (size_t k = 0; k < ws_n; ++k) bv.workspace[k] = nan("");
