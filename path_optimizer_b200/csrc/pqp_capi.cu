@@ -52,7 +52,7 @@ pqp_kp2_solve_kernel(const __grid_constant__ pqp::DevParams prm, const __grid_co
     int prob = blockIdx.x;
     if (order) prob = order[prob];
     pqp::Cta c{pqp::Warp(), pqp::CtaSync(), (int)(threadIdx.x >> 5), kNW, pqp_smem};
-    pqp::Kp2<IMAX, BW>::solve_path(c, prm, bv, prob, pqp_smem + 32, (size_t)smem_doubles - 32);
+    pqp::Kp2<IMAX, BW>::solve_path(c, prm, bv, prob, pqp_smem + 128, (size_t)smem_doubles - 128);
 }
 
 #ifndef PQP_KP3_MINBLOCKS
@@ -67,7 +67,7 @@ pqp_kp3_solve_kernel(const __grid_constant__ pqp::DevParams prm, const __grid_co
     int prob = blockIdx.x;
     if (order) prob = order[prob];
     pqp::Cta c{pqp::Warp(), pqp::CtaSync(), (int)(threadIdx.x >> 5), NW, pqp_smem};
-    pqp::Kp3<IMAX, BW, NW>::solve_path(c, prm, bv, prob, pqp_smem + 32, (size_t)smem_doubles - 32);
+    pqp::Kp3<IMAX, BW, NW>::solve_path(c, prm, bv, prob, pqp_smem + 128, (size_t)smem_doubles - 128);
 }
 
 // Shape classes.  keep_control_steps <= 4 (station spacing >= 0.24 m) maps onto one of the Kp2
@@ -79,7 +79,7 @@ struct Variant {
     bool (*fits)(int n, int keep);
 };
 template <int IMAX, int BW> size_t v_smem(int n, int keep) {
-    return (32 + pqp::Kp2<IMAX, BW>::smem_doubles(pqp::Kp2<IMAX, BW>::dims(n, keep))) * sizeof(double);
+    return (128 + pqp::Kp2<IMAX, BW>::smem_doubles(pqp::Kp2<IMAX, BW>::dims(n, keep))) * sizeof(double);
 }
 template <int IMAX, int BW> bool v_fits(int n, int keep) {
     return keep <= 10 && pqp::Kp2<IMAX, BW>::fits(pqp::kp2_dims(n, keep));
@@ -87,7 +87,7 @@ template <int IMAX, int BW> bool v_fits(int n, int keep) {
 size_t g_smem(int n, int keep) { return pqp::kp_smem_doubles(pqp::kp_dims(n, keep)) * sizeof(double); }
 bool g_fits(int, int keep) { return keep <= 10; }
 template <int IMAX, int BW, int NW> size_t v3_smem(int n, int keep) {
-    return (32 + pqp::Kp3<IMAX, BW, NW>::smem_doubles(pqp::Kp3<IMAX, BW, NW>::dims(n, keep))) * sizeof(double);
+    return (128 + pqp::Kp3<IMAX, BW, NW>::smem_doubles(pqp::Kp3<IMAX, BW, NW>::dims(n, keep))) * sizeof(double);
 }
 template <int IMAX, int BW, int NW> bool v3_fits(int n, int keep) { return pqp::Kp3<IMAX, BW, NW>::fits(n, keep); }
 #define PQP_VARIANT3(I, B, W) {I, B, W * 32, (const void *)pqp_kp3_solve_kernel<I, B, W>, v3_smem<I, B, W>, v3_fits<I, B, W>}

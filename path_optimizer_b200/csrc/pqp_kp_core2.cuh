@@ -203,21 +203,32 @@ struct Kp2 {
         double y[IMAX];
 #pragma unroll
         for (int k = 0; k < IMAX; ++k) y[k] = vec[k * vst];
+        // forward: y[k] -= sum_d L[k][k-d] y[k-d].  Only the d = 1 term depends on the pivot just
+        // computed, so the other terms are accumulated in two independent partial sums first and the
+        // serial chain is ONE DFMA per pivot (instead of BW).
 #pragma unroll
         for (int k = 1; k < IMAX; ++k) {
-            double acc = y[k];
+            double p0 = y[k], p1 = 0.0;
 #pragma unroll
-            for (int dd = BW; dd >= 1; --dd)
-                if (k - dd >= 0) acc -= PQP_F(k, dd) * y[k - dd];
-            y[k] = acc;
+            for (int dd = BW; dd >= 2; --dd)
+                if (k - dd >= 0) {
+                    if (dd & 1) p1 -= PQP_F(k, dd) * y[k - dd];
+                    else p0 -= PQP_F(k, dd) * y[k - dd];
+                }
+            y[k] = (p0 + p1) - PQP_F(k, 1) * y[k - 1];
         }
 #pragma unroll
         for (int k = IMAX - 1; k >= 0; --k) {
-            double acc = y[k] * PQP_F(k, 0);
+            double p0 = y[k] * PQP_F(k, 0), p1 = 0.0;
 #pragma unroll
-            for (int dd = BW; dd >= 1; --dd)
-                if (k + dd < IMAX) acc -= PQP_F(k + dd, dd) * y[k + dd];
-            y[k] = acc;
+            for (int dd = BW; dd >= 2; --dd)
+                if (k + dd < IMAX) {
+                    if (dd & 1) p1 -= PQP_F(k + dd, dd) * y[k + dd];
+                    else p0 -= PQP_F(k + dd, dd) * y[k + dd];
+                }
+            double r = p0 + p1;
+            if (k + 1 < IMAX) r -= PQP_F(k + 1, 1) * y[k + 1];
+            y[k] = r;
         }
 #pragma unroll
         for (int k = 0; k < IMAX; ++k) vec[k * vst] = y[k];
@@ -228,21 +239,32 @@ struct Kp2 {
         double y[IMAX];
 #pragma unroll
         for (int k = 0; k < IMAX; ++k) y[k] = in[k];
+        // forward: y[k] -= sum_d L[k][k-d] y[k-d].  Only the d = 1 term depends on the pivot just
+        // computed, so the other terms are accumulated in two independent partial sums first and the
+        // serial chain is ONE DFMA per pivot (instead of BW).
 #pragma unroll
         for (int k = 1; k < IMAX; ++k) {
-            double acc = y[k];
+            double p0 = y[k], p1 = 0.0;
 #pragma unroll
-            for (int dd = BW; dd >= 1; --dd)
-                if (k - dd >= 0) acc -= PQP_F(k, dd) * y[k - dd];
-            y[k] = acc;
+            for (int dd = BW; dd >= 2; --dd)
+                if (k - dd >= 0) {
+                    if (dd & 1) p1 -= PQP_F(k, dd) * y[k - dd];
+                    else p0 -= PQP_F(k, dd) * y[k - dd];
+                }
+            y[k] = (p0 + p1) - PQP_F(k, 1) * y[k - 1];
         }
 #pragma unroll
         for (int k = IMAX - 1; k >= 0; --k) {
-            double acc = y[k] * PQP_F(k, 0);
+            double p0 = y[k] * PQP_F(k, 0), p1 = 0.0;
 #pragma unroll
-            for (int dd = BW; dd >= 1; --dd)
-                if (k + dd < IMAX) acc -= PQP_F(k + dd, dd) * y[k + dd];
-            y[k] = acc;
+            for (int dd = BW; dd >= 2; --dd)
+                if (k + dd < IMAX) {
+                    if (dd & 1) p1 -= PQP_F(k + dd, dd) * y[k + dd];
+                    else p0 -= PQP_F(k + dd, dd) * y[k + dd];
+                }
+            double r = p0 + p1;
+            if (k + 1 < IMAX) r -= PQP_F(k + 1, 1) * y[k + 1];
+            y[k] = r;
         }
 #pragma unroll
         for (int k = 0; k < IMAX; ++k) outv[k] = y[k];

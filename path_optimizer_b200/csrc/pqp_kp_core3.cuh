@@ -71,14 +71,14 @@ struct Kp3 {
         PQP_DEV double *dsS() const { return ex(6); }                     // ds per station     [kT]
         PQP_DEV double *gS() const { return ex(7); }                      // separator rhs      [nS <= kT]
         PQP_DEV double *fac() const { return ex(8); }                     // [IMAX*(BW+1)*M]
-        PQP_DEV double *T() const { return fac() + IMAX * (BW + 1) * M; } // spikes [(k*6+c)*M + p]
-        PQP_DEV double *Sinv() const { return T() + IMAX * 6 * M; }       // [nS*nS]
+        PQP_DEV double *T() const { return fac() + IMAX * (BW + 1) * M; } // spikes T[c][pos], c < 6: [6*nv]
+        PQP_DEV double *Sinv() const { return T() + 6 * nv; }             // [nS*nS]
         PQP_DEV double *red() const { return Sinv() + nS * nS; }          // [kRed2*M] + blocks [27*M]
         PQP_DEV double *blk() const { return red() + kRed2 * M; }         // A|C|Off per chunk [27*M]
         PQP_DEV double *cpl() const { return blk() + 27 * M; }            // coupling coefs [12*M]
     };
     PQP_HD static size_t smem_doubles(const Kp3Dims &d) {
-        return 2 * (size_t)d.nv + 8 * (size_t)kT + (size_t)IMAX * (BW + 1) * d.M + (size_t)IMAX * 6 * d.M +
+        return 2 * (size_t)d.nv + 8 * (size_t)kT + (size_t)IMAX * (BW + 1) * d.M + 6 * (size_t)d.nv +
                (size_t)d.nS * d.nS + (size_t)(kRed2 + 27 + 12) * d.M;
     }
 
@@ -454,7 +454,7 @@ struct Kp3 {
                 int ka1 = 0, kul = 0, kat = 0, kur = 0;
                 bool has_int = false, has_right = false;
                 double lN0 = 0, lN1 = 0, lN2 = 0, lds = 0, lq = 0, rW0 = 0, rW1 = 0, rW2 = 0, rds = 0, rq = 0;
-                double *tcol = s.T() + sp_p;   // element (k, col) at tcol[(k*6+col)*Mst]
+                double *tcol = s.T() + sp_c * s.nv + sp_p * d.CS + 3;   // spike column: element k at tcol[k]
                 if (sp_act) {
                     const int e = sp_p * L, e2 = e + L;
                     const int g0 = kp_gx(ka, e);
@@ -479,11 +479,11 @@ struct Kp3 {
                         if (home > N - 1) home = N - 1;
                         kur = (home / L) * d.CS + (kp_gu(ka, j) - kp_gx(ka, (home / L) * L)) - lo_p;
                     }
-#pragma unroll 1
-                    for (int k = 0; k < IMAX; ++k) tcol[(k * 6 + sp_c) * Mst] = 0.0;
+#pragma unroll
+                    for (int k = 0; k < IMAX; ++k) tcol[k] = 0.0;
                     const bool colok = (sp_c < 3) ? has_int : has_right;
                     if (colok) {
-#define PQP_TC(k) tcol[((k) * 6 + sp_c) * Mst]
+#define PQP_TC(k) tcol[(k)]
                         if (sp_c == 0) { PQP_TC(ka1) += -lN0; PQP_TC(ka1 + 1) += -lN1 * lq; }
                         else if (sp_c == 1) { PQP_TC(ka1) += -lN0 * lds; PQP_TC(ka1 + 1) += -lN1; }
                         else if (sp_c == 2) { PQP_TC(ka1 + 1) += -lN1 * lds; PQP_TC(ka1 + 2) += -lN2; PQP_TC(kul) += lN2 * lds; }
@@ -491,7 +491,7 @@ struct Kp3 {
                         else if (sp_c == 4) { PQP_TC(kat) += -rW1 * rq; PQP_TC(kat + 1) += -rW1; PQP_TC(kat + 2) += -rW1 * rds; }
                         else { PQP_TC(kat + 2) += -rW2; PQP_TC(kur) += -rW2 * rds; }
 #undef PQP_TC
-                        K2::local_solve(tcol + sp_c * Mst, 6 * Mst, s.fac() + sp_p, Mst);
+                        K2::local_solve(tcol, 1, s.fac() + sp_p, Mst);
                     }
                 }
                 c.sync();
@@ -500,7 +500,7 @@ struct Kp3 {
                     double tl0 = 0, tl1 = 0, tl2 = 0, tr0 = 0, tr1 = 0, tr2 = 0;
                     const bool colok = (sp_c < 3) ? has_int : has_right;
                     if (colok) {
-#define PQP_TC(k) tcol[((k) * 6 + sp_c) * Mst]
+#define PQP_TC(k) tcol[(k)]
                         if (has_int) {
                             const double wa = PQP_TC(ka1), wb = PQP_TC(ka1 + 1), wc = PQP_TC(ka1 + 2), wu = PQP_TC(kul);
                             tl0 = -lN0 * wa - lN1 * lq * wb;
@@ -626,10 +626,10 @@ struct Kp3 {
                 c.sync();
                 double tsl = 0.0;   // x-tilde of the slack (decouples exactly)
                 if (st.live) {
-                    const double gKB = st.WKB * (2.0 * clampd(st.vKB, -pm.kmax, pm.kmax) - st.vKB);
-                    const double gSB = st.WSB * (2.0 * clampd(st.vSB, 0.0, pm.margin) - st.vSB);
-                    const double gH1 = st.WH1 * (2.0 * clampd(st.vH1, st.lH1, st.uH1) - st.vH1);
-                    const double gH3 = st.WH3 * (2.0 * clampd(st.vH3, st.lH3, st.uH3) - st.vH3);
+                    const double gKB = st.WKB * (2.0 * clamp2(st.vKB, -pm.kmax, pm.kmax) - st.vKB);
+                    const double gSB = st.WSB * (2.0 * clamp2(st.vSB, 0.0, pm.margin) - st.vSB);
+                    const double gH1 = st.WH1 * (2.0 * clamp2(st.vH1, st.lH1, st.uH1) - st.vH1);
+                    const double gH3 = st.WH3 * (2.0 * clamp2(st.vH3, st.lH3, st.uH3) - st.vH3);
                     const double g4m = st.WS4 * (2.0 * fmin(st.vS4m, st.uS4m) - st.vS4m);
                     const double g4p = st.WS4 * (2.0 * fmax(st.vS4p, st.lS4p) - st.vS4p);
                     const double g2m = st.WS2 * (2.0 * fmin(st.vS2m, st.uS2m) - st.vS2m);
@@ -645,8 +645,8 @@ struct Kp3 {
                         rb += st.ds * n0 + n1;
                         rc += st.ds * n1 + n2;
                     } else {
-                        ra += WEY * (2.0 * clampd(vEY, -1.0, 1.0) - vEY);
-                        rb += WEH * (2.0 * clampd(vEH, lEH, uEH) - vEH);
+                        ra += WEY * (2.0 * clamp2(vEY, -1.0, 1.0) - vEY);
+                        rb += WEH * (2.0 * clamp2(vEH, lEH, uEH) - vEH);
                     }
                     s.tr()[st.pos] = st.sga * st.xa + ra;
                     s.tr()[st.pos + 1] = st.sgb * st.xb + rb;
@@ -654,26 +654,32 @@ struct Kp3 {
                     tsl = (st.sgs * st.xs + rs) * st.ksinv;
                 }
                 if (ub.live) {
-                    double acc = ub.sg * ub.x + ub.W * (2.0 * clampd(ub.v, -kOsqpInfty, kOsqpInfty) - ub.v);
+                    double acc = ub.sg * ub.x + ub.W * (2.0 * clamp2(ub.v, -kOsqpInfty, kOsqpInfty) - ub.v);
                     for (int t = ub.t0; t <= ub.t1; ++t) acc += s.dsS()[t] * s.ex(2)[t + 1];
                     s.tr()[ub.pos] = acc;
                 }
                 c.sync();
-                // ---- (b1) separator rhs g = r_S - T' r_I  (threads 0..3M-1)
+                // ---- (b1) separator rhs g = r_S - T' r_I  (threads 0..3M-1; p fastest -> unit stride, conflict-free)
                 if (tid < nS) {
-                    const int p = tid / 3, r = tid % 3;
-                    double acc = s.tr()[p * d.CS + r];
-                    const double *Tl = s.T() + p;
+                    const int r = tid / M, p = tid - r * M;
                     const double *rI = s.tr() + p * d.CS + 3;
+                    const double *Tl = s.T() + r * s.nv + p * d.CS + 3;
+                    double a0 = rI[r - 3], a1 = 0.0, a2 = 0.0, a3 = 0.0;
 #pragma unroll
-                    for (int k = 0; k < IMAX; ++k) acc -= Tl[(k * 6 + r) * Mst] * rI[k];
-                    if (p > 0) {
-                        const double *Tr = s.T() + (p - 1);
-                        const double *rJ = s.tr() + (p - 1) * d.CS + 3;
-#pragma unroll
-                        for (int k = 0; k < IMAX; ++k) acc -= Tr[(k * 6 + 3 + r) * Mst] * rJ[k];
+                    for (int k = 0; k < IMAX; ++k) {
+                        if (k & 1) a1 -= Tl[k] * rI[k];
+                        else a0 -= Tl[k] * rI[k];
                     }
-                    s.gS()[tid] = acc;
+                    if (p > 0) {
+                        const double *Tr = Tl + 3 * s.nv - d.CS;
+                        const double *rJ = rI - d.CS;
+#pragma unroll
+                        for (int k = 0; k < IMAX; ++k) {
+                            if (k & 1) a3 -= Tr[k] * rJ[k];
+                            else a2 -= Tr[k] * rJ[k];
+                        }
+                    }
+                    s.gS()[3 * p + r] = (a0 + a1) + (a2 + a3);
                 }
                 c.sync();
                 // ---- (b2) y = K_I^-1 r_I on warp 0  ||  x_S = Sinv g on the following warps
@@ -685,6 +691,7 @@ struct Kp3 {
                         const double *row = s.Sinv() + t;
                         const double *gS = s.gS();
                         double a0 = 0, a1 = 0, a2 = 0;
+#pragma unroll 4
                         for (int k = 0; k < nS; k += 3) {     // nS = 3M
                             a0 += row[k * nS] * gS[k];
                             a1 += row[(k + 1) * nS] * gS[k + 1];
@@ -696,29 +703,29 @@ struct Kp3 {
                 c.sync();
                 // ---- (b3) x-tilde: separators take x_S, interiors y - T [x_Sp ; x_Sq]
                 double ta = 0, tb = 0, tc = 0, tu = 0;
-#define PQP_TX(k) ((s.yv()[p * d.CS + 3 + (k)] - (Tp[((k) * 6 + 0) * Mst] * xl0 + Tp[((k) * 6 + 1) * Mst] * xl1 + Tp[((k) * 6 + 2) * Mst] * xl2)) \
-                   - (Tp[((k) * 6 + 3) * Mst] * xr0 + Tp[((k) * 6 + 4) * Mst] * xr1 + Tp[((k) * 6 + 5) * Mst] * xr2))
+#define PQP_TX(q) ((s.yv()[q] - (Tq[q] * xl0 + Tq[nvs + (q)] * xl1 + Tq[2 * nvs + (q)] * xl2)) \
+                   - (Tq[3 * nvs + (q)] * xr0 + Tq[4 * nvs + (q)] * xr1 + Tq[5 * nvs + (q)] * xr2))
                 if (st.live) {
                     const int p = i / L;
                     if (st.sep) {
                         ta = s.ex(3)[3 * p]; tb = s.ex(3)[3 * p + 1]; tc = s.ex(3)[3 * p + 2];
                     } else {
-                        const int k0 = st.pos - (p * d.CS + 3);
-                        const double *Tp = s.T() + p;
+                        const double *Tq = s.T();
+                        const int nvs = s.nv;
                         const double xl0 = s.ex(3)[3 * p], xl1 = s.ex(3)[3 * p + 1], xl2 = s.ex(3)[3 * p + 2];
                         double xr0 = 0, xr1 = 0, xr2 = 0;
                         if (p + 1 < M) { xr0 = s.ex(3)[3 * p + 3]; xr1 = s.ex(3)[3 * p + 4]; xr2 = s.ex(3)[3 * p + 5]; }
-                        ta = PQP_TX(k0); tb = PQP_TX(k0 + 1); tc = PQP_TX(k0 + 2);
+                        ta = PQP_TX(st.pos); tb = PQP_TX(st.pos + 1); tc = PQP_TX(st.pos + 2);
                     }
                 }
                 if (ub.live) {
                     const int p = ub.pos / d.CS;
-                    const int k0 = ub.pos - (p * d.CS + 3);
-                    const double *Tp = s.T() + p;
+                    const double *Tq = s.T();
+                    const int nvs = s.nv;
                     const double xl0 = s.ex(3)[3 * p], xl1 = s.ex(3)[3 * p + 1], xl2 = s.ex(3)[3 * p + 2];
                     double xr0 = 0, xr1 = 0, xr2 = 0;
                     if (p + 1 < M) { xr0 = s.ex(3)[3 * p + 3]; xr1 = s.ex(3)[3 * p + 4]; xr2 = s.ex(3)[3 * p + 5]; }
-                    tu = PQP_TX(k0);
+                    tu = PQP_TX(ub.pos);
                 }
 #undef PQP_TX
                 c.sync();   // everyone has consumed tr (rhs): publish x-tilde there for the neighbours
@@ -739,17 +746,17 @@ struct Kp3 {
                     st.vD0 += alpha * (zD0 - st.b0);
                     st.vD1 += alpha * (zD1 - st.b1);
                     st.vD2 += alpha * (zD2 - st.b2);
-                    st.vKB += alpha * (tc - clampd(st.vKB, -pm.kmax, pm.kmax));
-                    st.vSB += alpha * (tsl - clampd(st.vSB, 0.0, pm.margin));
-                    st.vH1 += alpha * ((ta + d1 * tb) - clampd(st.vH1, st.lH1, st.uH1));
-                    st.vH3 += alpha * ((ta + d3 * tb) - clampd(st.vH3, st.lH3, st.uH3));
+                    st.vKB += alpha * (tc - clamp2(st.vKB, -pm.kmax, pm.kmax));
+                    st.vSB += alpha * (tsl - clamp2(st.vSB, 0.0, pm.margin));
+                    st.vH1 += alpha * ((ta + d1 * tb) - clamp2(st.vH1, st.lH1, st.uH1));
+                    st.vH3 += alpha * ((ta + d3 * tb) - clamp2(st.vH3, st.lH3, st.uH3));
                     st.vS4m += alpha * ((e4 - tsl) - fmin(st.vS4m, st.uS4m));
                     st.vS4p += alpha * ((e4 + tsl) - fmax(st.vS4p, st.lS4p));
                     st.vS2m += alpha * ((e2 - tsl) - fmin(st.vS2m, st.uS2m));
                     st.vS2p += alpha * ((e2 + tsl) - fmax(st.vS2p, st.lS2p));
                     if (st.last) {
-                        vEY += alpha * (ta - clampd(vEY, -1.0, 1.0));
-                        vEH += alpha * (tb - clampd(vEH, lEH, uEH));
+                        vEY += alpha * (ta - clamp2(vEY, -1.0, 1.0));
+                        vEH += alpha * (tb - clamp2(vEH, lEH, uEH));
                     }
                     st.xa = alpha * ta + (1.0 - alpha) * st.xa;
                     st.xb = alpha * tb + (1.0 - alpha) * st.xb;
@@ -757,7 +764,7 @@ struct Kp3 {
                     st.xs = alpha * tsl + (1.0 - alpha) * st.xs;
                 }
                 if (ub.live) {
-                    ub.v += alpha * (tu - clampd(ub.v, -kOsqpInfty, kOsqpInfty));
+                    ub.v += alpha * (tu - clamp2(ub.v, -kOsqpInfty, kOsqpInfty));
                     ub.x = alpha * tu + (1.0 - alpha) * ub.x;
                 }
                 // ---- (d) residuals, termination, adaptive rho
@@ -775,13 +782,13 @@ struct Kp3 {
                     const double cinv = 1.0 / cost_c;
 #define PQP_ROW(AX, V, LO, HI, EE)                                                   \
     {                                                                                \
-        const double ax_ = (AX), v_ = (V), z_ = clampd(v_, (LO), (HI)), r_ = ax_ - z_; \
+        const double ax_ = (AX), v_ = (V), z_ = clamp2(v_, (LO), (HI)), r_ = ax_ - z_; \
         const double e_ = (EE);                                                      \
         pr = fmax(pr, fabs(r_)); nz = fmax(nz, fabs(z_)); nax = fmax(nax, fabs(ax_)); \
         prs = fmax(prs, e_ * fabs(r_)); nzs = fmax(nzs, e_ * fabs(z_));              \
         naxs = fmax(naxs, e_ * fabs(ax_));                                           \
     }
-#define PQP_DUAL(V, LO, HI, WW) ((WW) * ((V) - clampd((V), (LO), (HI))) * cinv)
+#define PQP_DUAL(V, LO, HI, WW) ((WW) * ((V) - clamp2((V), (LO), (HI))) * cinv)
 #define PQP_VAR(PX, ATY, DD)                                                          \
     {                                                                                 \
         const double px_ = (PX), aty_ = (ATY), r_ = px_ + aty_, cd_ = cost_c * (DD);  \
@@ -860,10 +867,12 @@ struct Kp3 {
 #undef PQP_ROW
 #undef PQP_DUAL
 #undef PQP_VAR
-                    pr = c.max(pr); nz = c.max(nz); nax = c.max(nax);
-                    prs = c.max(prs); nzs = c.max(nzs); naxs = c.max(naxs);
-                    dr = c.max(dr); npx = c.max(npx); naty = c.max(naty);
-                    drs = c.max(drs); npxs = c.max(npxs); natys = c.max(natys);
+                    {
+                        double red12[12] = {pr, nz, nax, prs, nzs, naxs, dr, npx, naty, drs, npxs, natys};
+                        c.max_n(red12, 12);
+                        pr = red12[0]; nz = red12[1]; nax = red12[2]; prs = red12[3]; nzs = red12[4]; naxs = red12[5];
+                        dr = red12[6]; npx = red12[7]; naty = red12[8]; drs = red12[9]; npxs = red12[10]; natys = red12[11];
+                    }
                     pri_res = pr; dua_res = dr;
                     pri_nrm = fmax(nz, nax); dua_nrm = fmax(npx, naty);
                     if (can_check || iter == pm.max_iter) {
@@ -880,7 +889,7 @@ struct Kp3 {
                         if (rho_new > rho * pm.adaptive_rho_tolerance || rho_new < rho / pm.adaptive_rho_tolerance) {
                             const double ratio = rho / rho_new;   // y is kept: w = E^-1 y / rho_row rescales
                             double v, z;
-#define PQP_RESC(V, LO, HI) v = (V); z = clampd(v, (LO), (HI)); (V) = z + (v - z) * ratio;
+#define PQP_RESC(V, LO, HI) v = (V); z = clamp2(v, (LO), (HI)); (V) = z + (v - z) * ratio;
                             st.vD0 = st.b0 + (st.vD0 - st.b0) * ratio;
                             st.vD1 = st.b1 + (st.vD1 - st.b1) * ratio;
                             st.vD2 = st.b2 + (st.vD2 - st.b2) * ratio;

@@ -113,7 +113,7 @@ struct Cta {
     Warp w;
     CtaSync cs;
     int wid, nw;
-    double *scratch;   // >= 32 doubles of shared memory
+    double *scratch;   // >= 12 * nw doubles of shared memory (128 reserved)
     PQP_DEV int lane() const { return w.lane(); }
     PQP_DEV int tid() const { return wid * 32 + w.lane(); }
     PQP_DEV int nthreads() const { return nw * 32; }
@@ -140,6 +140,20 @@ struct Cta {
         for (int k = 1; k < nw; ++k) r += scratch[k];
         cs.sync();
         return r;
+    }
+    // n (<= 12) max-reductions at once: one shared-memory exchange and two barriers in total
+    PQP_DEV void max_n(double *v, int n) const {
+        for (int k = 0; k < n; ++k) v[k] = w.max(v[k]);
+        if (nw == 1) return;
+        if (w.lane() == 0)
+            for (int k = 0; k < n; ++k) scratch[wid * 12 + k] = v[k];
+        cs.sync();
+        for (int k = 0; k < n; ++k) {
+            double r = scratch[k];
+            for (int q = 1; q < nw; ++q) r = fmax(r, scratch[q * 12 + k]);
+            v[k] = r;
+        }
+        cs.sync();
     }
     PQP_DEV int any(int v) const {
         v = w.any(v);

@@ -25,8 +25,8 @@ void *lane_main(void *p) {
     LaneArgs *a = (LaneArgs *)p;
     pqp::Warp w{a->lane, a->sh};
     pqp::Cta c{w, pqp::CtaSync{a->cta}, a->wid, a->nw, a->smem};
-    double *sm = a->smem + 32;                 // first 32 doubles: CTA reduction scratch
-    const size_t cap = a->smem_doubles - 32;
+    double *sm = a->smem + 128;                // first 128 doubles: CTA reduction scratch
+    const size_t cap = a->smem_doubles - 128;
     switch (a->variant) {
     case 1: pqp::Kp2<17, 6>::solve_path(c, *a->prm, *a->bv, a->prob, sm, cap); break;
     case 2: pqp::Kp2<10, 7>::solve_path(c, *a->prm, *a->bv, a->prob, sm, cap); break;
