@@ -187,7 +187,8 @@ int pqp_set_params(pqp_handle *h, const pqp_params *params);
  *   x0               [batch][3] = {init offset, init heading error, start curvature}
  *                    (VehicleState::getInitError(), getStartState().k; solver_kp_as_input.cpp:143-147)
  *   end_heading      [batch] goal heading, VehicleState::getEndState().z (:196)
- *   max_k, max_kp    [sum n_points] / [sum ch]  KPC only (ReferencePath::getMaxKList/getMaxKpList); else NULL
+ *   max_k, max_kp    [sum n_points] each, KPC only (ReferencePath::getMaxKList / getMaxKpList, one entry per
+ *                    station; like the reference the solver reads the first ch entries of a path's max_kp); else NULL
  *   out_states       [sum n_points] optimized path: x, y, z(heading), k, s filled exactly as
  *                    getOptimizedPath does (solver_kp_as_input.cpp:26-43); v = a = 0
  *   out_frenet       optional [sum n_points][3] = (e_y, e_phi, kappa) raw QP solution

@@ -54,7 +54,7 @@ static void *worker(void *arg) {
         int st = oracle_solve_path(j->prm, j->formulation, n, j->ref + off, j->bounds + off,
                                    j->x0 + 3 * (size_t)b, j->end_heading[b],
                                    j->max_k ? j->max_k + off : NULL,
-                                   j->max_kp ? j->max_kp + j->ch_offsets[b] : NULL,
+                                   j->max_kp ? j->max_kp + off : NULL,
                                    j->out + off, j->frenet ? j->frenet + 3 * (size_t)off : NULL, &info);
         if (j->status) j->status[b] = st;
         if (j->iters) j->iters[b] = info.iters;

@@ -11,6 +11,9 @@
 #include <vector>
 
 #include "pqp_kp_core3.cuh"
+#include "pqp_gen_core.cuh"
+#include "pqp_forms.h"
+#include <thread>
 
 namespace {
 
@@ -39,6 +42,14 @@ pqp_kp_solve_kernel(const __grid_constant__ pqp::DevParams prm, const __grid_con
     if (order) prob = order[prob];
     pqp::Warp w;
     pqp::kp_solve_path(w, prm, bv, prob, pqp_smem, (size_t)smem_doubles);
+}
+
+// Generic banded-QP kernel ("K" and "KPC" formulations): one warp per path, sparse data from the host.
+__global__ void __launch_bounds__(32)
+pqp_gen_solve_kernel(const __grid_constant__ pqp::DevParams prm, const __grid_constant__ pqp::GenView gv, int smem_doubles) {
+    extern __shared__ double pqp_smem[];
+    pqp::Warp w;
+    pqp::gen_solve_qp(w, prm, gv, blockIdx.x, pqp_smem, (size_t)smem_doubles);
 }
 
 // Production kernels: one instantiation per (max interior size, half-bandwidth) shape class.
@@ -115,6 +126,7 @@ struct pqp_handle {
     int num_sms = 0;
     pqp_params params;
     pqp::DevParams dprm;
+    pqp::DevParams dprm_gen[2];
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     // device buffers for the host-pointer entry point
@@ -124,6 +136,9 @@ struct pqp_handle {
     double *d_x0 = nullptr, *d_end = nullptr, *d_frenet = nullptr, *d_ws = nullptr;
     // pinned host scratch for the small per-batch arrays
     int32_t *h_off = nullptr, *h_order = nullptr;
+    // generic-kernel staging (grow-only): one device blob + one pinned host blob
+    char *d_gen = nullptr, *h_gen = nullptr;
+    size_t gen_cap = 0;
 };
 
 extern "C" {
@@ -211,6 +226,7 @@ void pqp_destroy(pqp_handle *h) {
     cudaFree(h->d_ref); cudaFree(h->d_out); cudaFree(h->d_bounds);
     cudaFree(h->d_x0); cudaFree(h->d_end); cudaFree(h->d_frenet); cudaFree(h->d_ws);
     cudaFreeHost(h->h_off); cudaFreeHost(h->h_order);
+    cudaFree(h->d_gen); cudaFreeHost(h->h_gen);
     for (auto &e : h->ev) if (e) cudaEventDestroy(e);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -220,6 +236,7 @@ int pqp_set_params(pqp_handle *h, const pqp_params *params) {
     if (!h || !params) return PQP_ERR_ARG;
     h->params = *params;
     h->dprm = pqp::dev_params_from(*params);
+    h->dprm_gen[0] = h->dprm_gen[1] = h->dprm;
     return PQP_OK;
 }
 
@@ -257,6 +274,7 @@ int pqp_create(pqp_handle **out, const pqp_params *params, int device, int max_b
     // fails with cudaErrorNoKernelImageForDevice / InvalidDeviceFunction on anything but sm_100
     for (int v = 0; v < kNumVariants; ++v)
         PQP_TRY(cudaFuncSetAttribute(kVariants[v].fn, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin));
+    PQP_TRY(cudaFuncSetAttribute(pqp_gen_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin));
     PQP_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     for (auto &e : h->ev) PQP_TRY(cudaEventCreate(&e));
     const size_t B = (size_t)max_batch, T = (size_t)max_total_points;
@@ -317,7 +335,7 @@ int pqp_solve_batch_device(pqp_handle *h, int formulation, int batch, int total_
         return PQP_ERR_ARG;
     }
     if (formulation != PQP_FORM_KP) {
-        set_err("formulation not implemented on the device yet (KP only)");
+        set_err("K / KPC are assembled on the host: use pqp_solve_batch (host buffers) for them");
         return PQP_ERR_UNSUPPORTED;
     }
     if (batch == 0) return PQP_OK;
@@ -366,21 +384,154 @@ int pqp_solve_batch_device(pqp_handle *h, int formulation, int batch, int total_
     return PQP_OK;
 }
 
+// ---- "K" / "KPC": host assembles sparse band-ordered QPs, the generic kernel solves them ----------
+static int solve_batch_generic(pqp_handle *h, int formulation, int batch, const int32_t *n_points, const pqp_state *ref,
+                               const pqp_station_bounds *bounds, const double *x0, const double *end_heading,
+                               const double *max_k, const double *max_kp, pqp_state *out_states, double *out_frenet,
+                               int32_t *status, int32_t *iters, pqp_stats *stats) {
+    if (formulation == PQP_FORM_KPC && (!max_k || !max_kp)) {
+        set_err("KPC needs max_k and max_kp (ReferencePath::getMaxKList / getMaxKpList)");
+        return PQP_ERR_ARG;
+    }
+    std::vector<int64_t> off((size_t)batch + 1, 0);
+    for (int b = 0; b < batch; ++b) {
+        if (n_points[b] < 0) { set_err("negative n_points"); return PQP_ERR_ARG; }
+        off[b + 1] = off[b] + n_points[b];
+    }
+    if (off[batch] > h->max_total || batch > h->max_batch) { set_err("batch exceeds the handle's capacity"); return PQP_ERR_CAPACITY; }
+    std::vector<pqp::GenProblem> gp((size_t)batch);
+    std::vector<char> okv((size_t)batch, 0);
+    {
+        unsigned nt = std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
+        nt = std::min<unsigned>(nt, (unsigned)batch);
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < nt; ++t)
+            th.emplace_back([&, t]() {
+                for (int b = (int)t; b < batch; b += (int)nt) {
+                    const int64_t o = off[b];
+                    const int n = n_points[b];
+                    bool ok = false;
+                    if (formulation == PQP_FORM_K)
+                        ok = pqp::assemble_k(h->params, n, ref + o, bounds + o, x0 + 3 * (size_t)b, end_heading[b], gp[b]);
+                    else
+                        ok = pqp::assemble_kpc(h->params, n, ref + o, bounds + o, x0 + 3 * (size_t)b, end_heading[b],
+                                               max_k + o, max_kp + o, gp[b]);
+                    okv[b] = ok ? 1 : 0;
+                }
+            });
+        for (auto &t : th) t.join();
+    }
+    // layout of the staging blob
+    size_t sn = 0, sm = 0, sz = 0;
+    size_t smem = 0;
+    for (int b = 0; b < batch; ++b) {
+        if (!okv[b]) { gp[b] = pqp::GenProblem(); gp[b].N = n_points[b]; gp[b].out_idx.assign(3 * (size_t)n_points[b], 0); }
+        sn += gp[b].n; sm += gp[b].m; sz += gp[b].csc_row.size();
+        if (okv[b]) smem = std::max(smem, pqp::gen_smem_doubles(gp[b].n, gp[b].m, gp[b].bw) * sizeof(double));
+    }
+    if (smem > (size_t)h->smem_optin) {
+        // paths too long for one SM: they report PQP_INVALID_PROBLEM (the kernel checks the capacity)
+        smem = (size_t)h->smem_optin;
+    }
+    if (smem == 0) smem = 1024;
+    const size_t T = (size_t)off[batch], B = (size_t)batch;
+    auto al = [](size_t x) { return (x + 15) & ~(size_t)15; };
+    size_t o_meta = 0, o_Acol = al(o_meta + B * pqp::kGenMeta * 4), o_Aval = al(o_Acol + sm * 16), o_l = al(o_Aval + sm * 32),
+           o_u = al(o_l + sm * 8), o_Pd = al(o_u + sm * 8), o_Poi = al(o_Pd + sn * 8), o_Pov = al(o_Poi + sn * 8),
+           o_cp = al(o_Pov + sn * 16), o_cr = al(o_cp + (sn + B) * 4), o_cv = al(o_cr + sz * 4), o_sep = al(o_cv + sz * 8),
+           o_oi = al(o_sep + B * 128), o_end = al(o_oi + T * 12);
+    if (o_end > h->gen_cap) {
+        cudaFree(h->d_gen); cudaFreeHost(h->h_gen);
+        h->d_gen = nullptr; h->h_gen = nullptr; h->gen_cap = 0;
+        PQP_CUDA(cudaMalloc(&h->d_gen, o_end));
+        PQP_CUDA(cudaMallocHost(&h->h_gen, o_end));
+        h->gen_cap = o_end;
+    }
+    char *H = h->h_gen;
+    int32_t *meta = (int32_t *)(H + o_meta);
+    size_t an = 0, am = 0, az = 0;
+    for (int b = 0; b < batch; ++b) {
+        const pqp::GenProblem &g = gp[b];
+        int32_t *mb = meta + (size_t)pqp::kGenMeta * b;
+        memset(mb, 0, pqp::kGenMeta * 4);
+        mb[0] = g.n; mb[1] = g.m; mb[2] = g.n_den; mb[3] = g.bw; mb[4] = g.M; mb[5] = n_points[b];
+        mb[6] = (int32_t)off[b]; mb[7] = (int32_t)an; mb[8] = (int32_t)am; mb[9] = (int32_t)az; mb[10] = (int32_t)(an + b);
+        memcpy(H + o_Acol + am * 16, g.A_col.data(), g.A_col.size() * 4);
+        memcpy(H + o_Aval + am * 32, g.A_val.data(), g.A_val.size() * 8);
+        memcpy(H + o_l + am * 8, g.l.data(), g.l.size() * 8);
+        memcpy(H + o_u + am * 8, g.u.data(), g.u.size() * 8);
+        memcpy(H + o_Pd + an * 8, g.Pd.data(), g.Pd.size() * 8);
+        memcpy(H + o_Poi + an * 8, g.Po_idx.data(), g.Po_idx.size() * 4);
+        memcpy(H + o_Pov + an * 16, g.Po_val.data(), g.Po_val.size() * 8);
+        if (g.n > 0) memcpy(H + o_cp + (an + b) * 4, g.csc_ptr.data(), g.csc_ptr.size() * 4);
+        else *(int32_t *)(H + o_cp + (an + b) * 4) = 0;
+        memcpy(H + o_cr + az * 4, g.csc_row.data(), g.csc_row.size() * 4);
+        memcpy(H + o_cv + az * 8, g.csc_val.data(), g.csc_val.size() * 8);
+        memcpy(H + o_sep + (size_t)b * 128, g.sep, 128);
+        memcpy(H + o_oi + (size_t)off[b] * 12, g.out_idx.data(), g.out_idx.size() * 4);
+        an += g.n; am += g.m; az += g.csc_row.size();
+    }
+    PQP_CUDA(cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    PQP_CUDA(cudaEventRecord(h->ev[0], st));
+    PQP_CUDA(cudaMemcpyAsync(h->d_gen, H, o_end, cudaMemcpyHostToDevice, st));
+    PQP_CUDA(cudaMemcpyAsync(h->d_ref, ref, T * sizeof(pqp_state), cudaMemcpyHostToDevice, st));
+    PQP_CUDA(cudaEventRecord(h->ev[1], st));
+    char *D = h->d_gen;
+    pqp::GenView gv;
+    gv.batch = batch; gv.meta = (const int32_t *)(D + o_meta);
+    gv.A_col = (const int32_t *)(D + o_Acol); gv.A_val = (const double *)(D + o_Aval);
+    gv.l = (const double *)(D + o_l); gv.u = (const double *)(D + o_u); gv.Pd = (const double *)(D + o_Pd);
+    gv.Po_idx = (const int32_t *)(D + o_Poi); gv.Po_val = (const double *)(D + o_Pov);
+    gv.csc_ptr = (const int32_t *)(D + o_cp); gv.csc_row = (const int32_t *)(D + o_cr); gv.csc_val = (const double *)(D + o_cv);
+    gv.sep = (const int32_t *)(D + o_sep); gv.out_idx = (const int32_t *)(D + o_oi);
+    gv.ref = h->d_ref; gv.out_states = h->d_out; gv.out_frenet = out_frenet ? h->d_frenet : nullptr;
+    gv.status = h->d_status; gv.iters = h->d_iters;
+    pqp_gen_solve_kernel<<<batch, 32, smem, st>>>(h->dprm_gen[formulation == PQP_FORM_K ? 0 : 1], gv, (int)(smem / sizeof(double)));
+    PQP_CUDA(cudaGetLastError());
+    PQP_CUDA(cudaEventRecord(h->ev[2], st));
+    PQP_CUDA(cudaMemcpyAsync(out_states, h->d_out, T * sizeof(pqp_state), cudaMemcpyDeviceToHost, st));
+    if (out_frenet) PQP_CUDA(cudaMemcpyAsync(out_frenet, h->d_frenet, T * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    PQP_CUDA(cudaMemcpyAsync(status, h->d_status, B * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    std::vector<int32_t> iters_local;
+    int32_t *it_dst = iters;
+    if (!it_dst && stats) { iters_local.resize(B); it_dst = iters_local.data(); }
+    if (it_dst) PQP_CUDA(cudaMemcpyAsync(it_dst, h->d_iters, B * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    PQP_CUDA(cudaEventRecord(h->ev[3], st));
+    PQP_CUDA(cudaStreamSynchronize(st));
+    if (stats) {
+        PQP_CUDA(cudaEventElapsedTime(&stats->h2d_ms, h->ev[0], h->ev[1]));
+        PQP_CUDA(cudaEventElapsedTime(&stats->kernel_ms, h->ev[1], h->ev[2]));
+        PQP_CUDA(cudaEventElapsedTime(&stats->d2h_ms, h->ev[2], h->ev[3]));
+        stats->h2d_bytes = (int64_t)(o_end + T * sizeof(pqp_state));
+        stats->d2h_bytes = (int64_t)(T * sizeof(pqp_state) + (out_frenet ? T * 3 * sizeof(double) : 0) + B * 8);
+        stats->kernel_launches = 1;
+        for (size_t b = 0; b < B; ++b) {
+            stats->total_iters += it_dst[b];
+            stats->max_iters = std::max(stats->max_iters, it_dst[b]);
+            stats->n_solved += (status[b] == PQP_SOLVED);
+        }
+    }
+    return PQP_OK;
+}
+
 int pqp_solve_batch(pqp_handle *h, int formulation, int batch, const int32_t *n_points, const pqp_state *ref,
                     const pqp_station_bounds *bounds, const double *x0, const double *end_heading,
                     const double *max_k, const double *max_kp, pqp_state *out_states, double *out_frenet,
                     int32_t *status, int32_t *iters, pqp_stats *stats) {
-    (void)max_k; (void)max_kp;
     if (!h || batch < 0 || (batch > 0 && (!n_points || !ref || !bounds || !x0 || !end_heading || !out_states || !status))) {
         set_err("pqp_solve_batch: bad argument");
         return PQP_ERR_ARG;
     }
-    if (formulation != PQP_FORM_KP) {
-        set_err("formulation not implemented on the device yet (KP only)");
-        return PQP_ERR_UNSUPPORTED;
+    if (formulation != PQP_FORM_KP && formulation != PQP_FORM_K && formulation != PQP_FORM_KPC) {
+        set_err("unknown formulation");
+        return PQP_ERR_ARG;
     }
     if (stats) memset(stats, 0, sizeof(*stats));
     if (batch == 0) return PQP_OK;
+    if (formulation != PQP_FORM_KP)
+        return solve_batch_generic(h, formulation, batch, n_points, ref, bounds, x0, end_heading, max_k, max_kp, out_states,
+                                   out_frenet, status, iters, stats);
     if (batch > h->max_batch) {
         set_err("batch exceeds the handle's max_batch");
         return PQP_ERR_CAPACITY;

@@ -68,9 +68,10 @@ class BatchPathSolver:
     def max_points(self, formulation="KP"):
         return self._L.pqp_max_points(self._h, FORMULATIONS[formulation])
 
-    def solve(self, batch, formulation="KP", want_frenet=True, out=None):
+    def solve(self, batch, formulation="KP", want_frenet=True, out=None, max_k=None, max_kp=None):
         """batch: dict as produced by synth.* (host numpy arrays).  Returns dict(states, frenet,
-        status, iters, ok, stats).  `out` may carry preallocated (e.g. pinned) output arrays."""
+        status, iters, ok, stats).  `out` may carry preallocated (e.g. pinned) output arrays.
+        max_k / max_kp ([sum N] each) are the KPC limits (ReferencePath::getMaxKList / getMaxKpList)."""
         form = FORMULATIONS[formulation] if isinstance(formulation, str) else int(formulation)
         n_points = np.ascontiguousarray(batch["n_points"], dtype=np.int32)
         B = len(n_points)
@@ -86,8 +87,12 @@ class BatchPathSolver:
         status = out.get("status") if out.get("status") is not None else np.zeros(B, dtype=np.int32)
         iters = out.get("iters") if out.get("iters") is not None else np.zeros(B, dtype=np.int32)
         stats = Stats()
+        if max_k is not None:
+            max_k = np.ascontiguousarray(max_k, dtype=np.float64)
+            max_kp = np.ascontiguousarray(max_kp, dtype=np.float64)
+            assert len(max_k) == total and len(max_kp) == total
         rc = self._L.pqp_solve_batch(self._h, form, B, ptr(n_points), ptr(ref), ptr(bounds), ptr(x0),
-                                     ptr(end_heading), None, None, ptr(states), ptr(frenet), ptr(status),
+                                     ptr(end_heading), ptr(max_k), ptr(max_kp), ptr(states), ptr(frenet), ptr(status),
                                      ptr(iters), C.byref(stats))
         if rc != OK:
             raise PqpError(f"pqp_solve_batch failed (rc={rc}): {_lib.last_error()}")

@@ -35,6 +35,8 @@ def lib():
         _lib = C.CDLL(build())
         _lib.kp_emu_solve_batch.argtypes = [C.POINTER(Params), C.c_int] + [C.c_void_p] * 10 + [C.c_int, C.c_int, C.c_int]
         _lib.kp_emu_solve_batch.restype = C.c_int
+        _lib.gen_emu_solve_batch.argtypes = [C.POINTER(Params), C.c_int, C.c_int] + [C.c_void_p] * 12
+        _lib.gen_emu_solve_batch.restype = C.c_int
     return _lib
 
 
@@ -51,4 +53,21 @@ def solve_batch(params, batch, smem_bytes=227 * 1024, variant=0, nwarps=4):
     lib().kp_emu_solve_batch(C.byref(params), B, ptr(batch["n_points"]), ptr(batch["offsets"]), ptr(ref),
                              ptr(bounds), ptr(batch["x0"]), ptr(batch["end_heading"]), ptr(out),
                              ptr(frenet), ptr(status), ptr(iters), smem_bytes, variant, nwarps)
+    return dict(states=out, frenet=frenet, status=status, iters=iters)
+
+
+def solve_batch_generic(params, formulation, batch, max_k=None, max_kp=None):
+    """The generic banded kernel source (pqp_gen_core.cuh) + the host assembly (pqp_forms.h) for the
+    "K" (formulation 1) and "KPC" (2) formulations, under the warp emulator."""
+    B = len(batch["n_points"])
+    total = int(batch["offsets"][-1])
+    ref = np.ascontiguousarray(batch["ref"], dtype=STATE_DTYPE)
+    bounds = np.ascontiguousarray(batch["bounds"], dtype=BOUNDS_DTYPE)
+    out = np.zeros(total, dtype=STATE_DTYPE)
+    frenet = np.zeros((total, 3))
+    status = np.zeros(B, dtype=np.int32)
+    iters = np.zeros(B, dtype=np.int32)
+    lib().gen_emu_solve_batch(C.byref(params), int(formulation), B, ptr(batch["n_points"]), ptr(batch["offsets"]), ptr(ref),
+                              ptr(bounds), ptr(batch["x0"]), ptr(batch["end_heading"]), ptr(max_k), ptr(max_kp), ptr(out),
+                              ptr(frenet), ptr(status), ptr(iters))
     return dict(states=out, frenet=frenet, status=status, iters=iters)

@@ -82,3 +82,62 @@ extern "C" int kp_emu_solve_batch(const pqp_params *params, int batch, const int
     free(bv.workspace);
     return 0;
 }
+
+// ---- generic banded kernel ("K" / "KPC") under the same warp emulator -------------------------------
+#include "../../path_optimizer_b200/csrc/pqp_gen_core.cuh"
+#include "../../path_optimizer_b200/csrc/pqp_forms.h"
+#include <vector>
+
+namespace {
+struct GenLaneArgs {
+    pqp::EmuShared *sh;
+    int lane;
+    const pqp::DevParams *prm;
+    const pqp::GenView *gv;
+    double *smem;
+    size_t cap;
+};
+void *gen_lane_main(void *p) {
+    GenLaneArgs *a = (GenLaneArgs *)p;
+    pqp::Warp w{a->lane, a->sh};
+    pqp::gen_solve_qp(w, *a->prm, *a->gv, 0, a->smem, a->cap);
+    return nullptr;
+}
+}  // namespace
+
+extern "C" int gen_emu_solve_batch(const pqp_params *params, int formulation, int batch, const int32_t *n_points,
+                                   const int32_t *offsets, const pqp_state *ref, const pqp_station_bounds *bounds,
+                                   const double *x0, const double *end_heading, const double *max_k, const double *max_kp,
+                                   pqp_state *out_states, double *out_frenet, int32_t *status, int32_t *iters) {
+    pqp::DevParams prm = pqp::dev_params_from(*params);
+    for (int b = 0; b < batch; ++b) {
+        const int o = offsets[b], N = n_points[b];
+        pqp::GenProblem g;
+        bool ok = formulation == PQP_FORM_K
+                      ? pqp::assemble_k(*params, N, ref + o, bounds + o, x0 + 3 * b, end_heading[b], g)
+                      : pqp::assemble_kpc(*params, N, ref + o, bounds + o, x0 + 3 * b, end_heading[b], max_k + o, max_kp + o, g);
+        if (!ok) { status[b] = PQP_INVALID_PROBLEM; iters[b] = 0; continue; }
+        int32_t meta[pqp::kGenMeta] = {g.n, g.m, g.n_den, g.bw, g.M, N, 0, 0, 0, 0, 0};
+        pqp::GenView gv;
+        gv.batch = 1; gv.meta = meta;
+        gv.A_col = g.A_col.data(); gv.A_val = g.A_val.data(); gv.l = g.l.data(); gv.u = g.u.data();
+        gv.Pd = g.Pd.data(); gv.Po_idx = g.Po_idx.data(); gv.Po_val = g.Po_val.data();
+        gv.csc_ptr = g.csc_ptr.data(); gv.csc_row = g.csc_row.data(); gv.csc_val = g.csc_val.data();
+        gv.sep = g.sep; gv.out_idx = g.out_idx.data();
+        gv.ref = ref + o; gv.out_states = out_states + o; gv.out_frenet = out_frenet + 3 * (size_t)o;
+        gv.status = status + b; gv.iters = iters + b;
+        const size_t cap = pqp::gen_smem_doubles(g.n, g.m, g.bw);
+        std::vector<double> smem(cap, nan(""));
+        pqp::EmuShared sh;
+        pthread_barrier_init(&sh.bar, nullptr, 32);
+        pthread_t th[32];
+        GenLaneArgs args[32];
+        for (int l = 0; l < 32; ++l) {
+            args[l] = GenLaneArgs{&sh, l, &prm, &gv, smem.data(), cap};
+            pthread_create(&th[l], nullptr, gen_lane_main, &args[l]);
+        }
+        for (int l = 0; l < 32; ++l) pthread_join(th[l], nullptr);
+        pthread_barrier_destroy(&sh.bar);
+    }
+    return 0;
+}

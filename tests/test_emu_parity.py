@@ -92,3 +92,29 @@ def test_emu_shape_classes(oracle_params, variant, n, ds):
     if ds != 0.3:
         b["ref"]["s"] = np.arange(n) * ds
     _check(b, oracle_params, variant=variant)
+
+
+def _limits(batch):
+    """KPC limits as ReferencePathImpl::updateLimits derives them (reference_path_impl.cpp:203-235) for a
+    synthetic speed profile: friction circle and curvature-rate limit."""
+    total = int(batch["offsets"][-1])
+    v = 4.0 + 3.0 * np.sin(np.arange(total) * 0.05)
+    a = 0.5 * np.cos(np.arange(total) * 0.05)
+    max_k = np.sqrt((0.4 * 9.8) ** 2 - a ** 2) / v ** 2
+    max_kp = 0.1 / v
+    return max_k, max_kp
+
+
+@pytest.mark.parametrize("form", [1, 2])
+def test_emu_generic_kernel_k_and_kpc(oracle_params, form):
+    """"K" (SolverKAsInput) and "KPC" (SolverKpAsInputConstrained) on the generic banded kernel source +
+    host assembly (pqp_gen_core.cuh, pqp_forms.h) against the oracle's own restatement of those files."""
+    b = synth.curvy_corridors(4, n_points=[2, 9, 47, 120])
+    mk, mkp = _limits(b) if form == 2 else (None, None)
+    e = emu.solve_batch_generic(oracle_params, form, b, max_k=mk, max_kp=mkp)
+    o = oracle.solve_batch(oracle_params, form, b, max_k=mk, max_kp=mkp)
+    assert np.array_equal(e["status"], o["status"]) and np.array_equal(e["iters"], o["iters"])
+    assert (o["status"] == 1).any()
+    np.testing.assert_allclose(e["frenet"], o["frenet"], rtol=0, atol=TOL)
+    for f in "xyzks":
+        np.testing.assert_allclose(e["states"][f], o["states"][f], rtol=0, atol=TOL)

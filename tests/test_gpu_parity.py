@@ -175,3 +175,24 @@ def test_cpp_host_mirror(oracle_params, tmp_path):
     assert ok == 1
     np.testing.assert_allclose(path0["x"], ref["states"]["x"][:60], rtol=0, atol=FRENET_TOL)
     np.testing.assert_allclose(path0["s"], ref["states"]["s"][:60], rtol=0, atol=FRENET_TOL)
+
+
+@pytest.mark.parametrize("form,name", [(1, "K"), (2, "KPC")])
+def test_k_and_kpc_formulations(solver, oracle_params, form, name):
+    """The other two type strings of OsqpSolver::create (solver.cpp:34-39) behind the same ABI: host-side
+    sparse assembly + the generic banded kernel, against the oracle's restatement of
+    solver_k_as_input.cpp / solver_kp_as_input_constrained.cpp."""
+    rng = np.random.default_rng(11)
+    n_points = rng.integers(2, 180, size=24)
+    n_points[:3] = [2, 3, 5]
+    b = synth.curvy_corridors(24, n_points=n_points)
+    total = int(n_points.sum())
+    mk = mkp = None
+    if form == 2:
+        v = 4.0 + 3.0 * np.sin(np.arange(total) * 0.05)
+        a = 0.5 * np.cos(np.arange(total) * 0.05)
+        mk = np.sqrt((0.4 * 9.8) ** 2 - a ** 2) / v ** 2      # reference_path_impl.cpp:224-231
+        mkp = 0.1 / v
+    res = solver.solve(b, formulation=name, max_k=mk, max_kp=mkp)
+    ref = oracle.solve_batch(oracle_params, form, b, threads=8, max_k=mk, max_kp=mkp)
+    _compare(res, ref)
