@@ -25,6 +25,7 @@
 #define PQP_ORACLE_H_
 
 #include "../include/pqp.h"
+#include "../include/pqp_env.h"
 
 #ifdef __cplusplus
 extern "C" {
@@ -97,6 +98,44 @@ double oracle_solve_batch(const pqp_params *prm, int formulation, int batch,
                           const double *end_heading, const double *max_k, const double *max_kp,
                           pqp_state *out, double *frenet, int32_t *status, int32_t *iters,
                           int threads);
+
+/* ---- stages either side of the QP (pqp_oracle_env.c; rows N2-N4 of the scope table) ---- */
+
+/* Map::getObstacleDistance / isInside, src/tools/Map.cpp:16-26 over grid_map geometry. */
+int oracle_map_inside(const pqp_distance_map *m, double x, double y);
+double oracle_map_distance(const pqp_distance_map *m, double x, double y);
+
+/* tk::spline::set_points / operator() / deriv, src/tools/spline.cpp:161-318 (re-derived). */
+int oracle_spline_fit(int n, const double *t, const double *y, double *coef);
+double oracle_spline_eval(int n, const double *t, const double *coef, int order, double at);
+
+/* getClearanceWithDirectionStrict, reference_path_impl.cpp:283-472; out = {left, right}. */
+void oracle_clearance_strict(const pqp_params *prm, const pqp_distance_map *map, double sx,
+                             double sy, double sz, double out[2]);
+
+/* updateBoundsImproved / updateBounds, reference_path_impl.cpp:142-201 / 237-281. */
+int oracle_update_bounds(const pqp_params *prm, const pqp_distance_map *map, int mode, int n,
+                         const pqp_state *ref, int n_knots, const double *knots,
+                         const double *x_coef, const double *y_coef, pqp_station_bounds *out);
+
+/* CarGeometry circles + CollisionChecker, car_geometry.cpp:38-57, collision_checker.cpp:17-59. */
+void oracle_car_circles(const pqp_params *prm, double c[7][3]);
+int oracle_state_collision_free(const pqp_params *prm, const pqp_distance_map *map,
+                                const pqp_state *s);
+
+/* optimizePath tails, path_optimizer.cpp:191-202 and :203-230. */
+int oracle_finish_raw(const pqp_params *prm, const pqp_distance_map *map, int n, pqp_state *path,
+                      int collision_check, int *n_kept);
+int oracle_densify(const pqp_params *prm, const pqp_distance_map *map, int n, const pqp_state *path,
+                   double spacing, int collision_check, int max_out, pqp_state *out, int *n_out);
+
+/* solveWithoutSmoothing, path_optimizer.cpp:87-117, one path. */
+int oracle_plan_path(const pqp_params *prm, const pqp_distance_map *map, int formulation,
+                     int bounds_mode, int output_mode, int n, const pqp_state *ref, int n_knots,
+                     const double *knots, const double *x_coef, const double *y_coef,
+                     const double x0[3], double end_heading, double spacing, int collision_check,
+                     int max_out, pqp_state *out, int *n_out, int *status, int *iters,
+                     pqp_station_bounds *bounds_out);
 
 #ifdef __cplusplus
 }

@@ -3,7 +3,7 @@ product has no CPU fallback."""
 import ctypes as C
 import os
 
-from .abi import Params, Stats
+from .abi import DistanceMap, Params, Stats
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpqp.so")
@@ -12,6 +12,10 @@ LIB_PATH = os.path.join(_HERE, "libpqp.so")
 SYMBOLS = ["pqp_params_default", "pqp_params_update_config", "pqp_keep_control_steps", "pqp_problem_size",
            "pqp_create", "pqp_destroy", "pqp_set_params", "pqp_solve_batch", "pqp_solve_batch_device",
            "pqp_last_error", "pqp_version", "pqp_max_points"]
+# ... and include/pqp_env.h
+ENV_SYMBOLS = ["pqp_set_map", "pqp_map_distance", "pqp_spline_fit", "pqp_spline_eval", "pqp_update_bounds_batch",
+               "pqp_check_states", "pqp_finish_raw_batch", "pqp_densify_batch", "pqp_plan_batch"]
+SYMBOLS = SYMBOLS + ENV_SYMBOLS
 
 _lib = None
 
@@ -39,6 +43,18 @@ def load():
     L.pqp_last_error.restype = C.c_char_p
     L.pqp_version.restype = C.c_char_p
     L.pqp_max_points.argtypes = [vp, C.c_int]
+    # include/pqp_env.h
+    L.pqp_set_map.argtypes = [vp, C.POINTER(DistanceMap)]
+    L.pqp_map_distance.argtypes = [vp, C.c_int, vp, vp]
+    L.pqp_spline_fit.argtypes = [C.c_int, vp, vp, vp]
+    L.pqp_spline_eval.argtypes = [C.c_int, vp, vp, C.c_int, C.c_double]
+    L.pqp_spline_eval.restype = C.c_double
+    L.pqp_update_bounds_batch.argtypes = [vp, C.c_int, C.c_int] + [vp] * 8 + [C.POINTER(Stats)]
+    L.pqp_check_states.argtypes = [vp, C.c_int, vp, vp]
+    L.pqp_finish_raw_batch.argtypes = [vp, C.c_int, vp, vp, C.c_int, vp, vp, C.POINTER(Stats)]
+    L.pqp_densify_batch.argtypes = [vp, C.c_int, vp, vp, C.c_double, C.c_int, C.c_int, vp, vp, vp, C.POINTER(Stats)]
+    L.pqp_plan_batch.argtypes = ([vp, C.c_int, C.c_int, C.c_int, C.c_int] + [vp] * 8 +
+                                 [C.c_double, C.c_int, C.c_int] + [vp] * 6 + [C.POINTER(Stats)])
     _lib = L
     return L
 

@@ -67,6 +67,12 @@ class Stats(C.Structure):
     ]
 
 
+class DistanceMap(C.Structure):
+    """``pqp_distance_map`` (include/pqp_env.h)."""
+    _fields_ = [("distance", C.c_void_p), ("rows", C.c_int32), ("cols", C.c_int32),
+                ("resolution", C.c_double), ("center_x", C.c_double), ("center_y", C.c_double)]
+
+
 def ptr(arr, ctype=C.c_void_p):
     """Raw pointer of a C-contiguous numpy array (or None)."""
     if arr is None:

@@ -13,25 +13,16 @@
 #include "pqp_kp_core3.cuh"
 #include "pqp_gen_core.cuh"
 #include "pqp_forms.h"
+#include "pqp_handle.h"
 #include <thread>
+
+thread_local char pqp_g_err[512] = "";
 
 namespace {
 
 constexpr int kMaxBandGeneric = pqp::kMaxBand;
-thread_local char g_err[512] = "";
-
-void set_err(const char *fmt, const char *a = "", const char *b = "") {
-    snprintf(g_err, sizeof(g_err), fmt, a, b);
-}
-
-#define PQP_CUDA(call)                                                       \
-    do {                                                                     \
-        cudaError_t e_ = (call);                                             \
-        if (e_ != cudaSuccess) {                                             \
-            set_err("%s failed: %s", #call, cudaGetErrorString(e_));         \
-            return PQP_ERR_CUDA;                                             \
-        }                                                                    \
-    } while (0)
+#define set_err pqp_set_err
+#define g_err pqp_g_err
 
 // One warp (= one CTA) per path.  Shared memory holds the whole ADMM state and the KKT factor.
 __global__ void __launch_bounds__(32)
@@ -119,27 +110,6 @@ int pick_variant(int n, int keep) {
 
 }  // namespace
 
-struct pqp_handle {
-    int device = 0;
-    int max_batch = 0, max_total = 0;
-    int smem_optin = 0;
-    int num_sms = 0;
-    pqp_params params;
-    pqp::DevParams dprm;
-    pqp::DevParams dprm_gen[2];
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-    // device buffers for the host-pointer entry point
-    int32_t *d_n = nullptr, *d_off = nullptr, *d_order = nullptr, *d_status = nullptr, *d_iters = nullptr;
-    pqp_state *d_ref = nullptr, *d_out = nullptr;
-    pqp_station_bounds *d_bounds = nullptr;
-    double *d_x0 = nullptr, *d_end = nullptr, *d_frenet = nullptr, *d_ws = nullptr;
-    // pinned host scratch for the small per-batch arrays
-    int32_t *h_off = nullptr, *h_order = nullptr;
-    // generic-kernel staging (grow-only): one device blob + one pinned host blob
-    char *d_gen = nullptr, *h_gen = nullptr;
-    size_t gen_cap = 0;
-};
 
 extern "C" {
 
@@ -227,6 +197,7 @@ void pqp_destroy(pqp_handle *h) {
     cudaFree(h->d_x0); cudaFree(h->d_end); cudaFree(h->d_frenet); cudaFree(h->d_ws);
     cudaFreeHost(h->h_off); cudaFreeHost(h->h_order);
     cudaFree(h->d_gen); cudaFreeHost(h->h_gen);
+    if (h->env && h->env_free) h->env_free(h->env);
     for (auto &e : h->ev) if (e) cudaEventDestroy(e);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -442,6 +413,7 @@ static int solve_batch_generic(pqp_handle *h, int formulation, int batch, const 
            o_oi = al(o_sep + B * 128), o_end = al(o_oi + T * 12);
     if (o_end > h->gen_cap) {
         cudaFree(h->d_gen); cudaFreeHost(h->h_gen);
+    if (h->env && h->env_free) h->env_free(h->env);
         h->d_gen = nullptr; h->h_gen = nullptr; h->gen_cap = 0;
         PQP_CUDA(cudaMalloc(&h->d_gen, o_end));
         PQP_CUDA(cudaMallocHost(&h->h_gen, o_end));

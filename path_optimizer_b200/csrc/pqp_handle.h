@@ -1,0 +1,49 @@
+// pqp_handle.h -- the opaque handle behind include/pqp.h, shared by the translation units of
+// libpqp.so (pqp_capi.cu: the QP; pqp_env.cu: bounds / collision check / densify / plan chain).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/pqp.h"
+#include "pqp_device.cuh"
+
+struct pqp_handle {
+    int device = 0;
+    int max_batch = 0, max_total = 0;
+    int smem_optin = 0;
+    int num_sms = 0;
+    pqp_params params;
+    pqp::DevParams dprm;
+    pqp::DevParams dprm_gen[2];
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    // device buffers for the host-pointer entry point
+    int32_t *d_n = nullptr, *d_off = nullptr, *d_order = nullptr, *d_status = nullptr, *d_iters = nullptr;
+    pqp_state *d_ref = nullptr, *d_out = nullptr;
+    pqp_station_bounds *d_bounds = nullptr;
+    double *d_x0 = nullptr, *d_end = nullptr, *d_frenet = nullptr, *d_ws = nullptr;
+    // pinned host scratch for the small per-batch arrays
+    int32_t *h_off = nullptr, *h_order = nullptr;
+    // generic-kernel staging (grow-only): one device blob + one pinned host blob
+    char *d_gen = nullptr, *h_gen = nullptr;
+    size_t gen_cap = 0;
+    // state of the stages either side of the QP (pqp_env.cu): map, scratch buffers
+    void *env = nullptr;
+    void (*env_free)(void *) = nullptr;
+};
+
+// thread-local error text returned by pqp_last_error()
+extern thread_local char pqp_g_err[512];
+inline void pqp_set_err(const char *fmt, const char *a = "", const char *b = "") {
+    snprintf(pqp_g_err, sizeof(pqp_g_err), fmt, a, b);
+}
+
+#define PQP_CUDA(call)                                                       \
+    do {                                                                     \
+        cudaError_t e_ = (call);                                             \
+        if (e_ != cudaSuccess) {                                             \
+            pqp_set_err("%s failed: %s", #call, cudaGetErrorString(e_));     \
+            return PQP_ERR_CUDA;                                             \
+        }                                                                    \
+    } while (0)

@@ -145,3 +145,72 @@ def slice_batch(batch, begin, end):
     np.cumsum(out["n_points"], out=offsets[1:])
     out["offsets"] = offsets
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# Config 3: obstacle field + distance map (the input of the clearance-bounds stage)
+# ---------------------------------------------------------------------------------------------
+
+def disc_field_map(rows=1100, cols=250, resolution=0.2, n_discs=300, seed=BASE_SEED, config=3,
+                   center=(0.0, 0.0), keep_clear_halfwidth=1.7):
+    """Synthetic 0.2 m occupancy grid with random discs (radius U(0.5, 2) m) and its Euclidean
+    distance transform in metres -- what the reference builds with cv::distanceTransform(L2,
+    MASK_PRECISE) * resolution (path_optimizer_benchmark.cpp:39-43).  Discs whose edge would come
+    within `keep_clear_halfwidth` of the map's x axis are pushed out so that a corridor exists.
+    grid_map index convention: cell (i, j) centred at x = cx + L_x/2 - (i+0.5) res,
+    y = cy + L_y/2 - (j+0.5) res.  Returns dict(distance float32 [rows, cols], rows, cols,
+    resolution, center_x, center_y)."""
+    from scipy import ndimage
+    lx, ly = rows * resolution, cols * resolution
+    xs = center[0] + lx / 2 - (np.arange(rows) + 0.5) * resolution
+    ys = center[1] + ly / 2 - (np.arange(cols) + 0.5) * resolution
+    free = np.ones((rows, cols), dtype=bool)
+    idx = np.arange(n_discs, dtype=np.uint64)
+    cx = center[0] - lx / 2 + lx * uniform(seed, config, 0xFFFFF0, 1, idx)
+    cy = center[1] - ly / 2 + ly * uniform(seed, config, 0xFFFFF0, 2, idx)
+    rad = 0.5 + 1.5 * uniform(seed, config, 0xFFFFF0, 3, idx)
+    for k in range(n_discs):
+        y0 = cy[k]
+        gap = abs(y0 - center[1]) - rad[k]
+        if gap < keep_clear_halfwidth:
+            y0 = center[1] + np.sign(y0 - center[1] if y0 != center[1] else 1.0) * (keep_clear_halfwidth + rad[k])
+        free &= ((xs[:, None] - cx[k]) ** 2 + (ys[None, :] - y0) ** 2) > rad[k] ** 2
+    dist = ndimage.distance_transform_edt(free).astype(np.float32) * np.float32(resolution)
+    return dict(distance=np.ascontiguousarray(dist), rows=rows, cols=cols, resolution=float(resolution),
+                center_x=float(center[0]), center_y=float(center[1]))
+
+
+def map_reference_paths(batch, n=200, seed=BASE_SEED, first_path=0, config=3, n_points=None,
+                        x_range=(-100.0, 40.0), y_range=(-0.5, 0.5), heading_range=0.02, curvature_amp=0.004):
+    """Reference lines for config 3: kappa_ref(s) = A sin(2 pi s / L), A ~ U(0, curvature_amp), L ~ U(30, 80) m,
+    integrated to (x, y, heading) from a random start pose near the map's x axis.  No bounds: those
+    come from the clearance stage.  x0 = (0, 0, k_0) as solveWithoutSmoothing sets it
+    (path_optimizer.cpp:97); end heading = heading of the last station."""
+    if n_points is None:
+        n_points = np.full(batch, n, dtype=np.int32)
+    n_points = np.asarray(n_points, dtype=np.int32)
+    total = int(n_points.sum())
+    ref = np.zeros(total, dtype=STATE_DTYPE)
+    x0 = np.zeros((batch, 3))
+    end_heading = np.zeros(batch)
+    off = 0
+    for b in range(batch):
+        nb = int(n_points[b])
+        pid = np.uint64(first_path + b)
+        s = _accumulate_s(nb)
+        A = curvature_amp * uniform(seed, config, pid, 1)
+        L = 30.0 + 50.0 * uniform(seed, config, pid, 2)
+        k = A * np.sin(2 * np.pi * s / L)
+        th0 = heading_range * (2 * uniform(seed, config, pid, 20) - 1)
+        theta = th0 + np.concatenate([[0.0], np.cumsum(0.5 * (k[1:] + k[:-1]) * np.diff(s))])
+        xs = x_range[0] + (x_range[1] - x_range[0]) * uniform(seed, config, pid, 21)
+        ys = y_range[0] + (y_range[1] - y_range[0]) * uniform(seed, config, pid, 22)
+        x = xs + np.concatenate([[0.0], np.cumsum(np.cos(0.5 * (theta[1:] + theta[:-1])) * np.diff(s))])
+        y = ys + np.concatenate([[0.0], np.cumsum(np.sin(0.5 * (theta[1:] + theta[:-1])) * np.diff(s))])
+        r = ref[off:off + nb]
+        r["x"], r["y"], r["z"], r["k"], r["s"] = x, y, theta, k, s
+        x0[b, 2] = k[0]
+        end_heading[b] = theta[-1]
+        off += nb
+    out = _pack(n_points, ref, np.zeros(total, dtype=BOUNDS_DTYPE), x0, end_heading)
+    return out

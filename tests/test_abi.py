@@ -22,7 +22,7 @@ def L():
 
 
 def test_exports_every_declared_symbol(L):
-    header = open(os.path.join(ROOT, "include", "pqp.h")).read()
+    header = open(os.path.join(ROOT, "include", "pqp.h")).read() + open(os.path.join(ROOT, "include", "pqp_env.h")).read()
     declared = set(re.findall(r"\b(pqp_[a-z_]+)\s*\(", header))
     assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
     for sym in declared:
@@ -34,6 +34,35 @@ def test_record_sizes():
     # sizeof(pqp_params): 21 doubles + int (+pad) + 7 doubles + 5 ints (+pad) + double + 3 ints (+pad)
     assert C.sizeof(Params) == 21 * 8 + 8 + 7 * 8 + 24 + 8 + 16
     assert C.sizeof(Stats) == 56
+    from path_optimizer_b200.abi import DistanceMap
+    assert C.sizeof(DistanceMap) == 8 + 8 + 3 * 8
+
+
+def test_host_spline_helpers_match_oracle(L):
+    """pqp_spline_fit / pqp_spline_eval are host helpers (no GPU needed): same coefficients and values as the
+    oracle's restatement of tk::spline, including both extrapolation sides."""
+    from path_optimizer_b200 import planner
+    rng = np.random.default_rng(3)
+    t = np.cumsum(rng.uniform(0.2, 0.6, 40))
+    y = np.sin(t) + 0.1 * rng.standard_normal(40)
+    c = planner.spline_fit(t, y)
+    co = oracle.spline_fit(t, y)
+    assert np.abs(c - co).max() <= 1e-12
+    at = np.concatenate([[t[0] - 1.0, t[0], t[-1], t[-1] + 2.0], rng.uniform(t[0], t[-1], 50), t[5:8]])
+    for order in (0, 1, 2):
+        assert np.abs(planner.spline_eval(t, c, at, order) - oracle.spline_eval(t, co, at, order)).max() <= 1e-12
+    with pytest.raises(Exception):
+        planner.spline_fit(t[:2], y[:2])
+
+
+def test_env_calls_fail_without_gpu(L):
+    """Every map-based entry point needs a handle; creating one without a GPU fails, there is no CPU path."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from path_optimizer_b200 import planner
+    with pytest.raises(Exception):
+        planner.PathPlanner(max_batch=1, max_total_points=64)
 
 
 def test_params_default_matches_oracle_bytes(L):
