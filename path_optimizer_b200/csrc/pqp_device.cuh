@@ -102,4 +102,11 @@ PQP_DEV double rho_bar(double El, double Eu, double rho) {
     return rho;
 }
 
+// OSQP is_primal_infeasible on the certificate (||E dy||, u'dy+ + l'dy-, ||D^-1 A'dy||), all in
+// unscaled terms (see the kernels): dy is a certificate when it is non-trivial, separates the
+// bounds and is (nearly) orthogonal to the range of A.
+PQP_DEV bool primal_infeasible(double nrm, double lhs, double cert, double eps) {
+    return nrm > eps && lhs < -eps * nrm && cert < eps * nrm;
+}
+
 }  // namespace pqp

@@ -40,12 +40,12 @@ struct GenView {
 };
 
 PQP_HD size_t gen_smem_doubles(int n, int m, int bw) {
-    return 5 * (size_t)n + 3 * (size_t)m + (size_t)(bw + 1) * n + (size_t)kRedStride * 32;
+    return 5 * (size_t)n + 4 * (size_t)m + (size_t)(bw + 1) * n + (size_t)kRedStride * 32;
 }
 
 struct GenCtx {
     int n, m, bw, M;
-    double *D, *xr, *tr, *tmp, *sg, *v, *E, *W, *band, *red;
+    double *D, *xr, *tr, *tmp, *sg, *v, *E, *W, *wold, *band, *red;
     const int32_t *A_col, *csc_ptr, *csc_row, *sep, *Po_idx;
     const double *A_val, *l, *u, *Pd, *Po_val, *csc_val;
     int lo, hi, gsep;
@@ -285,7 +285,7 @@ PQP_DEV void gen_solve_qp(Warp &w, const DevParams &pm, const GenView &gv, int p
     if (!bad) {
         double *p = smem;
         cx.D = p; p += n; cx.xr = p; p += n; cx.tr = p; p += n; cx.tmp = p; p += n; cx.sg = p; p += n;
-        cx.v = p; p += m; cx.E = p; p += m; cx.W = p; p += m;
+        cx.v = p; p += m; cx.E = p; p += m; cx.W = p; p += m; cx.wold = p; p += m;
         cx.band = p; p += (size_t)(bw + 1) * n; cx.red = p;
         cx.lo = cx.hi = cx.gsep = 0;
         if (lane < M) {
@@ -359,6 +359,7 @@ PQP_DEV void gen_solve_qp(Warp &w, const DevParams &pm, const GenView &gv, int p
         if (!gen_factor(w, cx, cost_c)) status = PQP_NON_CVX;
         const double alpha = pm.alpha;
         double pri_res = 0, dua_res = 0, pri_nrm = 0, dua_nrm = 0;
+        double inf_nrm = 0, inf_lhs = 0, inf_cert = 0;   // primal-infeasibility certificate of the last check
         iter = 1;
         while (status == PQP_UNSOLVED && iter < pm.max_iter) {
             ++iter;
@@ -375,9 +376,13 @@ PQP_DEV void gen_solve_qp(Warp &w, const DevParams &pm, const GenView &gv, int p
             }
             w.sync();
             gen_solve(w, cx);
+            // iterations that end in a termination check first park w = v - clamp(v): the check needs
+            // delta_y = W (w_new - w_old) (OSQP update_y / is_primal_infeasible)
+            const bool chk = (pm.check_termination && (iter % pm.check_termination == 0)) || iter == pm.max_iter;
             for (int r = lane; r < m; r += 32) {
-                const double vv = cx.v[r];
-                cx.v[r] = vv + alpha * (gen_row_dot(cx, r, cx.tr) - clampd(vv, cx.l[r], cx.u[r]));
+                const double vv = cx.v[r], zz = clampd(vv, cx.l[r], cx.u[r]);
+                if (chk) cx.wold[r] = vv - zz;
+                cx.v[r] = vv + alpha * (gen_row_dot(cx, r, cx.tr) - zz);
             }
             for (int j = lane; j < n; j += 32) cx.xr[j] = alpha * cx.tr[j] + (1.0 - alpha) * cx.xr[j];
             w.sync();
@@ -412,11 +417,39 @@ PQP_DEV void gen_solve_qp(Warp &w, const DevParams &pm, const GenView &gv, int p
                 pr = w.max(pr); nz = w.max(nz); nax = w.max(nax); prs = w.max(prs); nzs = w.max(nzs); naxs = w.max(naxs);
                 dr = w.max(dr); npx = w.max(npx); naty = w.max(naty); drs = w.max(drs); npxs = w.max(npxs); natys = w.max(natys);
                 w.sync();
+                // ---- primal-infeasibility certificate (OSQP is_primal_infeasible) in unscaled terms:
+                // g = W (w_new - w_old) = E delta_y projected on the cone of the finite (scaled) bounds;
+                // ||g||_inf, u'g+ + l'g-, ||A'g||_inf.  g overwrites wold.
+                if (chk) {
+                    double c_nrm = 0, c_lhs = 0, c_cert = 0;
+                    for (int r = lane; r < m; r += 32) {
+                        const double vv = cx.v[r], lr = cx.l[r], ur = cx.u[r];
+                        double g = cx.W[r] * ((vv - clampd(vv, lr, ur)) - cx.wold[r]);
+                        const bool u_inf = cx.E[r] * ur > kOsqpInfty * kMinScaling;
+                        const bool l_inf = cx.E[r] * lr < -kOsqpInfty * kMinScaling;
+                        if (u_inf) g = l_inf ? 0.0 : fmin(g, 0.0);
+                        else if (l_inf) g = fmax(g, 0.0);
+                        cx.wold[r] = g;
+                        c_nrm = fmax(c_nrm, fabs(g));
+                        c_lhs += ur * fmax(g, 0.0) + lr * fmin(g, 0.0);
+                    }
+                    w.sync();
+                    for (int j = lane; j < n; j += 32) {
+                        double aty = 0.0;
+                        for (int e = cx.csc_ptr[j]; e < cx.csc_ptr[j + 1]; ++e) aty += cx.csc_val[e] * cx.wold[cx.csc_row[e]];
+                        c_cert = fmax(c_cert, fabs(aty));
+                    }
+                    inf_nrm = w.max(c_nrm); inf_cert = w.max(c_cert); inf_lhs = w.sum(c_lhs);
+                    w.sync();
+                }
                 pri_res = pr; dua_res = dr; pri_nrm = fmax(nz, nax); dua_nrm = fmax(npx, naty);
                 if (can_check || iter == pm.max_iter) {
+                    // OSQP check_termination; q = 0, so the dual-infeasibility test (q'dx < 0) never fires
+                    const bool prim_ok = pri_res < pm.eps_abs + pm.eps_rel * pri_nrm;
                     if (pri_res > kOsqpInfty || dua_res > kOsqpInfty) status = PQP_NON_CVX;
-                    else if (pri_res < pm.eps_abs + pm.eps_rel * pri_nrm && dua_res < pm.eps_abs + pm.eps_rel * dua_nrm)
-                        status = PQP_SOLVED;
+                    else if (prim_ok && dua_res < pm.eps_abs + pm.eps_rel * dua_nrm) status = PQP_SOLVED;
+                    else if (!prim_ok && primal_infeasible(inf_nrm, inf_lhs, inf_cert, pm.eps_prim_inf))
+                        status = PQP_PRIMAL_INFEASIBLE;
                 }
                 if (status == PQP_UNSOLVED && can_adapt) {
                     const double pn = prs / (fmax(nzs, naxs) + 1e-10);
@@ -439,10 +472,11 @@ PQP_DEV void gen_solve_qp(Warp &w, const DevParams &pm, const GenView &gv, int p
             }
         }
         if (status == PQP_UNSOLVED) {
-            if (pri_res < 10 * pm.eps_abs + 10 * pm.eps_rel * pri_nrm && dua_res < 10 * pm.eps_abs + 10 * pm.eps_rel * dua_nrm)
-                status = PQP_SOLVED_INACCURATE;
-            else
-                status = PQP_MAX_ITER_REACHED;
+            const bool prim_ok = pri_res < 10 * pm.eps_abs + 10 * pm.eps_rel * pri_nrm;
+            if (prim_ok && dua_res < 10 * pm.eps_abs + 10 * pm.eps_rel * dua_nrm) status = PQP_SOLVED_INACCURATE;
+            else if (!prim_ok && primal_infeasible(inf_nrm, inf_lhs, inf_cert, 10 * pm.eps_prim_inf))
+                status = PQP_PRIMAL_INFEASIBLE;
+            else status = PQP_MAX_ITER_REACHED;
         }
     }
     // ---- epilogue: getOptimizedPath (solver_k_as_input.cpp:22-44, ..._constrained.cpp:26-43)

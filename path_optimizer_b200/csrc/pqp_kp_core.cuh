@@ -34,6 +34,18 @@
 
 namespace pqp {
 
+// Global-memory workspace of one path (BatchView::workspace): 16 doubles per station + kWsPerPath
+// for the scaling vectors the v2/v3 kernels keep out of shared memory (E: 9N + ch + 2, D: nv, N),
+// plus 16 doubles per station for w = v - clamp(v) of the previous iterate, parked only on
+// iterations that end in a termination check (11N + 2 used): region = 32 N + kWsPerPath.
+constexpr int kWsPerPath = 2048;
+constexpr int kWsPerStation = 32;
+PQP_HD size_t kp2_ws_doubles(size_t total_points, size_t batch) { return kWsPerStation * total_points + (size_t)kWsPerPath * batch; }
+PQP_HD double *kp_ws_base(double *workspace, int off, int prob) {
+    return workspace + (size_t)off * kWsPerStation + (size_t)prob * kWsPerPath;
+}
+PQP_HD double *kp_ws_wold(double *ws, int N) { return ws + 16 * (size_t)N + kWsPerPath; }
+
 struct KpDims {
     int N, keep, ch, h, nred, bw, L, M;
 };
@@ -773,6 +785,9 @@ PQP_DEV void kp_solve_path(Warp &w, const DevParams &prm, const BatchView &bv, i
         if (!kp_factor(w, cx)) status = PQP_NON_CVX;
         const double alpha = pm.alpha;
         double pri_res = 0, dua_res = 0, pri_nrm = 0, dua_nrm = 0;
+        double inf_nrm = 0, inf_lhs = 0, inf_cert = 0;   // primal-infeasibility certificate of the last check
+        // (without a workspace -- test harnesses of this core alone -- infeasibility is not detected)
+        double *wold = bv.workspace ? kp_ws_wold(kp_ws_base(bv.workspace, off, prob), N) : nullptr;
         iter = 1;
         while (status == PQP_UNSOLVED && iter < pm.max_iter) {
             ++iter;
@@ -826,6 +841,29 @@ PQP_DEV void kp_solve_path(Warp &w, const DevParams &prm, const BatchView &bv, i
             w.sync();
             // ---- (b) reduced KKT solve
             kp_solve(w, cx);
+            // iterations that end in a termination check first park w = v - clamp(v): the check needs
+            // delta_y = W (w_new - w_old) (OSQP update_y / is_primal_infeasible)
+            const bool chk = wold && ((pm.check_termination && (iter % pm.check_termination == 0)) || iter == pm.max_iter);
+            if (chk) {
+                for (int i = lane; i < N; i += 32) {
+                    double b0, b1, b2, v;
+                    kp_dyn_bounds(cx, i, b0, b1, b2);
+                    double *wo = wold + i;
+                    wo[0] = s.vD()[i] - b0; wo[N] = s.vD()[N + i] - b1; wo[2 * N] = s.vD()[2 * N + i] - b2;
+                    v = s.vKB()[i]; wo[3 * N] = v - clampd(v, -pm.kmax, pm.kmax);
+                    v = s.vSB()[i]; wo[4 * N] = v - clampd(v, 0.0, pm.margin);
+                    v = s.vH1()[i]; wo[5 * N] = v - clampd(v, s.lH1()[i], s.uH1()[i]);
+                    v = s.vH3()[i]; wo[6 * N] = v - clampd(v, s.lH3()[i], s.uH3()[i]);
+                    v = s.vS4m()[i]; wo[7 * N] = v - clampd(v, -kOsqpInfty, s.uS4m()[i]);
+                    v = s.vS4p()[i]; wo[8 * N] = v - clampd(v, s.lS4p()[i], kOsqpInfty);
+                    v = s.vS2m()[i]; wo[9 * N] = v - clampd(v, -kOsqpInfty, s.uS2m()[i]);
+                    v = s.vS2p()[i]; wo[10 * N] = v - clampd(v, s.lS2p()[i], kOsqpInfty);
+                    if (i == N - 1) {
+                        v = s.vEnd()[0]; wold[11 * N] = v - clampd(v, -1.0, 1.0);
+                        v = s.vEnd()[1]; wold[11 * N + 1] = v - clampd(v, cx.lEH, cx.uEH);
+                    }
+                }
+            }
             // ---- (c) v += alpha (A xt - clamp(v)),  x = alpha xt + (1 - alpha) x
             for (int i = lane; i < N; i += 32) {
                 const KpRows zt = kp_apply_A(cx, i, s.tr(), s.ts());
@@ -949,6 +987,69 @@ PQP_DEV void kp_solve_path(Warp &w, const DevParams &prm, const BatchView &bv, i
 #undef PQP_ROW
 #undef PQP_DUAL
 #undef PQP_VAR
+                // ---- primal-infeasibility certificate (OSQP is_primal_infeasible) in unscaled terms:
+                // g = W (w_new - w_old) = E delta_y projected on the cone of the finite bounds;
+                // ||g||_inf, u'g+ + l'g-, ||A'g||_inf.  The control rows are free (g = 0).
+                if (chk) {
+                    double c_nrm = 0, c_lhs = 0, c_cert = 0;
+#define PQP_G(V, LO, HI, WW, WO) ((WW) * (((V) - clampd((V), (LO), (HI))) - (WO)))
+#define PQP_ACC(G, LO, HI) { const double g_ = (G); c_nrm = fmax(c_nrm, fabs(g_)); c_lhs += (HI) * fmax(g_, 0.0) + (LO) * fmin(g_, 0.0); }
+                    w.sync();   // the dual-residual pass has consumed gD
+                    for (int i = lane; i < N; i += 32) {
+                        const KpRowW W = kp_row_weights(cx, i, rho);
+                        double b0, b1, b2;
+                        kp_dyn_bounds(cx, i, b0, b1, b2);
+                        const double *wo = wold + i;
+                        s.gD()[i] = W.D0 * ((s.vD()[i] - b0) - wo[0]);
+                        s.gD()[N + i] = W.D1 * ((s.vD()[N + i] - b1) - wo[N]);
+                        s.gD()[2 * N + i] = W.D2 * ((s.vD()[2 * N + i] - b2) - wo[2 * N]);
+                    }
+                    w.sync();
+                    for (int i = lane; i < N; i += 32) {
+                        const KpRowW W = kp_row_weights(cx, i, rho);
+                        double b0, b1, b2;
+                        kp_dyn_bounds(cx, i, b0, b1, b2);
+                        const double *wo = wold + i;
+                        KpRows g;
+                        g.D0 = s.gD()[i]; g.D1 = s.gD()[N + i]; g.D2 = s.gD()[2 * N + i];
+                        g.KB = PQP_G(s.vKB()[i], -pm.kmax, pm.kmax, W.KB, wo[3 * N]);
+                        g.SB = PQP_G(s.vSB()[i], 0.0, pm.margin, W.SB, wo[4 * N]);
+                        g.H1 = PQP_G(s.vH1()[i], s.lH1()[i], s.uH1()[i], W.H1, wo[5 * N]);
+                        g.H3 = PQP_G(s.vH3()[i], s.lH3()[i], s.uH3()[i], W.H3, wo[6 * N]);
+                        // one-sided rows: l = -inf keeps the positive part, u = +inf the negative part
+                        g.S4m = fmax(PQP_G(s.vS4m()[i], -kOsqpInfty, s.uS4m()[i], W.S4, wo[7 * N]), 0.0);
+                        g.S4p = fmin(PQP_G(s.vS4p()[i], s.lS4p()[i], kOsqpInfty, W.S4, wo[8 * N]), 0.0);
+                        g.S2m = fmax(PQP_G(s.vS2m()[i], -kOsqpInfty, s.uS2m()[i], W.S2, wo[9 * N]), 0.0);
+                        g.S2p = fmin(PQP_G(s.vS2p()[i], s.lS2p()[i], kOsqpInfty, W.S2, wo[10 * N]), 0.0);
+                        PQP_ACC(g.D0, b0, b0) PQP_ACC(g.D1, b1, b1) PQP_ACC(g.D2, b2, b2)
+                        PQP_ACC(g.KB, -pm.kmax, pm.kmax) PQP_ACC(g.SB, 0.0, pm.margin)
+                        PQP_ACC(g.H1, s.lH1()[i], s.uH1()[i]) PQP_ACC(g.H3, s.lH3()[i], s.uH3()[i])
+                        PQP_ACC(g.S4m, 0.0, s.uS4m()[i]) PQP_ACC(g.S4p, s.lS4p()[i], 0.0)
+                        PQP_ACC(g.S2m, 0.0, s.uS2m()[i]) PQP_ACC(g.S2p, s.lS2p()[i], 0.0)
+                        double gEY = 0, gEH = 0;
+                        if (i == N - 1) {
+                            gEY = PQP_G(s.vEnd()[0], -1.0, 1.0, kp_w_ey(cx, rho), wold[11 * N]);
+                            gEH = PQP_G(s.vEnd()[1], cx.lEH, cx.uEH, kp_w_eh(cx, rho), wold[11 * N + 1]);
+                            if (cx.uEH >= kOsqpInfty) gEH = (cx.lEH <= -kOsqpInfty) ? 0.0 : fmin(gEH, 0.0);
+                            else if (cx.lEH <= -kOsqpInfty) gEH = fmax(gEH, 0.0);
+                            PQP_ACC(gEY, -1.0, 1.0)
+                            PQP_ACC(gEH, (cx.lEH <= -kOsqpInfty ? 0.0 : cx.lEH), (cx.uEH >= kOsqpInfty ? 0.0 : cx.uEH))
+                        }
+                        double ra, rb, rc, rs;
+                        kp_apply_At(cx, i, g, gEY, gEH, ra, rb, rc, rs);
+                        c_cert = fmax(c_cert, fmax(fmax(fabs(ra), fabs(rb)), fmax(fabs(rc), fabs(rs))));
+                    }
+                    for (int j = lane; j < ch; j += 32) {
+                        double aty = 0.0;
+                        int t1 = j * d.keep + d.keep - 1;
+                        if (t1 > N - 2) t1 = N - 2;
+                        for (int t = j * d.keep; t <= t1; ++t) aty += s.ds()[t] * s.gD()[2 * N + t + 1];
+                        c_cert = fmax(c_cert, fabs(aty));
+                    }
+#undef PQP_G
+#undef PQP_ACC
+                    inf_nrm = w.max(c_nrm); inf_cert = w.max(c_cert); inf_lhs = w.sum(c_lhs);
+                }
                 pr = w.max(pr); nz = w.max(nz); nax = w.max(nax);
                 prs = w.max(prs); nzs = w.max(nzs); naxs = w.max(naxs);
                 dr = w.max(dr); npx = w.max(npx); naty = w.max(naty);
@@ -957,11 +1058,13 @@ PQP_DEV void kp_solve_path(Warp &w, const DevParams &prm, const BatchView &bv, i
                 pri_res = pr; dua_res = dr;
                 pri_nrm = fmax(nz, nax); dua_nrm = fmax(npx, naty);
                 if (can_check || iter == pm.max_iter) {
-                    // OSQP check_termination (unscaled residuals, strict <); ||q|| = 0
+                    // OSQP check_termination (unscaled residuals, strict <); ||q|| = 0, so the
+                    // dual-infeasibility test (q'dx < 0) never fires
+                    const bool prim_ok = pri_res < pm.eps_abs + pm.eps_rel * pri_nrm;
                     if (pri_res > kOsqpInfty || dua_res > kOsqpInfty) status = PQP_NON_CVX;
-                    else if (pri_res < pm.eps_abs + pm.eps_rel * pri_nrm &&
-                             dua_res < pm.eps_abs + pm.eps_rel * dua_nrm)
-                        status = PQP_SOLVED;
+                    else if (prim_ok && dua_res < pm.eps_abs + pm.eps_rel * dua_nrm) status = PQP_SOLVED;
+                    else if (!prim_ok && primal_infeasible(inf_nrm, inf_lhs, inf_cert, pm.eps_prim_inf))
+                        status = PQP_PRIMAL_INFEASIBLE;
                 }
                 if (status == PQP_UNSOLVED && can_adapt) {
                     // OSQP compute_rho_estimate on the SCALED residuals
@@ -1003,11 +1106,11 @@ PQP_DEV void kp_solve_path(Warp &w, const DevParams &prm, const BatchView &bv, i
         }
         if (status == PQP_UNSOLVED) {
             // max_iter reached: OSQP re-checks with 10x tolerances
-            if (pri_res < 10 * pm.eps_abs + 10 * pm.eps_rel * pri_nrm &&
-                dua_res < 10 * pm.eps_abs + 10 * pm.eps_rel * dua_nrm)
-                status = PQP_SOLVED_INACCURATE;
-            else
-                status = PQP_MAX_ITER_REACHED;
+            const bool prim_ok = pri_res < 10 * pm.eps_abs + 10 * pm.eps_rel * pri_nrm;
+            if (prim_ok && dua_res < 10 * pm.eps_abs + 10 * pm.eps_rel * dua_nrm) status = PQP_SOLVED_INACCURATE;
+            else if (!prim_ok && primal_infeasible(inf_nrm, inf_lhs, inf_cert, 10 * pm.eps_prim_inf))
+                status = PQP_PRIMAL_INFEASIBLE;
+            else status = PQP_MAX_ITER_REACHED;
         }
     }
     // ---- epilogue: getOptimizedPath, solver_kp_as_input.cpp:26-43

@@ -46,8 +46,7 @@ constexpr int kRed2 = 30;  // per separator: Sinv[9] | Off[9] | G[9] | g[3]
 
 // doubles of workspace (global memory) a path needs: E (9N + ch + 2), Dr (nv), Dsl (N)
 // (nv <= 32 chunks of at most 52 slots); laid out at workspace + 16*offset + kWsPerPath*path.
-constexpr int kWsPerPath = 2048;
-PQP_HD size_t kp2_ws_doubles(size_t total_points, size_t batch) { return 16 * total_points + (size_t)kWsPerPath * batch; }
+// (workspace layout helpers: kWsPerPath, kp2_ws_doubles, kp_ws_base, kp_ws_wold -- pqp_device.cuh)
 
 template <int IMAX, int BW>
 struct Kp2 {
@@ -873,7 +872,7 @@ struct Kp2 {
         }
         Smem &s = cx.s;
         s.base = smem; s.N = N; s.ch = d.ch; s.nv = d.nv; s.M = d.M; s.R = (N + 31) / 32;
-        cx.ws = bv.workspace + (size_t)off * 16 + (size_t)prob * kWsPerPath;
+        cx.ws = kp_ws_base(bv.workspace, off, prob);
         const int ch = d.ch;
         const DevParams &pm = prm;
         cx.x0[0] = bv.x0[3 * (size_t)prob];
@@ -959,6 +958,8 @@ struct Kp2 {
             if (!factor(c, cx)) status = PQP_NON_CVX;
             const double alpha = pm.alpha;
             double pri_res = 0, dua_res = 0, pri_nrm = 0, dua_nrm = 0;
+            double inf_nrm = 0, inf_lhs = 0, inf_cert = 0;   // primal-infeasibility certificate of the last check
+            double *wold = kp_ws_wold(cx.ws, N);
             const auto gxi = s.gxi();
         const int *gui = s.gui();
             iter = 1;
@@ -1011,6 +1012,29 @@ struct Kp2 {
                 c.sync();
                 // ---- (b) reduced KKT solve
                 solve(c, cx);
+                // iterations that end in a termination check first park w = v - clamp(v): the check needs
+                // delta_y = W (w_new - w_old) (OSQP update_y / is_primal_infeasible)
+                const bool chk = wold && ((pm.check_termination && (iter % pm.check_termination == 0)) || iter == pm.max_iter);
+                if (chk) {
+                    for (int i = tid; i < N; i += nt) {
+                        double b0, b1, b2, v;
+                        dyn_bounds(cx, i, b0, b1, b2);
+                        double *wo = wold + i;
+                        wo[0] = s.vD(0)[i] - b0; wo[N] = s.vD(1)[i] - b1; wo[2 * N] = s.vD(2)[i] - b2;
+                        v = s.vKB()[i]; wo[3 * N] = v - clampd(v, -pm.kmax, pm.kmax);
+                        v = s.vSB()[i]; wo[4 * N] = v - clampd(v, 0.0, pm.margin);
+                        v = s.vH1()[i]; wo[5 * N] = v - clampd(v, s.lH1()[i], s.uH1()[i]);
+                        v = s.vH3()[i]; wo[6 * N] = v - clampd(v, s.lH3()[i], s.uH3()[i]);
+                        v = s.vS4m()[i]; wo[7 * N] = v - clampd(v, -kOsqpInfty, s.uS4m()[i]);
+                        v = s.vS4p()[i]; wo[8 * N] = v - clampd(v, s.lS4p()[i], kOsqpInfty);
+                        v = s.vS2m()[i]; wo[9 * N] = v - clampd(v, -kOsqpInfty, s.uS2m()[i]);
+                        v = s.vS2p()[i]; wo[10 * N] = v - clampd(v, s.lS2p()[i], kOsqpInfty);
+                        if (i == N - 1) {
+                            v = s.vEnd()[0]; wold[11 * N] = v - clampd(v, -1.0, 1.0);
+                            v = s.vEnd()[1]; wold[11 * N + 1] = v - clampd(v, cx.lEH, cx.uEH);
+                        }
+                    }
+                }
                 // ---- (c) v += alpha (A xt - clamp(v)),  x = alpha xt + (1 - alpha) x
                 for (int i = tid; i < N; i += nt) {
                     const KpRows zt = apply_A(cx, i, s.tr(), s.ts());
@@ -1129,6 +1153,67 @@ struct Kp2 {
 #undef PQP_ROW
 #undef PQP_DUAL
 #undef PQP_VAR
+                    // ---- primal-infeasibility certificate (OSQP is_primal_infeasible) in unscaled terms:
+                    // g = W (w_new - w_old) = E delta_y projected on the cone of the finite bounds;
+                    // ||g||_inf, u'g+ + l'g-, ||A'g||_inf.  The control rows are free (g = 0).
+                    if (chk) {
+                        double c_nrm = 0, c_lhs = 0, c_cert = 0;
+#define PQP_G(V, LO, HI, WW, WO) ((WW) * (((V) - clampd((V), (LO), (HI))) - (WO)))
+#define PQP_ACC(G, LO, HI) { const double g_ = (G); c_nrm = fmax(c_nrm, fabs(g_)); c_lhs += (HI) * fmax(g_, 0.0) + (LO) * fmin(g_, 0.0); }
+                        c.sync();   // the dual-residual pass has consumed gD
+                        for (int i = tid; i < N; i += nt) {
+                            double b0, b1, b2;
+                            dyn_bounds(cx, i, b0, b1, b2);
+                            const double *wo = wold + i;
+                            s.gD(0)[i] = s.WD(0)[i] * ((s.vD(0)[i] - b0) - wo[0]);
+                            s.gD(1)[i] = s.WD(1)[i] * ((s.vD(1)[i] - b1) - wo[N]);
+                            s.gD(2)[i] = s.WD(2)[i] * ((s.vD(2)[i] - b2) - wo[2 * N]);
+                        }
+                        c.sync();
+                        for (int i = tid; i < N; i += nt) {
+                            double b0, b1, b2;
+                            dyn_bounds(cx, i, b0, b1, b2);
+                            const double *wo = wold + i;
+                            KpRows g;
+                            g.D0 = s.gD(0)[i]; g.D1 = s.gD(1)[i]; g.D2 = s.gD(2)[i];
+                            g.KB = PQP_G(s.vKB()[i], -pm.kmax, pm.kmax, s.WKB()[i], wo[3 * N]);
+                            g.SB = PQP_G(s.vSB()[i], 0.0, pm.margin, s.WSB()[i], wo[4 * N]);
+                            g.H1 = PQP_G(s.vH1()[i], s.lH1()[i], s.uH1()[i], s.WH1()[i], wo[5 * N]);
+                            g.H3 = PQP_G(s.vH3()[i], s.lH3()[i], s.uH3()[i], s.WH3()[i], wo[6 * N]);
+                            // one-sided rows: l = -inf keeps the positive part, u = +inf the negative part
+                            g.S4m = fmax(PQP_G(s.vS4m()[i], -kOsqpInfty, s.uS4m()[i], s.WS4()[i], wo[7 * N]), 0.0);
+                            g.S4p = fmin(PQP_G(s.vS4p()[i], s.lS4p()[i], kOsqpInfty, s.WS4()[i], wo[8 * N]), 0.0);
+                            g.S2m = fmax(PQP_G(s.vS2m()[i], -kOsqpInfty, s.uS2m()[i], s.WS2()[i], wo[9 * N]), 0.0);
+                            g.S2p = fmin(PQP_G(s.vS2p()[i], s.lS2p()[i], kOsqpInfty, s.WS2()[i], wo[10 * N]), 0.0);
+                            PQP_ACC(g.D0, b0, b0) PQP_ACC(g.D1, b1, b1) PQP_ACC(g.D2, b2, b2)
+                            PQP_ACC(g.KB, -pm.kmax, pm.kmax) PQP_ACC(g.SB, 0.0, pm.margin)
+                            PQP_ACC(g.H1, s.lH1()[i], s.uH1()[i]) PQP_ACC(g.H3, s.lH3()[i], s.uH3()[i])
+                            PQP_ACC(g.S4m, 0.0, s.uS4m()[i]) PQP_ACC(g.S4p, s.lS4p()[i], 0.0)
+                            PQP_ACC(g.S2m, 0.0, s.uS2m()[i]) PQP_ACC(g.S2p, s.lS2p()[i], 0.0)
+                            double gEY = 0, gEH = 0;
+                            if (i == N - 1) {
+                                gEY = PQP_G(s.vEnd()[0], -1.0, 1.0, s.WEnd()[0], wold[11 * N]);
+                                gEH = PQP_G(s.vEnd()[1], cx.lEH, cx.uEH, s.WEnd()[1], wold[11 * N + 1]);
+                                if (cx.uEH >= kOsqpInfty) gEH = (cx.lEH <= -kOsqpInfty) ? 0.0 : fmin(gEH, 0.0);
+                                else if (cx.lEH <= -kOsqpInfty) gEH = fmax(gEH, 0.0);
+                                PQP_ACC(gEY, -1.0, 1.0)
+                                PQP_ACC(gEH, (cx.lEH <= -kOsqpInfty ? 0.0 : cx.lEH), (cx.uEH >= kOsqpInfty ? 0.0 : cx.uEH))
+                            }
+                            double ra, rb, rc, rs;
+                            apply_At(cx, i, g, gEY, gEH, ra, rb, rc, rs);
+                            c_cert = fmax(c_cert, fmax(fmax(fabs(ra), fabs(rb)), fmax(fabs(rc), fabs(rs))));
+                        }
+                        for (int j = tid; j < ch; j += nt) {
+                            double aty = 0.0;
+                            int t1 = j * keep + keep - 1;
+                            if (t1 > N - 2) t1 = N - 2;
+                            for (int t = j * keep; t <= t1; ++t) aty += s.ds()[t] * s.gD(2)[t + 1];
+                            c_cert = fmax(c_cert, fabs(aty));
+                        }
+#undef PQP_G
+#undef PQP_ACC
+                        inf_nrm = c.max(c_nrm); inf_cert = c.max(c_cert); inf_lhs = c.sum(c_lhs);
+                    }
                     pr = c.max(pr); nz = c.max(nz); nax = c.max(nax);
                     prs = c.max(prs); nzs = c.max(nzs); naxs = c.max(naxs);
                     dr = c.max(dr); npx = c.max(npx); naty = c.max(naty);
@@ -1137,10 +1222,12 @@ struct Kp2 {
                     pri_res = pr; dua_res = dr;
                     pri_nrm = fmax(nz, nax); dua_nrm = fmax(npx, naty);
                     if (can_check || iter == pm.max_iter) {
+                        // OSQP check_termination; q = 0, so the dual-infeasibility test never fires
+                        const bool prim_ok = pri_res < pm.eps_abs + pm.eps_rel * pri_nrm;
                         if (pri_res > kOsqpInfty || dua_res > kOsqpInfty) status = PQP_NON_CVX;
-                        else if (pri_res < pm.eps_abs + pm.eps_rel * pri_nrm &&
-                                 dua_res < pm.eps_abs + pm.eps_rel * dua_nrm)
-                            status = PQP_SOLVED;
+                        else if (prim_ok && dua_res < pm.eps_abs + pm.eps_rel * dua_nrm) status = PQP_SOLVED;
+                        else if (!prim_ok && primal_infeasible(inf_nrm, inf_lhs, inf_cert, pm.eps_prim_inf))
+                            status = PQP_PRIMAL_INFEASIBLE;
                     }
                     if (status == PQP_UNSOLVED && can_adapt) {
                         const double rho = cx.rho;
@@ -1180,11 +1267,11 @@ struct Kp2 {
                 }
             }
             if (status == PQP_UNSOLVED) {
-                if (pri_res < 10 * pm.eps_abs + 10 * pm.eps_rel * pri_nrm &&
-                    dua_res < 10 * pm.eps_abs + 10 * pm.eps_rel * dua_nrm)
-                    status = PQP_SOLVED_INACCURATE;
-                else
-                    status = PQP_MAX_ITER_REACHED;
+                const bool prim_ok = pri_res < 10 * pm.eps_abs + 10 * pm.eps_rel * pri_nrm;
+                if (prim_ok && dua_res < 10 * pm.eps_abs + 10 * pm.eps_rel * dua_nrm) status = PQP_SOLVED_INACCURATE;
+                else if (!prim_ok && primal_infeasible(inf_nrm, inf_lhs, inf_cert, 10 * pm.eps_prim_inf))
+                    status = PQP_PRIMAL_INFEASIBLE;
+                else status = PQP_MAX_ITER_REACHED;
             }
         }
         // ---- epilogue: getOptimizedPath, solver_kp_as_input.cpp:26-43

@@ -146,7 +146,8 @@ struct Kp3 {
         Smem s;
         s.base = smem; s.nv = d.nv; s.M = d.M; s.nS = d.nS; s.ch = d.ch;
         const int M = d.M, L = d.L, ch = d.ch, nS = d.nS, Mst = d.M;
-        double *ws = bv.workspace + (size_t)off * 16 + (size_t)prob * kWsPerPath;  // E[9] per station, [9N..] EUB, EEnd; then D
+        double *ws = kp_ws_base(bv.workspace, off, prob);  // E[9] per station, [9N..] EUB, EEnd; then D
+        double *wold = kp_ws_wold(ws, N);                  // w = v - clamp(v) of the previous iterate (infeasibility check)
         const KpDims ka = kp_dims(N, keep);
         // ---- station / control ownership and padded positions
         St st;
@@ -614,6 +615,7 @@ struct Kp3 {
             if (!refactor()) status = PQP_NON_CVX;
             const double alpha = pm.alpha;
             double pri_res = 0, dua_res = 0, pri_nrm = 0, dua_nrm = 0;
+            double inf_nrm = 0, inf_lhs = 0, inf_cert = 0;   // primal-infeasibility certificate of the last check
             const double d1 = pm.d1, d2 = pm.d2, d3 = pm.d3, d4 = pm.d4;
             iter = 1;
             while (status == PQP_UNSOLVED && iter < pm.max_iter) {
@@ -733,6 +735,25 @@ struct Kp3 {
                 if (ub.live) s.tr()[ub.pos] = tu;
                 c.sync();
                 // ---- (c) v += alpha (A xt - clamp(v)),  x = alpha xt + (1 - alpha) x
+                // (iterations that end in a termination check first park w = v - clamp(v): the
+                //  check needs delta_y = W (w_new - w_old), OSQP update_y / is_primal_infeasible)
+                const bool chk = (pm.check_termination && (iter % pm.check_termination == 0)) || iter == pm.max_iter;
+                if (chk && st.live) {
+                    double *wo = wold + i;
+                    wo[0] = st.vD0 - st.b0; wo[N] = st.vD1 - st.b1; wo[2 * N] = st.vD2 - st.b2;
+                    wo[3 * N] = st.vKB - clamp2(st.vKB, -pm.kmax, pm.kmax);
+                    wo[4 * N] = st.vSB - clamp2(st.vSB, 0.0, pm.margin);
+                    wo[5 * N] = st.vH1 - clamp2(st.vH1, st.lH1, st.uH1);
+                    wo[6 * N] = st.vH3 - clamp2(st.vH3, st.lH3, st.uH3);
+                    wo[7 * N] = st.vS4m - fmin(st.vS4m, st.uS4m);
+                    wo[8 * N] = st.vS4p - fmax(st.vS4p, st.lS4p);
+                    wo[9 * N] = st.vS2m - fmin(st.vS2m, st.uS2m);
+                    wo[10 * N] = st.vS2p - fmax(st.vS2p, st.lS2p);
+                    if (st.last) {
+                        wold[11 * N] = vEY - clamp2(vEY, -1.0, 1.0);
+                        wold[11 * N + 1] = vEH - clamp2(vEH, lEH, uEH);
+                    }
+                }
                 if (st.live) {
                     double zD0 = -ta, zD1 = -tb, zD2 = -tc;
                     if (!st.first) {
@@ -867,19 +888,85 @@ struct Kp3 {
 #undef PQP_ROW
 #undef PQP_DUAL
 #undef PQP_VAR
+                    // ---- primal-infeasibility certificate (OSQP is_primal_infeasible) in unscaled terms:
+                    // g = W (w_new - w_old) = E delta_y, projected on the cone of the finite bounds;
+                    // ||g||_inf, u'g+ + l'g-, ||A'g||_inf.  The control rows are free (g = 0).
+                    double c_nrm = 0, c_lhs = 0, c_cert = 0;
+                    if (chk) {
+#define PQP_G(V, LO, HI, WW, WO) ((WW) * (((V) - clamp2((V), (LO), (HI))) - (WO)))
+#define PQP_ACC(G, LO, HI) { const double g_ = (G); c_nrm = fmax(c_nrm, fabs(g_)); c_lhs += (HI) * fmax(g_, 0.0) + (LO) * fmin(g_, 0.0); }
+                        double gD0 = 0, gD1 = 0, gD2 = 0;
+                        const double *wo = wold + (st.live ? i : 0);
+                        if (st.live) {
+                            gD0 = st.WD0 * ((st.vD0 - st.b0) - wo[0]);
+                            gD1 = st.WD1 * ((st.vD1 - st.b1) - wo[N]);
+                            gD2 = st.WD2 * ((st.vD2 - st.b2) - wo[2 * N]);
+                        }
+                        c.sync();   // the dual-residual pass has consumed ex(0..2)
+                        if (st.live) { s.ex(0)[i] = gD0; s.ex(1)[i] = gD1; s.ex(2)[i] = gD2; }
+                        c.sync();
+                        if (st.live) {
+                            const double gKB = PQP_G(st.vKB, -pm.kmax, pm.kmax, st.WKB, wo[3 * N]);
+                            const double gSB = PQP_G(st.vSB, 0.0, pm.margin, st.WSB, wo[4 * N]);
+                            const double gH1 = PQP_G(st.vH1, st.lH1, st.uH1, st.WH1, wo[5 * N]);
+                            const double gH3 = PQP_G(st.vH3, st.lH3, st.uH3, st.WH3, wo[6 * N]);
+                            // one-sided rows: l = -inf keeps the positive part, u = +inf the negative part
+                            const double g4m = fmax(PQP_G(st.vS4m, -kOsqpInfty, st.uS4m, st.WS4, wo[7 * N]), 0.0);
+                            const double g4p = fmin(PQP_G(st.vS4p, st.lS4p, kOsqpInfty, st.WS4, wo[8 * N]), 0.0);
+                            const double g2m = fmax(PQP_G(st.vS2m, -kOsqpInfty, st.uS2m, st.WS2, wo[9 * N]), 0.0);
+                            const double g2p = fmin(PQP_G(st.vS2p, st.lS2p, kOsqpInfty, st.WS2, wo[10 * N]), 0.0);
+                            PQP_ACC(gD0, st.b0, st.b0) PQP_ACC(gD1, st.b1, st.b1) PQP_ACC(gD2, st.b2, st.b2)
+                            PQP_ACC(gKB, -pm.kmax, pm.kmax) PQP_ACC(gSB, 0.0, pm.margin)
+                            PQP_ACC(gH1, st.lH1, st.uH1) PQP_ACC(gH3, st.lH3, st.uH3)
+                            PQP_ACC(g4m, 0.0, st.uS4m) PQP_ACC(g4p, st.lS4p, 0.0)
+                            PQP_ACC(g2m, 0.0, st.uS2m) PQP_ACC(g2p, st.lS2p, 0.0)
+                            const double s4 = g4m + g4p, s2 = g2m + g2p;
+                            double ra = -gD0 + gH1 + gH3 + s4 + s2;
+                            double rb = -gD1 + d1 * gH1 + d3 * gH3 + d4 * s4 + d2 * s2;
+                            double rc = -gD2 + gKB;
+                            const double rs = gSB - g4m + g4p - g2m + g2p;
+                            if (!st.last) {
+                                const double n0 = s.ex(0)[i + 1], n1 = s.ex(1)[i + 1], n2 = s.ex(2)[i + 1];
+                                ra += n0 + st.q10 * n1;
+                                rb += st.ds * n0 + n1;
+                                rc += st.ds * n1 + n2;
+                            } else {
+                                const double gEY = PQP_G(vEY, -1.0, 1.0, WEY, wold[11 * N]);
+                                double gEH = PQP_G(vEH, lEH, uEH, WEH, wold[11 * N + 1]);
+                                PQP_ACC(gEY, -1.0, 1.0)
+                                if (uEH >= kOsqpInfty) gEH = (lEH <= -kOsqpInfty) ? 0.0 : fmin(gEH, 0.0);
+                                else if (lEH <= -kOsqpInfty) gEH = fmax(gEH, 0.0);
+                                PQP_ACC(gEH, (lEH <= -kOsqpInfty ? 0.0 : lEH), (uEH >= kOsqpInfty ? 0.0 : uEH))
+                                ra += gEY;
+                                rb += gEH;
+                            }
+                            c_cert = fmax(fmax(fabs(ra), fabs(rb)), fmax(fabs(rc), fabs(rs)));
+                        }
+                        if (ub.live) {
+                            double aty = 0.0;
+                            for (int t = ub.t0; t <= ub.t1; ++t) aty += s.dsS()[t] * s.ex(2)[t + 1];
+                            c_cert = fmax(c_cert, fabs(aty));
+                        }
+#undef PQP_G
+#undef PQP_ACC
+                        c_lhs = c.sum(c_lhs);
+                    }
                     {
-                        double red12[12] = {pr, nz, nax, prs, nzs, naxs, dr, npx, naty, drs, npxs, natys};
-                        c.max_n(red12, 12);
-                        pr = red12[0]; nz = red12[1]; nax = red12[2]; prs = red12[3]; nzs = red12[4]; naxs = red12[5];
-                        dr = red12[6]; npx = red12[7]; naty = red12[8]; drs = red12[9]; npxs = red12[10]; natys = red12[11];
+                        double red[14] = {pr, nz, nax, prs, nzs, naxs, dr, npx, naty, drs, npxs, natys, c_nrm, c_cert};
+                        c.max_n(red, 14);
+                        pr = red[0]; nz = red[1]; nax = red[2]; prs = red[3]; nzs = red[4]; naxs = red[5];
+                        dr = red[6]; npx = red[7]; naty = red[8]; drs = red[9]; npxs = red[10]; natys = red[11];
+                        if (chk) { inf_nrm = red[12]; inf_cert = red[13]; inf_lhs = c_lhs; }
                     }
                     pri_res = pr; dua_res = dr;
                     pri_nrm = fmax(nz, nax); dua_nrm = fmax(npx, naty);
                     if (can_check || iter == pm.max_iter) {
+                        // OSQP check_termination; q = 0, so the dual-infeasibility test (q'dx < 0) never fires
+                        const bool prim_ok = pri_res < pm.eps_abs + pm.eps_rel * pri_nrm;
                         if (pri_res > kOsqpInfty || dua_res > kOsqpInfty) status = PQP_NON_CVX;
-                        else if (pri_res < pm.eps_abs + pm.eps_rel * pri_nrm &&
-                                 dua_res < pm.eps_abs + pm.eps_rel * dua_nrm)
-                            status = PQP_SOLVED;
+                        else if (prim_ok && dua_res < pm.eps_abs + pm.eps_rel * dua_nrm) status = PQP_SOLVED;
+                        else if (!prim_ok && primal_infeasible(inf_nrm, inf_lhs, inf_cert, pm.eps_prim_inf))
+                            status = PQP_PRIMAL_INFEASIBLE;
                     }
                     if (status == PQP_UNSOLVED && can_adapt) {
                         const double pn = prs / (fmax(nzs, naxs) + 1e-10);
@@ -912,11 +999,11 @@ struct Kp3 {
                 }
             }
             if (status == PQP_UNSOLVED) {
-                if (pri_res < 10 * pm.eps_abs + 10 * pm.eps_rel * pri_nrm &&
-                    dua_res < 10 * pm.eps_abs + 10 * pm.eps_rel * dua_nrm)
-                    status = PQP_SOLVED_INACCURATE;
-                else
-                    status = PQP_MAX_ITER_REACHED;
+                const bool prim_ok = pri_res < 10 * pm.eps_abs + 10 * pm.eps_rel * pri_nrm;
+                if (prim_ok && dua_res < 10 * pm.eps_abs + 10 * pm.eps_rel * dua_nrm) status = PQP_SOLVED_INACCURATE;
+                else if (!prim_ok && primal_infeasible(inf_nrm, inf_lhs, inf_cert, 10 * pm.eps_prim_inf))
+                    status = PQP_PRIMAL_INFEASIBLE;
+                else status = PQP_MAX_ITER_REACHED;
             }
         }
         // ---- epilogue: getOptimizedPath, solver_kp_as_input.cpp:26-43

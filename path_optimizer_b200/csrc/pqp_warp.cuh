@@ -113,7 +113,7 @@ struct Cta {
     Warp w;
     CtaSync cs;
     int wid, nw;
-    double *scratch;   // >= 12 * nw doubles of shared memory (128 reserved)
+    double *scratch;   // >= 16 * nw doubles of shared memory (128 reserved, nw <= 8)
     PQP_DEV int lane() const { return w.lane(); }
     PQP_DEV int tid() const { return wid * 32 + w.lane(); }
     PQP_DEV int nthreads() const { return nw * 32; }
@@ -141,16 +141,16 @@ struct Cta {
         cs.sync();
         return r;
     }
-    // n (<= 12) max-reductions at once: one shared-memory exchange and two barriers in total
+    // n (<= 16) max-reductions at once: one shared-memory exchange and two barriers in total
     PQP_DEV void max_n(double *v, int n) const {
         for (int k = 0; k < n; ++k) v[k] = w.max(v[k]);
         if (nw == 1) return;
         if (w.lane() == 0)
-            for (int k = 0; k < n; ++k) scratch[wid * 12 + k] = v[k];
+            for (int k = 0; k < n; ++k) scratch[wid * 16 + k] = v[k];
         cs.sync();
         for (int k = 0; k < n; ++k) {
             double r = scratch[k];
-            for (int q = 1; q < nw; ++q) r = fmax(r, scratch[q * 12 + k]);
+            for (int q = 1; q < nw; ++q) r = fmax(r, scratch[q * 16 + k]);
             v[k] = r;
         }
         cs.sync();

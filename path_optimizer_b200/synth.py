@@ -214,3 +214,29 @@ def map_reference_paths(batch, n=200, seed=BASE_SEED, first_path=0, config=3, n_
         off += nb
     out = _pack(n_points, ref, np.zeros(total, dtype=BOUNDS_DTYPE), x0, end_heading)
     return out
+
+
+def infeasible_corridors(batch, n=60, seed=BASE_SEED, first_path=0, config=6):
+    """Corridors no path can satisfy (the reference logs "QP failed", path_optimizer.cpp:184): the
+    vehicle starts ON the reference line (x0 offset 0 is an equality row) but from some station on
+    the hard rows of circles 0 and 2 demand a lateral offset the dynamics cannot reach, or demand
+    two incompatible offsets at once.  Every second path stays feasible as a control."""
+    b = curvy_corridors(batch, n, seed=seed, first_path=first_path, config=config)
+    off = b["offsets"]
+    for p in range(batch):
+        if p % 2 == 1:
+            continue
+        lo, hi = off[p], off[p + 1]
+        kind = (p // 2) % 3
+        bb = b["bounds"][lo:hi]
+        if kind == 0:       # offset >= 0.6 m demanded from station 0 while e_y(0) = x0
+            bb["c0_lb"], bb["c0_ub"] = 0.6, 1.5
+            bb["c2_lb"], bb["c2_ub"] = 0.6, 1.5
+            b["x0"][p, 0] = 0.0
+        elif kind == 1:     # a 3 m jump between stations 1 and 2 (ds = 0.3 m, |kappa| bounded)
+            bb["c0_lb"][2:], bb["c0_ub"][2:] = 3.0, 4.0
+            bb["c2_lb"][2:], bb["c2_ub"][2:] = 3.0, 4.0
+        else:               # rear circle pushed left, front circle pushed right by more than the wheelbase allows
+            bb["c0_lb"][10:], bb["c0_ub"][10:] = 2.0, 2.5
+            bb["c2_lb"][10:], bb["c2_ub"][10:] = -2.5, -2.0
+    return b

@@ -118,3 +118,26 @@ def test_emu_generic_kernel_k_and_kpc(oracle_params, form):
     np.testing.assert_allclose(e["frenet"], o["frenet"], rtol=0, atol=TOL)
     for f in "xyzks":
         np.testing.assert_allclose(e["states"][f], o["states"][f], rtol=0, atol=TOL)
+
+
+@pytest.mark.parametrize("variant", [0, 1, 7])
+def test_emu_primal_infeasible(oracle_params, variant):
+    """Corridors with no feasible path: OSQP's primal-infeasibility certificate fires (status -3) at the
+    same check iteration as in the oracle, the output is NaN, feasible neighbours are untouched."""
+    b = synth.infeasible_corridors(6, 60)
+    e = emu.solve_batch(oracle_params, b, variant=variant)
+    o = oracle.solve_batch(oracle_params, 0, b)
+    assert np.array_equal(e["status"], o["status"]) and np.array_equal(e["iters"], o["iters"])
+    assert (o["status"][0::2] == -3).all() and (o["status"][1::2] == 1).all()
+    assert (o["iters"][0::2] < 4000).all()
+    assert np.isnan(e["frenet"][:60]).all()
+    ok = np.repeat(o["status"] == 1, 60)
+    np.testing.assert_allclose(e["frenet"][ok], o["frenet"][ok], rtol=0, atol=TOL)
+
+
+def test_emu_generic_kernel_primal_infeasible(oracle_params):
+    b = synth.infeasible_corridors(4, 40)
+    e = emu.solve_batch_generic(oracle_params, 1, b)
+    o = oracle.solve_batch(oracle_params, 1, b)
+    assert np.array_equal(e["status"], o["status"]) and np.array_equal(e["iters"], o["iters"])
+    assert (o["status"][0::2] == -3).all()

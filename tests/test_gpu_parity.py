@@ -196,3 +196,26 @@ def test_k_and_kpc_formulations(solver, oracle_params, form, name):
     res = solver.solve(b, formulation=name, max_k=mk, max_kp=mkp)
     ref = oracle.solve_batch(oracle_params, form, b, threads=8, max_k=mk, max_kp=mkp)
     _compare(res, ref)
+
+
+def test_primal_infeasible_corridors(solver):
+    """No feasible path: status -3 at the oracle's check iteration, NaN output, on every kernel class
+    (thread-per-station, chunked, generic fallback via a long keep), neighbours untouched."""
+    prm = oracle.default_params()
+    for n, ds in ((60, 0.3), (180, 0.3), (60, 0.2)):
+        b = synth.infeasible_corridors(16, n)
+        if ds != 0.3:
+            b["ref"]["s"] = np.tile(np.arange(n) * ds, 16)
+        res = solver.solve(b)
+        ref = oracle.solve_batch(prm, 0, b, threads=8)
+        assert np.array_equal(res["status"], ref["status"])
+        assert np.array_equal(res["iters"], ref["iters"])
+        assert (ref["status"][0::2] == -3).all() and (ref["iters"][0::2] < 4000).all()
+        assert np.isnan(res["frenet"][:n]).all()
+        ok = np.repeat(ref["status"] == SOLVED, n)
+        np.testing.assert_allclose(res["frenet"][ok], ref["frenet"][ok], rtol=0, atol=FRENET_TOL)
+    b = synth.infeasible_corridors(8, 50)
+    res = solver.solve(b, "K")
+    ref = oracle.solve_batch(prm, 1, b, threads=8)
+    assert np.array_equal(res["status"], ref["status"]) and np.array_equal(res["iters"], ref["iters"])
+    assert (ref["status"][0::2] == -3).all()
