@@ -20,6 +20,7 @@
 // Reference being replaced: src/solver/solver_kp_as_input.cpp:26-203 + the OSQP solve at
 // src/solver/solver.cpp:66-74.
 #pragma once
+#include <type_traits>
 #include "pqp_kp_core2.cuh"
 
 namespace pqp {
@@ -614,12 +615,34 @@ struct Kp3 {
 
             if (!refactor()) status = PQP_NON_CVX;
             const double alpha = pm.alpha;
-            double pri_res = 0, dua_res = 0, pri_nrm = 0, dua_nrm = 0;
-            double inf_nrm = 0, inf_lhs = 0, inf_cert = 0;   // primal-infeasibility certificate of the last check
             const double d1 = pm.d1, d2 = pm.d2, d3 = pm.d3, d4 = pm.d4;
-            iter = 1;
-            while (status == PQP_UNSOLVED && iter < pm.max_iter) {
-                ++iter;
+            // An iteration that ends in a termination check needs delta_y = W (w_new - w_old) (OSQP
+            // update_y / is_primal_infeasible): w = v - clamp(v) is parked in the workspace at the END
+            // of the iteration before it, which keeps the hot part of the loop free of this code.
+            auto is_check = [&](int k) { return (pm.check_termination && (k % pm.check_termination == 0)) || k == pm.max_iter; };
+            auto park_w = [&]() {
+                if (st.live) {
+                    double *wo = wold + i;
+                    wo[0] = st.vD0 - st.b0; wo[N] = st.vD1 - st.b1; wo[2 * N] = st.vD2 - st.b2;
+                    wo[3 * N] = st.vKB - clamp2(st.vKB, -pm.kmax, pm.kmax);
+                    wo[4 * N] = st.vSB - clamp2(st.vSB, 0.0, pm.margin);
+                    wo[5 * N] = st.vH1 - clamp2(st.vH1, st.lH1, st.uH1);
+                    wo[6 * N] = st.vH3 - clamp2(st.vH3, st.lH3, st.uH3);
+                    wo[7 * N] = st.vS4m - fmin(st.vS4m, st.uS4m);
+                    wo[8 * N] = st.vS4p - fmax(st.vS4p, st.lS4p);
+                    wo[9 * N] = st.vS2m - fmin(st.vS2m, st.uS2m);
+                    wo[10 * N] = st.vS2p - fmax(st.vS2p, st.lS2p);
+                    if (st.last) {
+                        wold[11 * N] = vEY - clamp2(vEY, -1.0, 1.0);
+                        wold[11 * N + 1] = vEH - clamp2(vEH, lEH, uEH);
+                    }
+                }
+            };
+            // One ADMM iteration.  Instantiated twice: the plain form runs in the tight inner loop between
+            // two "events" (termination check / rho adaptation / last iteration), the checked form runs
+            // the event iteration itself -- the rarely executed residual, certificate and refactorisation
+            // code then does not take part in the register allocation of the hot loop.
+            auto step = [&](auto with_check) {
                 // ---- (a) g = W (2 clamp(v) - v) per row; rhs = sigma x + A' g
                 const double gD0 = st.WD0 * (2.0 * st.b0 - st.vD0);
                 const double gD1 = st.WD1 * (2.0 * st.b1 - st.vD1);
@@ -735,25 +758,6 @@ struct Kp3 {
                 if (ub.live) s.tr()[ub.pos] = tu;
                 c.sync();
                 // ---- (c) v += alpha (A xt - clamp(v)),  x = alpha xt + (1 - alpha) x
-                // (iterations that end in a termination check first park w = v - clamp(v): the
-                //  check needs delta_y = W (w_new - w_old), OSQP update_y / is_primal_infeasible)
-                const bool chk = (pm.check_termination && (iter % pm.check_termination == 0)) || iter == pm.max_iter;
-                if (chk && st.live) {
-                    double *wo = wold + i;
-                    wo[0] = st.vD0 - st.b0; wo[N] = st.vD1 - st.b1; wo[2 * N] = st.vD2 - st.b2;
-                    wo[3 * N] = st.vKB - clamp2(st.vKB, -pm.kmax, pm.kmax);
-                    wo[4 * N] = st.vSB - clamp2(st.vSB, 0.0, pm.margin);
-                    wo[5 * N] = st.vH1 - clamp2(st.vH1, st.lH1, st.uH1);
-                    wo[6 * N] = st.vH3 - clamp2(st.vH3, st.lH3, st.uH3);
-                    wo[7 * N] = st.vS4m - fmin(st.vS4m, st.uS4m);
-                    wo[8 * N] = st.vS4p - fmax(st.vS4p, st.lS4p);
-                    wo[9 * N] = st.vS2m - fmin(st.vS2m, st.uS2m);
-                    wo[10 * N] = st.vS2p - fmax(st.vS2p, st.lS2p);
-                    if (st.last) {
-                        wold[11 * N] = vEY - clamp2(vEY, -1.0, 1.0);
-                        wold[11 * N + 1] = vEH - clamp2(vEH, lEH, uEH);
-                    }
-                }
                 if (st.live) {
                     double zD0 = -ta, zD1 = -tb, zD2 = -tc;
                     if (!st.first) {
@@ -789,10 +793,11 @@ struct Kp3 {
                     ub.x = alpha * tu + (1.0 - alpha) * ub.x;
                 }
                 // ---- (d) residuals, termination, adaptive rho
-                const bool can_check = pm.check_termination && (iter % pm.check_termination == 0);
-                const bool can_adapt = pm.adaptive_rho && pm.adaptive_rho_interval &&
-                                       (iter % pm.adaptive_rho_interval == 0);
-                if (can_check || can_adapt || iter == pm.max_iter) {
+                if constexpr (decltype(with_check)::value) {
+                    const bool can_check = pm.check_termination && (iter % pm.check_termination == 0);
+                    const bool can_adapt = pm.adaptive_rho && pm.adaptive_rho_interval &&
+                                           (iter % pm.adaptive_rho_interval == 0);
+                    const bool chk = can_check || iter == pm.max_iter;
                     // publish x (neighbours need station i-1 and the control) and read the scalings
                     c.sync();
                     if (st.live) { s.tr()[st.pos] = st.xa; s.tr()[st.pos + 1] = st.xb; s.tr()[st.pos + 2] = st.xc; }
@@ -956,17 +961,26 @@ struct Kp3 {
                         c.max_n(red, 14);
                         pr = red[0]; nz = red[1]; nax = red[2]; prs = red[3]; nzs = red[4]; naxs = red[5];
                         dr = red[6]; npx = red[7]; naty = red[8]; drs = red[9]; npxs = red[10]; natys = red[11];
-                        if (chk) { inf_nrm = red[12]; inf_cert = red[13]; inf_lhs = c_lhs; }
+                        c_nrm = red[12]; c_cert = red[13];
                     }
-                    pri_res = pr; dua_res = dr;
-                    pri_nrm = fmax(nz, nax); dua_nrm = fmax(npx, naty);
-                    if (can_check || iter == pm.max_iter) {
+                    // No residual or certificate is carried across iterations (registers): the 10x
+                    // re-check OSQP does when max_iter is reached is decided right here.
+                    const double pri_res = pr, dua_res = dr;
+                    const double pri_nrm = fmax(nz, nax), dua_nrm = fmax(npx, naty);
+                    if (chk) {
                         // OSQP check_termination; q = 0, so the dual-infeasibility test (q'dx < 0) never fires
                         const bool prim_ok = pri_res < pm.eps_abs + pm.eps_rel * pri_nrm;
                         if (pri_res > kOsqpInfty || dua_res > kOsqpInfty) status = PQP_NON_CVX;
                         else if (prim_ok && dua_res < pm.eps_abs + pm.eps_rel * dua_nrm) status = PQP_SOLVED;
-                        else if (!prim_ok && primal_infeasible(inf_nrm, inf_lhs, inf_cert, pm.eps_prim_inf))
+                        else if (!prim_ok && primal_infeasible(c_nrm, c_lhs, c_cert, pm.eps_prim_inf))
                             status = PQP_PRIMAL_INFEASIBLE;
+                        if (status == PQP_UNSOLVED && iter == pm.max_iter) {
+                            const bool prim_ok10 = pri_res < 10 * pm.eps_abs + 10 * pm.eps_rel * pri_nrm;
+                            if (prim_ok10 && dua_res < 10 * pm.eps_abs + 10 * pm.eps_rel * dua_nrm) status = PQP_SOLVED_INACCURATE;
+                            else if (!prim_ok10 && primal_infeasible(c_nrm, c_lhs, c_cert, 10 * pm.eps_prim_inf))
+                                status = PQP_PRIMAL_INFEASIBLE;
+                            else status = PQP_MAX_ITER_REACHED;
+                        }
                     }
                     if (status == PQP_UNSOLVED && can_adapt) {
                         const double pn = prs / (fmax(nzs, naxs) + 1e-10);
@@ -997,14 +1011,30 @@ struct Kp3 {
                         }
                     }
                 }
+            };
+            // first iteration after `it` that needs the checked form
+            auto next_event = [&](int it) {
+                int k = pm.max_iter;
+                if (pm.check_termination > 0) { const int q = (it / pm.check_termination + 1) * pm.check_termination; k = q < k ? q : k; }
+                if (pm.adaptive_rho && pm.adaptive_rho_interval > 0) {
+                    const int q = (it / pm.adaptive_rho_interval + 1) * pm.adaptive_rho_interval;
+                    k = q < k ? q : k;
+                }
+                return k;
+            };
+            iter = 1;
+            while (status == PQP_UNSOLVED && iter < pm.max_iter) {
+                const int ev = next_event(iter);
+                while (iter + 1 < ev) {
+                    ++iter;
+                    step(std::false_type{});
+                }
+                if (is_check(ev)) park_w();
+                ++iter;
+                step(std::true_type{});
             }
-            if (status == PQP_UNSOLVED) {
-                const bool prim_ok = pri_res < 10 * pm.eps_abs + 10 * pm.eps_rel * pri_nrm;
-                if (prim_ok && dua_res < 10 * pm.eps_abs + 10 * pm.eps_rel * dua_nrm) status = PQP_SOLVED_INACCURATE;
-                else if (!prim_ok && primal_infeasible(inf_nrm, inf_lhs, inf_cert, 10 * pm.eps_prim_inf))
-                    status = PQP_PRIMAL_INFEASIBLE;
-                else status = PQP_MAX_ITER_REACHED;
-            }
+            // (max_iter <= 1: the loop never ran; zero residuals pass the 10x check)
+            if (status == PQP_UNSOLVED) status = PQP_SOLVED_INACCURATE;
         }
         // ---- epilogue: getOptimizedPath, solver_kp_as_input.cpp:26-43
         const bool has_sol = (status == PQP_SOLVED || status == PQP_SOLVED_INACCURATE || status == PQP_MAX_ITER_REACHED);
