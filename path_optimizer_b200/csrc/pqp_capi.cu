@@ -101,6 +101,7 @@ const Variant kVariants[] = {
     {0, kMaxBandGeneric, 32, (const void *)pqp_kp_solve_kernel, g_smem, g_fits},  // generic fallback (last)
 };
 constexpr int kNumVariants = (int)(sizeof(kVariants) / sizeof(kVariants[0]));
+constexpr int kMaxChunks = PQP_MAX_CHUNKS;   // host-buffer entry point: pipelined chunks per call
 
 int pick_variant(int n, int keep) {
     for (int v = 0; v < kNumVariants; ++v)
@@ -199,7 +200,9 @@ void pqp_destroy(pqp_handle *h) {
     cudaFree(h->d_gen); cudaFreeHost(h->h_gen);
     if (h->env && h->env_free) h->env_free(h->env);
     for (auto &e : h->ev) if (e) cudaEventDestroy(e);
+    for (auto &e : h->ev_chunk) if (e) cudaEventDestroy(e);
     if (h->stream) cudaStreamDestroy(h->stream);
+    if (h->stream2) cudaStreamDestroy(h->stream2);
     delete h;
 }
 
@@ -247,6 +250,8 @@ int pqp_create(pqp_handle **out, const pqp_params *params, int device, int max_b
         PQP_TRY(cudaFuncSetAttribute(kVariants[v].fn, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin));
     PQP_TRY(cudaFuncSetAttribute(pqp_gen_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin));
     PQP_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    PQP_TRY(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
+    for (auto &e : h->ev_chunk) PQP_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     for (auto &e : h->ev) PQP_TRY(cudaEventCreate(&e));
     const size_t B = (size_t)max_batch, T = (size_t)max_total_points;
     PQP_TRY(cudaMalloc(&h->d_n, B * sizeof(int32_t)));
@@ -508,12 +513,11 @@ int pqp_solve_batch(pqp_handle *h, int formulation, int batch, const int32_t *n_
         set_err("batch exceeds the handle's max_batch");
         return PQP_ERR_CAPACITY;
     }
-    // offsets; shape class and shared-memory need per path; per-class longest-first order
+    // offsets; shape class and shared-memory need per path
     long long total = 0;
     h->h_off[0] = 0;
     std::vector<int> cls((size_t)batch);
-    size_t smem_v[kNumVariants] = {0};
-    int count_v[kNumVariants] = {0};
+    std::vector<size_t> need_b((size_t)batch);
     for (int b = 0; b < batch; ++b) {
         const int n = n_points[b];
         if (n < 0) { set_err("negative n_points"); return PQP_ERR_ARG; }
@@ -534,32 +538,42 @@ int pqp_solve_batch(pqp_handle *h, int formulation, int batch, const int32_t *n_
             need = kVariants[v].smem(2, 1);
         }
         cls[b] = v;
-        smem_v[v] = std::max(smem_v[v], need);
-        count_v[v]++;
+        need_b[b] = need;
     }
-    int start_v[kNumVariants + 1];
-    start_v[0] = 0;
-    for (int v = 0; v < kNumVariants; ++v) start_v[v + 1] = start_v[v] + count_v[v];
-    {
+    // The batch is cut into contiguous chunks of paths that are pipelined over two streams: the
+    // upload of chunk k+1 and the download of chunk k-1 overlap the kernels of chunk k (whose CTAs
+    // also fill the SMs the previous chunk's tail leaves idle).  Small batches stay in one chunk.
+    const int n_chunks = std::max(1, std::min(kMaxChunks, batch / 192));
+    int cb[kMaxChunks + 1];
+    cb[0] = 0;
+    for (int k = 1; k <= n_chunks; ++k) {
+        // equal station counts per chunk
+        const long long target = total * k / n_chunks;
+        int b = cb[k - 1];
+        while (b < batch && h->h_off[b] < target) ++b;
+        cb[k] = (k == n_chunks) ? batch : std::max(b, cb[k - 1]);
+    }
+    // per chunk: per-class longest-first order (written into the pinned order array at the chunk's range)
+    int count_cv[kMaxChunks][kNumVariants];
+    int start_cv[kMaxChunks][kNumVariants + 1];
+    size_t smem_cv[kMaxChunks][kNumVariants];
+    for (int k = 0; k < n_chunks; ++k) {
+        for (int v = 0; v < kNumVariants; ++v) { count_cv[k][v] = 0; smem_cv[k][v] = 0; }
+        for (int b = cb[k]; b < cb[k + 1]; ++b) {
+            count_cv[k][cls[b]]++;
+            smem_cv[k][cls[b]] = std::max(smem_cv[k][cls[b]], need_b[b]);
+        }
+        start_cv[k][0] = cb[k];
+        for (int v = 0; v < kNumVariants; ++v) start_cv[k][v + 1] = start_cv[k][v] + count_cv[k][v];
         int fill[kNumVariants];
-        for (int v = 0; v < kNumVariants; ++v) fill[v] = start_v[v];
-        for (int b = 0; b < batch; ++b) h->h_order[fill[cls[b]]++] = b;
+        for (int v = 0; v < kNumVariants; ++v) fill[v] = start_cv[k][v];
+        for (int b = cb[k]; b < cb[k + 1]; ++b) h->h_order[fill[cls[b]]++] = b;
         for (int v = 0; v < kNumVariants; ++v)
-            std::stable_sort(h->h_order + start_v[v], h->h_order + start_v[v + 1],
+            std::stable_sort(h->h_order + start_cv[k][v], h->h_order + start_cv[k][v + 1],
                              [&](int a, int b) { return n_points[a] > n_points[b]; });
     }
     PQP_CUDA(cudaSetDevice(h->device));
-    cudaStream_t st = h->stream;
-    const size_t T = (size_t)total, B = (size_t)batch;
-    PQP_CUDA(cudaEventRecord(h->ev[0], st));
-    PQP_CUDA(cudaMemcpyAsync(h->d_n, n_points, B * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-    PQP_CUDA(cudaMemcpyAsync(h->d_off, h->h_off, (B + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-    PQP_CUDA(cudaMemcpyAsync(h->d_order, h->h_order, B * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-    PQP_CUDA(cudaMemcpyAsync(h->d_ref, ref, T * sizeof(pqp_state), cudaMemcpyHostToDevice, st));
-    PQP_CUDA(cudaMemcpyAsync(h->d_bounds, bounds, T * sizeof(pqp_station_bounds), cudaMemcpyHostToDevice, st));
-    PQP_CUDA(cudaMemcpyAsync(h->d_x0, x0, B * 3 * sizeof(double), cudaMemcpyHostToDevice, st));
-    PQP_CUDA(cudaMemcpyAsync(h->d_end, end_heading, B * sizeof(double), cudaMemcpyHostToDevice, st));
-    PQP_CUDA(cudaEventRecord(h->ev[1], st));
+    const size_t B = (size_t)batch, T = (size_t)total;
     pqp::BatchView bv;
     bv.batch = batch; bv.n_points = h->d_n; bv.offsets = h->d_off; bv.ref = h->d_ref; bv.bounds = h->d_bounds;
     bv.x0 = h->d_x0; bv.end_heading = h->d_end; bv.out_states = h->d_out;
@@ -570,26 +584,55 @@ int pqp_solve_batch(pqp_handle *h, int formulation, int batch, const int32_t *n_
 #ifdef PQP_PHASE_TIMING
     static long long *d_dbg = nullptr;
     if (!d_dbg) cudaMalloc(&d_dbg, sizeof(long long) * 32 * 65536);
-    cudaMemsetAsync(d_dbg, 0, sizeof(long long) * 24 * (size_t)batch, st);
+    cudaMemsetAsync(d_dbg, 0, sizeof(long long) * 24 * (size_t)batch, h->stream);
+    cudaStreamSynchronize(h->stream);
     bv.debug = d_dbg;
 #endif
-    int launches = 0;
-    for (int v = 0; v < kNumVariants; ++v) {
-        if (!count_v[v]) continue;
-        int rc = launch_variant(h, v, bv, count_v[v], h->d_order + start_v[v], smem_v[v], st);
-        if (rc != PQP_OK) return rc;
-        ++launches;
-    }
-    PQP_CUDA(cudaEventRecord(h->ev[2], st));
-    PQP_CUDA(cudaMemcpyAsync(out_states, h->d_out, T * sizeof(pqp_state), cudaMemcpyDeviceToHost, st));
-    if (out_frenet) PQP_CUDA(cudaMemcpyAsync(out_frenet, h->d_frenet, T * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
-    PQP_CUDA(cudaMemcpyAsync(status, h->d_status, B * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     std::vector<int32_t> iters_local;
     int32_t *it_dst = iters;
     if (!it_dst && stats) { iters_local.resize(B); it_dst = iters_local.data(); }
-    if (it_dst) PQP_CUDA(cudaMemcpyAsync(it_dst, h->d_iters, B * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    PQP_CUDA(cudaEventRecord(h->ev[3], st));
-    PQP_CUDA(cudaStreamSynchronize(st));
+    cudaStream_t sts[2] = {h->stream, h->stream2};
+    int launches = 0;
+    // ev[0] start | ev[1] first kernel may start | ev[2] last kernel done | ev[3] all done
+    PQP_CUDA(cudaEventRecord(h->ev[0], sts[0]));
+    PQP_CUDA(cudaStreamWaitEvent(sts[1], h->ev[0], 0));
+    // the offsets array is indexed by absolute path id and read by every chunk's kernel
+    PQP_CUDA(cudaMemcpyAsync(h->d_off, h->h_off, (B + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, sts[0]));
+    PQP_CUDA(cudaMemcpyAsync(h->d_order, h->h_order, B * sizeof(int32_t), cudaMemcpyHostToDevice, sts[0]));
+    PQP_CUDA(cudaEventRecord(h->ev_chunk[0], sts[0]));
+    PQP_CUDA(cudaStreamWaitEvent(sts[1], h->ev_chunk[0], 0));
+    for (int k = 0; k < n_chunks; ++k) {
+        cudaStream_t st = sts[k & 1];
+        const int pb = cb[k], pe = cb[k + 1];
+        if (pe == pb) continue;
+        const size_t o0 = (size_t)h->h_off[pb], nT = (size_t)h->h_off[pe] - o0, nB = (size_t)(pe - pb);
+        PQP_CUDA(cudaMemcpyAsync(h->d_n + pb, n_points + pb, nB * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        PQP_CUDA(cudaMemcpyAsync(h->d_ref + o0, ref + o0, nT * sizeof(pqp_state), cudaMemcpyHostToDevice, st));
+        PQP_CUDA(cudaMemcpyAsync(h->d_bounds + o0, bounds + o0, nT * sizeof(pqp_station_bounds), cudaMemcpyHostToDevice, st));
+        PQP_CUDA(cudaMemcpyAsync(h->d_x0 + 3 * (size_t)pb, x0 + 3 * (size_t)pb, nB * 3 * sizeof(double), cudaMemcpyHostToDevice, st));
+        PQP_CUDA(cudaMemcpyAsync(h->d_end + pb, end_heading + pb, nB * sizeof(double), cudaMemcpyHostToDevice, st));
+        if (k == 0) PQP_CUDA(cudaEventRecord(h->ev[1], st));
+        for (int v = 0; v < kNumVariants; ++v) {
+            if (!count_cv[k][v]) continue;
+            int rc = launch_variant(h, v, bv, count_cv[k][v], h->d_order + start_cv[k][v], smem_cv[k][v], st);
+            if (rc != PQP_OK) return rc;
+            ++launches;
+        }
+        PQP_CUDA(cudaEventRecord(h->ev_chunk[1 + k], st));   // this chunk's kernels done
+        PQP_CUDA(cudaMemcpyAsync(out_states + o0, h->d_out + o0, nT * sizeof(pqp_state), cudaMemcpyDeviceToHost, st));
+        if (out_frenet)
+            PQP_CUDA(cudaMemcpyAsync(out_frenet + 3 * o0, h->d_frenet + 3 * o0, nT * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
+        PQP_CUDA(cudaMemcpyAsync(status + pb, h->d_status + pb, nB * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        if (it_dst) PQP_CUDA(cudaMemcpyAsync(it_dst + pb, h->d_iters + pb, nB * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    }
+    // join: stream 0 waits for every chunk's kernels (ev[2]) and then for stream 1's copies (ev[3])
+    for (int k = 0; k < n_chunks; ++k)
+        if (cb[k + 1] > cb[k] && (k & 1)) PQP_CUDA(cudaStreamWaitEvent(sts[0], h->ev_chunk[1 + k], 0));
+    PQP_CUDA(cudaEventRecord(h->ev[2], sts[0]));
+    PQP_CUDA(cudaEventRecord(h->ev_chunk[kMaxChunks + 1], sts[1]));
+    PQP_CUDA(cudaStreamWaitEvent(sts[0], h->ev_chunk[kMaxChunks + 1], 0));
+    PQP_CUDA(cudaEventRecord(h->ev[3], sts[0]));
+    PQP_CUDA(cudaStreamSynchronize(sts[0]));
 #ifdef PQP_PHASE_TIMING
     {
         std::vector<long long> dbg(24 * (size_t)batch);
@@ -611,6 +654,9 @@ int pqp_solve_batch(pqp_handle *h, int formulation, int batch, const int32_t *n_
     }
 #endif
     if (stats) {
+        // Consecutive, non-overlapping spans of the pipelined call: head (before the first kernel
+        // can start) | middle (first kernel start -> last kernel end; later chunks' copies overlap
+        // it) | tail (remaining downloads).  Their sum is the whole device-side time of the call.
         PQP_CUDA(cudaEventElapsedTime(&stats->h2d_ms, h->ev[0], h->ev[1]));
         PQP_CUDA(cudaEventElapsedTime(&stats->kernel_ms, h->ev[1], h->ev[2]));
         PQP_CUDA(cudaEventElapsedTime(&stats->d2h_ms, h->ev[2], h->ev[3]));

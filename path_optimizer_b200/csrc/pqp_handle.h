@@ -8,6 +8,8 @@
 #include "../../include/pqp.h"
 #include "pqp_device.cuh"
 
+#define PQP_MAX_CHUNKS 4
+
 struct pqp_handle {
     int device = 0;
     int max_batch = 0, max_total = 0;
@@ -17,6 +19,8 @@ struct pqp_handle {
     pqp::DevParams dprm;
     pqp::DevParams dprm_gen[2];
     cudaStream_t stream = nullptr;
+    cudaStream_t stream2 = nullptr;                 // second lane of the host-buffer pipeline
+    cudaEvent_t ev_chunk[PQP_MAX_CHUNKS + 2] = {};  // [0] shared arrays uploaded, [1+k] chunk k kernels done, [last] lane 2 drained
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     // device buffers for the host-pointer entry point
     int32_t *d_n = nullptr, *d_off = nullptr, *d_order = nullptr, *d_status = nullptr, *d_iters = nullptr;
