@@ -202,3 +202,47 @@ def test_plan_full_size(pl, field):
             assert np.abs(r1["states"][f][lo + o:lo + o + k] - want["states"][f][o:o + k]).max(initial=0.0) <= FRENET_TOL
     print(f"plan 2048x200: h2d {r1['stats'].h2d_ms:.3f} ms, kernels {r1['stats'].kernel_ms:.3f} ms, "
           f"d2h {r1['stats'].d2h_ms:.3f} ms, solved {int((r1['status'] == SOLVED).sum())}")
+
+
+def test_cpp_planner_mirror(field, tmp_path):
+    """The C++ host side of the chain (include/pqp_planner.hpp: PathOptimizerGpu::solveWithoutSmoothing batched and
+    with the reference's single-path signature, pqp::Spline = tk::spline's interface) through a compiled driver."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "tests", "cpp", "planner_driver")
+    src = exe + ".cpp"
+    if not os.path.exists(exe) or os.path.getmtime(src) > os.path.getmtime(exe):
+        subprocess.run(["g++", "-O2", "-std=c++17", src, "-o", exe, "-L" + os.path.join(root, "path_optimizer_b200"),
+                        "-lpqp", "-Wl,-rpath," + os.path.join(root, "path_optimizer_b200")], check=True)
+    prm = oracle.default_params()
+    b = synth.map_reference_paths(12, 90, y_range=(-1.0, 1.0), heading_range=0.03, curvature_amp=0.008)
+    B = 12
+    veh = np.column_stack([b["x0"], b["end_heading"]])
+    fin, fout = tmp_path / "in.bin", tmp_path / "out.bin"
+    with open(fin, "wb") as f:
+        f.write(np.array([field["rows"], field["cols"]], dtype=np.int32).tobytes())
+        f.write(np.array([field["resolution"], field["center_x"], field["center_y"]], dtype=np.float64).tobytes())
+        f.write(np.ascontiguousarray(field["distance"], dtype=np.float32).tobytes())
+        f.write(np.int32(B).tobytes()); f.write(b["n_points"].tobytes()); f.write(b["ref"].tobytes())
+        f.write(np.ascontiguousarray(veh).tobytes())
+    subprocess.run([exe, str(fin), str(fout)], check=True)
+    raw = open(fout, "rb").read()
+    n_out = np.frombuffer(raw, dtype=np.int32, count=B)
+    ok = np.frombuffer(raw, dtype=np.int32, count=B, offset=4 * B)
+    status = np.frombuffer(raw, dtype=np.int32, count=B, offset=8 * B)
+    o = 12 * B
+    spl = planner.reference_splines(b)
+    want = oracle.plan(prm, field, b, bounds_mode=planner.BOUNDS_IMPROVED, splines=spl)
+    assert (n_out == want["n_out"]).all() and (ok == want["ok"]).all() and (status == want["status"]).all()
+    for i in range(B):
+        p = np.frombuffer(raw, dtype=STATE_DTYPE, count=n_out[i], offset=o)
+        o += STATE_DTYPE.itemsize * int(n_out[i])
+        lo = b["offsets"][i]
+        for f_ in ("x", "y", "z", "k", "s"):
+            assert np.abs(p[f_] - want["states"][f_][lo:lo + n_out[i]]).max(initial=0.0) <= FRENET_TOL
+    ok0, n0 = np.frombuffer(raw, dtype=np.int32, count=2, offset=o)
+    one = oracle.plan(prm, field, synth.slice_batch(b, 0, 1), bounds_mode=planner.BOUNDS_SIMPLE)
+    assert ok0 == one["ok"][0] and n0 == one["n_out"][0]
+    p0 = np.frombuffer(raw, dtype=STATE_DTYPE, count=n0, offset=o + 8)
+    assert np.abs(p0["x"] - one["states"]["x"][:n0]).max(initial=0.0) <= FRENET_TOL
