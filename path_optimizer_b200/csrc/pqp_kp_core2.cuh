@@ -269,6 +269,40 @@ struct Kp2 {
         for (int k = 0; k < IMAX; ++k) outv[k] = y[k];
     }
 
+    // Column j of K_I^-1 into registers: x = K_I^-1 e_j (the forward sweep starts at row j).  Used by
+    // the thread-per-station kernel to build the dense interior inverses at a refactorisation.
+    PQP_NOINLINE static void local_solve_unit(int j, double *x, const double *fcol, int Mst) {
+        double y[IMAX];
+#pragma unroll
+        for (int k = 0; k < IMAX; ++k) y[k] = (k == j) ? 1.0 : 0.0;
+#pragma unroll
+        for (int k = 1; k < IMAX; ++k) {
+            double p0 = y[k], p1 = 0.0;
+#pragma unroll
+            for (int dd = BW; dd >= 2; --dd)
+                if (k - dd >= 0) {
+                    if (dd & 1) p1 -= PQP_F(k, dd) * y[k - dd];
+                    else p0 -= PQP_F(k, dd) * y[k - dd];
+                }
+            y[k] = (p0 + p1) - PQP_F(k, 1) * y[k - 1];
+        }
+#pragma unroll
+        for (int k = IMAX - 1; k >= 0; --k) {
+            double p0 = y[k] * PQP_F(k, 0), p1 = 0.0;
+#pragma unroll
+            for (int dd = BW; dd >= 2; --dd)
+                if (k + dd < IMAX) {
+                    if (dd & 1) p1 -= PQP_F(k + dd, dd) * y[k + dd];
+                    else p0 -= PQP_F(k + dd, dd) * y[k + dd];
+                }
+            double r = p0 + p1;
+            if (k + 1 < IMAX) r -= PQP_F(k + 1, 1) * y[k + 1];
+            y[k] = r;
+        }
+#pragma unroll
+        for (int k = 0; k < IMAX; ++k) x[k] = y[k];
+    }
+
     // ---- row weights for the current rho, from the workspace E ----------------------------------
     PQP_DEV static void weights(const Cta &c, Ctx &cx) {
         const Smem &s = cx.s;

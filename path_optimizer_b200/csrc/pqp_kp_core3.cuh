@@ -49,6 +49,12 @@ template <int IMAX, int BW, int NW>
 struct Kp3 {
     static constexpr int kT = NW * 32;     // threads = max stations
     using K2 = Kp2<IMAX, BW>;              // reuses the unrolled interior factor / solve
+    // Small interiors keep a DENSE inverse (row-major, [interior][row][kRow]) in place of the band
+    // factor once a refactorisation is done: y = K_I^-1 r_I then is a mat-vec spread over every thread
+    // of the CTA instead of M serial banded substitutions on warp 0 (the longest phase of an iteration).
+    static constexpr bool kDense = (IMAX <= 17);
+    static constexpr int kRow = IMAX + 1;                // row pitch of a dense inverse (even: 128-bit loads stay aligned, 4*lane word offsets)
+    static constexpr int kFacSlots = kDense ? IMAX * kRow : IMAX * (BW + 1);
 
     PQP_HD static Kp3Dims dims(int N, int keep) {
         Kp3Dims d = kp3_dims_raw(N, keep);
@@ -71,15 +77,15 @@ struct Kp3 {
         PQP_DEV double *ex(int k) const { return base + 2 * nv + k * kT; }  // 6 exchange rows of kT
         PQP_DEV double *dsS() const { return ex(6); }                     // ds per station     [kT]
         PQP_DEV double *gS() const { return ex(7); }                      // separator rhs      [nS <= kT]
-        PQP_DEV double *fac() const { return ex(8); }                     // [IMAX*(BW+1)*M]
-        PQP_DEV double *T() const { return fac() + IMAX * (BW + 1) * M; } // spikes T[c][pos], c < 6: [6*nv]
+        PQP_DEV double *fac() const { return ex(8); }                     // [IMAX*(BW+1)*M]; kDense: then K_I^-1 [M][IMAX][kRow]
+        PQP_DEV double *T() const { return fac() + kFacSlots * M; }       // spikes T[c][pos], c < 6: [6*nv]
         PQP_DEV double *Sinv() const { return T() + 6 * nv; }             // [nS*nS]
         PQP_DEV double *red() const { return Sinv() + nS * nS; }          // [kRed2*M] + blocks [27*M]
         PQP_DEV double *blk() const { return red() + kRed2 * M; }         // A|C|Off per chunk [27*M]
         PQP_DEV double *cpl() const { return blk() + 27 * M; }            // coupling coefs [12*M]
     };
     PQP_HD static size_t smem_doubles(const Kp3Dims &d) {
-        return 2 * (size_t)d.nv + 8 * (size_t)kT + (size_t)IMAX * (BW + 1) * d.M + 6 * (size_t)d.nv +
+        return 2 * (size_t)d.nv + 8 * (size_t)kT + (size_t)kFacSlots * d.M + 6 * (size_t)d.nv +
                (size_t)d.nS * d.nS + (size_t)(kRed2 + 27 + 12) * d.M;
     }
 
@@ -610,6 +616,30 @@ struct Kp3 {
                         x0 = y0; x1 = y1; x2 = y2;
                     }
                 }
+                if constexpr (kDense) {
+                    // ---- dense interior inverses: task (p, j) = column j of K_p^-1 from the band factor,
+                    //      kept in registers until every thread is done with the factor, then written
+                    //      over it row-major: kinv[(p * IMAX + k) * kRow + j] (symmetric: column j = row j).
+                    constexpr int kTasks = (IMAX * 17 + kT - 1) / kT;   // M <= 17
+                    double xc[kTasks][IMAX];
+#pragma unroll
+                    for (int t = 0; t < kTasks; ++t) {
+                        const int q = tid + t * kT;
+                        if (q < IMAX * M) K2::local_solve_unit(q / M, xc[t], s.fac() + (q % M), Mst);
+                    }
+                    c.sync();
+#pragma unroll
+                    for (int t = 0; t < kTasks; ++t) {
+                        const int q = tid + t * kT;
+                        if (q < IMAX * M) {
+                            const int j = q / M, p = q % M;
+                            double *kv = s.fac() + (size_t)(p * IMAX + j) * kRow;   // row j
+#pragma unroll
+                            for (int k = 0; k < IMAX; ++k) kv[k] = xc[t][k];
+                            kv[IMAX] = 0.0;
+                        }
+                    }
+                }
                 return !c.any(!ok);   // (contains CTA barriers)
             };
 
@@ -707,8 +737,37 @@ struct Kp3 {
                     s.gS()[3 * p + r] = (a0 + a1) + (a2 + a3);
                 }
                 c.sync();
-                // ---- (b2) y = K_I^-1 r_I on warp 0  ||  x_S = Sinv g on the following warps
-                if (wid == 0) {
+                // ---- (b2) x_S = Sinv g on the first 3M threads  ||  y = K_I^-1 r_I:
+                //      dense interiors: row tasks (p, k) spread over all the OTHER threads of the CTA;
+                //      otherwise M banded substitutions on the lanes of warp 0 (and Sinv g on warps 1..).
+                if constexpr (kDense) {
+                    if (tid < nS) {
+                        const double *row = s.Sinv() + tid;
+                        const double *gS = s.gS();
+                        double a0 = 0, a1 = 0, a2 = 0;
+#pragma unroll 4
+                        for (int k = 0; k < nS; k += 3) {     // nS = 3M
+                            a0 += row[k * nS] * gS[k];
+                            a1 += row[(k + 1) * nS] * gS[k + 1];
+                            a2 += row[(k + 2) * nS] * gS[k + 2];
+                        }
+                        s.ex(3)[tid] = (a0 + a1) + a2;
+                    } else {
+                        const int nw_ = kT - nS;              // worker threads
+                        for (int q = tid - nS; q < IMAX * M; q += nw_) {
+                            const int p = q / IMAX, k = q - p * IMAX;
+                            const double *kv = s.fac() + (size_t)q * kRow;
+                            const double *rI = s.tr() + p * d.CS + 3;
+                            double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+                            for (int j = 0; j < IMAX; ++j) {
+                                if (j & 1) a1 += kv[j] * rI[j];
+                                else a0 += kv[j] * rI[j];
+                            }
+                            s.yv()[p * d.CS + 3 + k] = a0 + a1;
+                        }
+                    }
+                } else if (wid == 0) {
                     if (lane < M) K2::local_solve2(s.tr() + lo, s.yv() + lo, s.fac() + lane, Mst);
                 } else {
                     const int t = tid - 32;
