@@ -219,3 +219,38 @@ def test_primal_infeasible_corridors(solver):
     ref = oracle.solve_batch(prm, 1, b, threads=8)
     assert np.array_equal(res["status"], ref["status"]) and np.array_equal(res["iters"], ref["iters"])
     assert (ref["status"][0::2] == -3).all()
+
+
+def test_pipelined_host_path_mixed_chunks(solver, oracle_params):
+    """pqp_solve_batch cuts batches of >= 384 paths into up to four chunks pipelined over two streams.  A batch
+    whose chunks differ in length mix, shape class (keep 3 and 4, N up to 250) and feasibility must come back
+    exactly as the same paths solved alone: chunk boundaries, per-chunk launch order and the overlapped copies
+    leave no trace.  Host buffers here are plain pageable numpy arrays."""
+    rng = np.random.default_rng(23)
+    B = 640
+    n_points = rng.integers(20, 130, size=B)
+    n_points[rng.integers(0, B, 24)] = rng.integers(130, 250, size=24)      # some long paths (other shape classes)
+    b = synth.curvy_corridors(B, n_points=n_points)
+    off = b["offsets"]
+    for p in rng.integers(0, B, 60):                                          # keep = 4 paths (0.25 m stations)
+        b["ref"]["s"][off[p]:off[p + 1]] = np.arange(n_points[p]) * 0.25
+    bad = synth.infeasible_corridors(2, int(n_points[5]))
+    b["bounds"][off[5]:off[6]] = bad["bounds"][:n_points[5]]                  # one infeasible path in chunk 0
+    b["x0"][5] = bad["x0"][0]
+    res = solver.solve(b)
+    assert res["stats"].kernel_launches >= 4
+    idx = np.r_[0:12, 155:170, 318:330, 470:482, B - 10:B]
+    for lo, hi in ((0, 12), (155, 170), (318, 330), (470, 482), (B - 10, B)):
+        sub = synth.slice_batch(b, lo, hi)
+        ref = oracle.solve_batch(oracle_params, 0, sub, threads=8)
+        assert np.array_equal(res["status"][lo:hi], ref["status"])
+        assert np.array_equal(res["iters"][lo:hi], ref["iters"])
+        np.testing.assert_allclose(res["frenet"][off[lo]:off[hi]], ref["frenet"], rtol=0, atol=FRENET_TOL)
+        np.testing.assert_allclose(res["states"]["s"][off[lo]:off[hi]], ref["states"]["s"], rtol=0, atol=FRENET_TOL)
+    assert res["status"][5] == -3
+    # the same batch again, and as two half batches: bitwise identical
+    res2 = solver.solve(b)
+    assert res2["frenet"].tobytes() == res["frenet"].tobytes() and np.array_equal(res2["iters"], res["iters"])
+    half = solver.solve(synth.slice_batch(b, 0, B // 2))
+    assert half["frenet"].tobytes() == res["frenet"][:off[B // 2]].tobytes()
+    assert len(idx) > 0
