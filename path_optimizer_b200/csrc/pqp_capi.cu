@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -103,9 +104,16 @@ const Variant kVariants[] = {
 constexpr int kNumVariants = (int)(sizeof(kVariants) / sizeof(kVariants[0]));
 constexpr int kMaxChunks = PQP_MAX_CHUNKS;   // host-buffer entry point: pipelined chunks per call
 
+// PQP_SKIP_VARIANTS=<bitmask> (diagnostics only): leave shape classes out of the selection, e.g. to time a
+// fallback kernel on a batch the preferred class would take.
+unsigned skip_mask() {
+    static const unsigned m = [] { const char *e = getenv("PQP_SKIP_VARIANTS"); return e ? (unsigned)strtoul(e, nullptr, 0) : 0u; }();
+    return m;
+}
+
 int pick_variant(int n, int keep) {
     for (int v = 0; v < kNumVariants; ++v)
-        if (kVariants[v].fits(n, keep)) return v;
+        if (!((skip_mask() >> v) & 1u) && kVariants[v].fits(n, keep)) return v;
     return -1;
 }
 
@@ -335,7 +343,7 @@ int pqp_solve_batch_device(pqp_handle *h, int formulation, int batch, int total_
     int v = -1;
     size_t smem = 0;
     for (int cand = 0; cand < kNumVariants && v < 0; ++cand) {
-        bool all = true;
+        bool all = !((skip_mask() >> cand) & 1u);
         size_t need = 0;
         for (int k = k_lo; k <= k_hi; ++k) {
             if (!kVariants[cand].fits(nmax, k)) { all = false; break; }
@@ -584,7 +592,7 @@ int pqp_solve_batch(pqp_handle *h, int formulation, int batch, const int32_t *n_
 #ifdef PQP_PHASE_TIMING
     static long long *d_dbg = nullptr;
     if (!d_dbg) cudaMalloc(&d_dbg, sizeof(long long) * 32 * 65536);
-    cudaMemsetAsync(d_dbg, 0, sizeof(long long) * 24 * (size_t)batch, h->stream);
+    cudaMemsetAsync(d_dbg, 0, sizeof(long long) * 16 * (size_t)batch, h->stream);
     cudaStreamSynchronize(h->stream);
     bv.debug = d_dbg;
 #endif
@@ -635,22 +643,20 @@ int pqp_solve_batch(pqp_handle *h, int formulation, int batch, const int32_t *n_
     PQP_CUDA(cudaStreamSynchronize(sts[0]));
 #ifdef PQP_PHASE_TIMING
     {
-        std::vector<long long> dbg(24 * (size_t)batch);
+        std::vector<long long> dbg(16 * (size_t)batch);
         cudaMemcpy(dbg.data(), bv.debug, dbg.size() * sizeof(long long), cudaMemcpyDeviceToHost);
-        const char *names[10] = {"a1 gD+sync", "a2 rhs+sync", "b1 g+sync", "b2 work", "b2 wait", "b3 xt+2sync", "c update", "-", "-", "d check/rest"};
+        const char *names[6] = {"a1 publish", "a2 rhs", "b1 sep rhs", "b2 Sinv g || y", "b3 x-tilde", "c update"};
         for (int wsel = 0; wsel < 2; ++wsel) {
-            double tot[10] = {0}; double its = 0;
-            for (int b = 0; b < batch; ++b) { for (int k = 0; k < 10; ++k) tot[k] += (double)dbg[(2 * (size_t)b + wsel) * 12 + k]; its += (double)dbg[(2 * (size_t)b + wsel) * 12 + 10]; }
+            double tot[6] = {0}, its = 0;
+            for (int b = 0; b < batch; ++b) {
+                for (int k = 0; k < 6; ++k) tot[k] += (double)dbg[(2 * (size_t)b + wsel) * 8 + k];
+                its += (double)dbg[(2 * (size_t)b + wsel) * 8 + 6];
+            }
             fprintf(stderr, "[phase cycles per iteration, warp %d]", wsel);
             double sum = 0;
-            for (int k = 0; k < 10; ++k) if (names[k][0] != '-') { fprintf(stderr, " %s=%.0f", names[k], tot[k] / its); sum += tot[k] / its; }
-            fprintf(stderr, " | total=%.0f\n", sum);
+            for (int k = 0; k < 6; ++k) { fprintf(stderr, " %s=%.0f", names[k], tot[k] / its); sum += tot[k] / its; }
+            fprintf(stderr, " | total=%.0f (%.0f iterations)\n", sum, its / batch);
         }
-        std::vector<long long> g(8 * (size_t)batch);
-        cudaMemcpy(g.data(), bv.debug + 24 * 65536, g.size() * sizeof(long long), cudaMemcpyDeviceToHost);
-        double tg[8] = {0};
-        for (int b = 0; b < batch; ++b) for (int k = 0; k < 8; ++k) tg[k] += (double)g[8 * (size_t)b + k] / batch;
-        fprintf(stderr, "[cycles per path] setup=%.0f scale=%.0f refactor(all)=%.0f checks(all)=%.0f epilogue=%.0f loop-other=%.0f\n", tg[0], tg[1], tg[2], tg[3], tg[4], tg[5]);
     }
 #endif
     if (stats) {

@@ -672,13 +672,49 @@ struct Kp3 {
             // two "events" (termination check / rho adaptation / last iteration), the checked form runs
             // the event iteration itself -- the rarely executed residual, certificate and refactorisation
             // code then does not take part in the register allocation of the hot loop.
+            // y = K_I^-1 r_I for the dense interiors: row tasks q = (p, k) in [q0, q1) strided over the threads that own
+            // no separator row.  (Spreading them over the b1 phase as well, or splitting b1 over lane pairs, shortens the
+            // per-CTA critical path but measured SLOWER: with two CTAs per SM the idle warps of one CTA are the issue
+            // slots of the other, so what counts is the instruction total, not the balance inside one CTA.)
+            auto dense_rows = [&](int q0, int q1) {
+                if constexpr (kDense) {
+                    const int nw_ = kT - nS;
+                    for (int q = q0 + (tid - nS); q < q1; q += nw_) {
+                        const int p = q / IMAX, k = q - p * IMAX;
+                        const double *kv = s.fac() + (size_t)q * kRow;
+                        const double *rI = s.tr() + p * d.CS + 3;
+                        double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+                        for (int j = 0; j < IMAX; ++j) {
+                            if (j & 1) a1 += kv[j] * rI[j];
+                            else a0 += kv[j] * rI[j];
+                        }
+                        s.yv()[p * d.CS + 3 + k] = a0 + a1;
+                    }
+                }
+            };
+            const int yQ = IMAX * M;
+#ifdef PQP_PHASE_TIMING
+            // clock64() at the phase boundaries, accumulated per warp-0 / warp-1 lead thread in shared scratch
+            // (diagnostic builds only): slots 0..5 = a1, a2, b1, b2, b3, c ; 6 = iterations
+            double *ph_acc = c.scratch + 100 + 8 * (wid & 1);
+            if ((tid & 31) == 0 && wid < 2) for (int k = 0; k < 8; ++k) ph_acc[k] = 0.0;
+            long long ph_t = 0;
+#define PQP_PH(k) if ((tid & 31) == 0 && wid < 2) { const long long now_ = clock64(); ph_acc[k] += (double)(now_ - ph_t); ph_t = now_; }
+#define PQP_PH_START if ((tid & 31) == 0 && wid < 2) { ph_t = clock64(); ph_acc[6] += 1.0; }
+#else
+#define PQP_PH(k)
+#define PQP_PH_START
+#endif
             auto step = [&](auto with_check) {
+                PQP_PH_START
                 // ---- (a) g = W (2 clamp(v) - v) per row; rhs = sigma x + A' g
                 const double gD0 = st.WD0 * (2.0 * st.b0 - st.vD0);
                 const double gD1 = st.WD1 * (2.0 * st.b1 - st.vD1);
                 const double gD2 = st.WD2 * (2.0 * st.b2 - st.vD2);
                 if (st.live) { s.ex(0)[i] = gD0; s.ex(1)[i] = gD1; s.ex(2)[i] = gD2; }
                 c.sync();
+                PQP_PH(0)
                 double tsl = 0.0;   // x-tilde of the slack (decouples exactly)
                 if (st.live) {
                     const double gKB = st.WKB * (2.0 * clamp2(st.vKB, -pm.kmax, pm.kmax) - st.vKB);
@@ -714,6 +750,7 @@ struct Kp3 {
                     s.tr()[ub.pos] = acc;
                 }
                 c.sync();
+                PQP_PH(1)
                 // ---- (b1) separator rhs g = r_S - T' r_I  (threads 0..3M-1; p fastest -> unit stride, conflict-free)
                 if (tid < nS) {
                     const int r = tid / M, p = tid - r * M;
@@ -737,6 +774,7 @@ struct Kp3 {
                     s.gS()[3 * p + r] = (a0 + a1) + (a2 + a3);
                 }
                 c.sync();
+                PQP_PH(2)
                 // ---- (b2) x_S = Sinv g on the first 3M threads  ||  y = K_I^-1 r_I:
                 //      dense interiors: row tasks (p, k) spread over all the OTHER threads of the CTA;
                 //      otherwise M banded substitutions on the lanes of warp 0 (and Sinv g on warps 1..).
@@ -753,19 +791,7 @@ struct Kp3 {
                         }
                         s.ex(3)[tid] = (a0 + a1) + a2;
                     } else {
-                        const int nw_ = kT - nS;              // worker threads
-                        for (int q = tid - nS; q < IMAX * M; q += nw_) {
-                            const int p = q / IMAX, k = q - p * IMAX;
-                            const double *kv = s.fac() + (size_t)q * kRow;
-                            const double *rI = s.tr() + p * d.CS + 3;
-                            double a0 = 0.0, a1 = 0.0;
-#pragma unroll
-                            for (int j = 0; j < IMAX; ++j) {
-                                if (j & 1) a1 += kv[j] * rI[j];
-                                else a0 += kv[j] * rI[j];
-                            }
-                            s.yv()[p * d.CS + 3 + k] = a0 + a1;
-                        }
+                        dense_rows(0, yQ);
                     }
                 } else if (wid == 0) {
                     if (lane < M) K2::local_solve2(s.tr() + lo, s.yv() + lo, s.fac() + lane, Mst);
@@ -785,6 +811,7 @@ struct Kp3 {
                     }
                 }
                 c.sync();
+                PQP_PH(3)
                 // ---- (b3) x-tilde: separators take x_S, interiors y - T [x_Sp ; x_Sq]
                 double ta = 0, tb = 0, tc = 0, tu = 0;
 #define PQP_TX(q) ((s.yv()[q] - (Tq[q] * xl0 + Tq[nvs + (q)] * xl1 + Tq[2 * nvs + (q)] * xl2)) \
@@ -816,6 +843,7 @@ struct Kp3 {
                 if (st.live) { s.tr()[st.pos] = ta; s.tr()[st.pos + 1] = tb; s.tr()[st.pos + 2] = tc; }
                 if (ub.live) s.tr()[ub.pos] = tu;
                 c.sync();
+                PQP_PH(4)
                 // ---- (c) v += alpha (A xt - clamp(v)),  x = alpha xt + (1 - alpha) x
                 if (st.live) {
                     double zD0 = -ta, zD1 = -tb, zD2 = -tc;
@@ -851,6 +879,7 @@ struct Kp3 {
                     ub.v += alpha * (tu - clamp2(ub.v, -kOsqpInfty, kOsqpInfty));
                     ub.x = alpha * tu + (1.0 - alpha) * ub.x;
                 }
+                PQP_PH(5)
                 // ---- (d) residuals, termination, adaptive rho
                 if constexpr (decltype(with_check)::value) {
                     const bool can_check = pm.check_termination && (iter % pm.check_termination == 0);
@@ -1095,6 +1124,12 @@ struct Kp3 {
             // (max_iter <= 1: the loop never ran; zero residuals pass the 10x check)
             if (status == PQP_UNSOLVED) status = PQP_SOLVED_INACCURATE;
         }
+#ifdef PQP_PHASE_TIMING
+        if (bv.debug && (tid & 31) == 0 && wid < 2 && status != PQP_INVALID_PROBLEM) {
+            const double *acc = c.scratch + 100 + 8 * (wid & 1);
+            for (int k = 0; k < 8; ++k) bv.debug[(2 * (size_t)prob + wid) * 8 + k] = (long long)acc[k];
+        }
+#endif
         // ---- epilogue: getOptimizedPath, solver_kp_as_input.cpp:26-43
         const bool has_sol = (status == PQP_SOLVED || status == PQP_SOLVED_INACCURATE || status == PQP_MAX_ITER_REACHED);
         c.sync();
