@@ -716,15 +716,26 @@ struct Kp3 {
                 c.sync();
                 PQP_PH(0)
                 double tsl = 0.0;   // x-tilde of the slack (decouples exactly)
+                // z = clamp(v) of the station-local rows is needed twice per iteration (here and in the update (c)):
+                // computed once, carried across the solve phases
+                double zKB = 0, zSB = 0, zH1 = 0, zH3 = 0, z4m = 0, z4p = 0, z2m = 0, z2p = 0;
                 if (st.live) {
-                    const double gKB = st.WKB * (2.0 * clamp2(st.vKB, -pm.kmax, pm.kmax) - st.vKB);
-                    const double gSB = st.WSB * (2.0 * clamp2(st.vSB, 0.0, pm.margin) - st.vSB);
-                    const double gH1 = st.WH1 * (2.0 * clamp2(st.vH1, st.lH1, st.uH1) - st.vH1);
-                    const double gH3 = st.WH3 * (2.0 * clamp2(st.vH3, st.lH3, st.uH3) - st.vH3);
-                    const double g4m = st.WS4 * (2.0 * fmin(st.vS4m, st.uS4m) - st.vS4m);
-                    const double g4p = st.WS4 * (2.0 * fmax(st.vS4p, st.lS4p) - st.vS4p);
-                    const double g2m = st.WS2 * (2.0 * fmin(st.vS2m, st.uS2m) - st.vS2m);
-                    const double g2p = st.WS2 * (2.0 * fmax(st.vS2p, st.lS2p) - st.vS2p);
+                    zKB = clamp2(st.vKB, -pm.kmax, pm.kmax);
+                    zSB = clamp2(st.vSB, 0.0, pm.margin);
+                    zH1 = clamp2(st.vH1, st.lH1, st.uH1);
+                    zH3 = clamp2(st.vH3, st.lH3, st.uH3);
+                    z4m = fmin(st.vS4m, st.uS4m);
+                    z4p = fmax(st.vS4p, st.lS4p);
+                    z2m = fmin(st.vS2m, st.uS2m);
+                    z2p = fmax(st.vS2p, st.lS2p);
+                    const double gKB = st.WKB * (2.0 * zKB - st.vKB);
+                    const double gSB = st.WSB * (2.0 * zSB - st.vSB);
+                    const double gH1 = st.WH1 * (2.0 * zH1 - st.vH1);
+                    const double gH3 = st.WH3 * (2.0 * zH3 - st.vH3);
+                    const double g4m = st.WS4 * (2.0 * z4m - st.vS4m);
+                    const double g4p = st.WS4 * (2.0 * z4p - st.vS4p);
+                    const double g2m = st.WS2 * (2.0 * z2m - st.vS2m);
+                    const double g2p = st.WS2 * (2.0 * z2p - st.vS2p);
                     const double s4 = g4m + g4p, s2 = g2m + g2p;
                     double ra = -gD0 + gH1 + gH3 + s4 + s2;
                     double rb = -gD1 + d1 * gH1 + d3 * gH3 + d4 * s4 + d2 * s2;
@@ -858,14 +869,14 @@ struct Kp3 {
                     st.vD0 += alpha * (zD0 - st.b0);
                     st.vD1 += alpha * (zD1 - st.b1);
                     st.vD2 += alpha * (zD2 - st.b2);
-                    st.vKB += alpha * (tc - clamp2(st.vKB, -pm.kmax, pm.kmax));
-                    st.vSB += alpha * (tsl - clamp2(st.vSB, 0.0, pm.margin));
-                    st.vH1 += alpha * ((ta + d1 * tb) - clamp2(st.vH1, st.lH1, st.uH1));
-                    st.vH3 += alpha * ((ta + d3 * tb) - clamp2(st.vH3, st.lH3, st.uH3));
-                    st.vS4m += alpha * ((e4 - tsl) - fmin(st.vS4m, st.uS4m));
-                    st.vS4p += alpha * ((e4 + tsl) - fmax(st.vS4p, st.lS4p));
-                    st.vS2m += alpha * ((e2 - tsl) - fmin(st.vS2m, st.uS2m));
-                    st.vS2p += alpha * ((e2 + tsl) - fmax(st.vS2p, st.lS2p));
+                    st.vKB += alpha * (tc - zKB);
+                    st.vSB += alpha * (tsl - zSB);
+                    st.vH1 += alpha * ((ta + d1 * tb) - zH1);
+                    st.vH3 += alpha * ((ta + d3 * tb) - zH3);
+                    st.vS4m += alpha * ((e4 - tsl) - z4m);
+                    st.vS4p += alpha * ((e4 + tsl) - z4p);
+                    st.vS2m += alpha * ((e2 - tsl) - z2m);
+                    st.vS2p += alpha * ((e2 + tsl) - z2p);
                     if (st.last) {
                         vEY += alpha * (ta - clamp2(vEY, -1.0, 1.0));
                         vEH += alpha * (tb - clamp2(vEH, lEH, uEH));
