@@ -141,3 +141,28 @@ def test_emu_generic_kernel_primal_infeasible(oracle_params):
     o = oracle.solve_batch(oracle_params, 1, b)
     assert np.array_equal(e["status"], o["status"]) and np.array_equal(e["iters"], o["iters"])
     assert (o["status"][0::2] == -3).all()
+
+
+PARAM_CASES = {
+    "adaptive_off_maxiter": dict(adaptive_rho=0, max_iter=300),
+    "interval100": dict(adaptive_rho_interval=100),
+    "check7_interval35": dict(check_termination=7, adaptive_rho_interval=35),
+    "no_end_heading_weights": dict(constraint_end_heading=0, KP_curvature_weight=3.0, KP_curvature_rate_weight=50.0,
+                                   KP_deviation_weight=0.7, KP_slack_weight=10.0),
+    "scaling0_rho1": dict(scaling=0, rho=1.0, sigma=1e-5),
+    "check0": dict(check_termination=0, max_iter=120),
+}
+
+
+@pytest.mark.parametrize("case", sorted(PARAM_CASES))
+def test_emu_parameter_sweep(oracle_params, case):
+    """Every setting in pqp_params is honoured the way the oracle (= OSQP's rules) honours it: check and adaptation
+    intervals, adaptive rho off, no end-heading row, other weights, no scaling, no termination checks at all."""
+    p = oracle_params.copy()
+    for k, v in PARAM_CASES[case].items():
+        setattr(p, k, v)
+    b = synth.curvy_corridors(2, n_points=[60, 100])
+    e = emu.solve_batch(p, b, variant=5)
+    o = oracle.solve_batch(p, 0, b)
+    assert np.array_equal(e["status"], o["status"]) and np.array_equal(e["iters"], o["iters"])
+    np.testing.assert_allclose(e["frenet"], o["frenet"], rtol=0, atol=TOL)

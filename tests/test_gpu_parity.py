@@ -254,3 +254,51 @@ def test_pipelined_host_path_mixed_chunks(solver, oracle_params):
     half = solver.solve(synth.slice_batch(b, 0, B // 2))
     assert half["frenet"].tobytes() == res["frenet"][:off[B // 2]].tobytes()
     assert len(idx) > 0
+
+
+PARAM_CASES = {
+    "adaptive_off": dict(adaptive_rho=0),
+    "interval100": dict(adaptive_rho_interval=100),
+    "eps1e-5": dict(eps_abs=1e-5, eps_rel=1e-5),
+    "alpha1": dict(alpha=1.0),
+    "check10": dict(check_termination=10),
+    "check7_interval35": dict(check_termination=7, adaptive_rho_interval=35),
+    "no_end_heading": dict(constraint_end_heading=0),
+    "weights": dict(KP_curvature_weight=3.0, KP_curvature_rate_weight=50.0, KP_deviation_weight=0.7, KP_slack_weight=10.0),
+    "rho1": dict(rho=1.0, sigma=1e-5),
+    "scaling0": dict(scaling=0),
+    "scaling3": dict(scaling=3),
+    "margin": dict(expected_safety_margin=0.6),
+    "maxiter60": dict(max_iter=60),
+    "check0": dict(check_termination=0, max_iter=120),
+    "vehicle": dict(car_length=4.2, car_width=1.8, rear_axle_to_center=1.2, wheel_base=2.6, max_steering_angle=0.45),
+}
+
+
+@pytest.mark.parametrize("case", sorted(PARAM_CASES))
+def test_parameter_sweep(case):
+    """Every field of pqp_params is honoured the way the oracle honours it, on every KP kernel class (thread-per-station,
+    chunked, generic fallback) and on the generic K kernel: intervals, tolerances, relaxation, weights, scaling,
+    end-heading switch, vehicle geometry (d1..d4 recomputed by pqp_params_update_config)."""
+    import ctypes as C
+    from path_optimizer_b200 import _lib
+    from path_optimizer_b200.solver import BatchPathSolver
+    p = oracle.default_params()
+    for k, v in PARAM_CASES[case].items():
+        setattr(p, k, v)
+    _lib.load().pqp_params_update_config(C.byref(p))
+    s = BatchPathSolver(params=p, max_batch=16, max_total_points=16 * 300)
+    b = synth.curvy_corridors(6, n_points=[60, 100, 33, 150, 220, 48])
+    off = b["offsets"]
+    b["ref"]["s"][off[5]:off[6]] = np.arange(48) * 0.2          # keep = 6 -> generic fallback kernel
+    res = s.solve(b)
+    ref = oracle.solve_batch(p, 0, b, threads=6)
+    assert np.array_equal(res["status"], ref["status"]), (res["status"], ref["status"])
+    assert np.array_equal(res["iters"], ref["iters"]), (res["iters"], ref["iters"])
+    np.testing.assert_allclose(res["frenet"], ref["frenet"], rtol=0, atol=FRENET_TOL)
+    small = synth.slice_batch(b, 0, 3)
+    rk = s.solve(small, "K")
+    ok_ = oracle.solve_batch(p, 1, small, threads=3)
+    assert np.array_equal(rk["status"], ok_["status"]) and np.array_equal(rk["iters"], ok_["iters"])
+    np.testing.assert_allclose(rk["frenet"], ok_["frenet"], rtol=0, atol=FRENET_TOL)
+    s.close()
