@@ -11,6 +11,7 @@
 #include <new>
 #include <vector>
 
+#include "pqp_kernels.h"
 #include "pqp_kp_core3.cuh"
 #include "pqp_gen_core.cuh"
 #include "pqp_forms.h"
@@ -21,87 +22,31 @@ thread_local char pqp_g_err[512] = "";
 
 namespace {
 
-constexpr int kMaxBandGeneric = pqp::kMaxBand;
 #define set_err pqp_set_err
 #define g_err pqp_g_err
 
-// One warp (= one CTA) per path.  Shared memory holds the whole ADMM state and the KKT factor.
-__global__ void __launch_bounds__(32)
-pqp_kp_solve_kernel(const __grid_constant__ pqp::DevParams prm, const __grid_constant__ pqp::BatchView bv,
-                    const int32_t *__restrict__ order, int smem_doubles) {
-    extern __shared__ double pqp_smem[];
-    int prob = blockIdx.x;
-    if (order) prob = order[prob];
-    pqp::Warp w;
-    pqp::kp_solve_path(w, prm, bv, prob, pqp_smem, (size_t)smem_doubles);
-}
-
-// Generic banded-QP kernel ("K" and "KPC" formulations): one warp per path, sparse data from the host.
-__global__ void __launch_bounds__(32)
-pqp_gen_solve_kernel(const __grid_constant__ pqp::DevParams prm, const __grid_constant__ pqp::GenView gv, int smem_doubles) {
-    extern __shared__ double pqp_smem[];
-    pqp::Warp w;
-    pqp::gen_solve_qp(w, prm, gv, blockIdx.x, pqp_smem, (size_t)smem_doubles);
-}
-
-// Production kernels: one instantiation per (max interior size, half-bandwidth) shape class.
-// A CTA of kNW warps solves one path: all warps share the per-station phases, warp 0 runs the KKT solve.
-constexpr int kNW = 4;
-template <int IMAX, int BW>
-__global__ void __launch_bounds__(kNW * 32, 3)
-pqp_kp2_solve_kernel(const __grid_constant__ pqp::DevParams prm, const __grid_constant__ pqp::BatchView bv,
-                     const int32_t *__restrict__ order, int smem_doubles) {
-    extern __shared__ double pqp_smem[];
-    int prob = blockIdx.x;
-    if (order) prob = order[prob];
-    pqp::Cta c{pqp::Warp(), pqp::CtaSync(), (int)(threadIdx.x >> 5), kNW, pqp_smem};
-    pqp::Kp2<IMAX, BW>::solve_path(c, prm, bv, prob, pqp_smem + 128, (size_t)smem_doubles - 128);
-}
-
-#ifndef PQP_KP3_MINBLOCKS
-#define PQP_KP3_MINBLOCKS 2
-#endif
-// Thread-per-station kernels (pqp_kp_core3.cuh): NW warps per path, N <= 32*NW stations.
-template <int IMAX, int BW, int NW>
-__global__ void __launch_bounds__(NW * 32, NW <= 4 ? PQP_KP3_MINBLOCKS : 1)
-pqp_kp3_solve_kernel(const __grid_constant__ pqp::DevParams prm, const __grid_constant__ pqp::BatchView bv,
-                     const int32_t *__restrict__ order, int smem_doubles) {
-    extern __shared__ double pqp_smem[];
-    int prob = blockIdx.x;
-    if (order) prob = order[prob];
-    pqp::Cta c{pqp::Warp(), pqp::CtaSync(), (int)(threadIdx.x >> 5), NW, pqp_smem};
-    pqp::Kp3<IMAX, BW, NW>::solve_path(c, prm, bv, prob, pqp_smem + 128, (size_t)smem_doubles - 128);
-}
-
-// Shape classes.  keep_control_steps <= 4 (station spacing >= 0.24 m) maps onto one of the Kp2
-// instantiations; anything else runs on the generic kernel.
-struct Variant {
-    int imax, bw, threads;
-    const void *fn;
-    size_t (*smem)(int n, int keep);
-    bool (*fits)(int n, int keep);
+// Shape classes, in order of preference (the records come from the kernels' own translation units, pqp_kernels.h).
+// keep_control_steps <= 4 (station spacing >= 0.24 m) maps onto one of the Kp3 / Kp2 instantiations; anything else
+// runs on the one-warp generic kernel (last).
+typedef PqpVariant Variant;
+constexpr int kNumVariants = 14;
+struct VariantTable {
+    Variant v[kNumVariants];
+    VariantTable() {
+        int k = 0;
+        pqp_variant_k3_17_6_4_17(&v[k++]); pqp_variant_k3_23_7_4_17(&v[k++]); pqp_variant_k3_27_7_4_17(&v[k++]);
+        pqp_variant_k3_17_6_8_34(&v[k++]); pqp_variant_k3_23_7_8_34(&v[k++]); pqp_variant_k3_27_7_8_34(&v[k++]);
+        pqp_variant_k3_37_7_8_17(&v[k++]);
+        pqp_variant_k2_17_6(&v[k++]); pqp_variant_k2_10_7(&v[k++]); pqp_variant_k2_17_7(&v[k++]);
+        pqp_variant_k2_27_7(&v[k++]); pqp_variant_k2_37_7(&v[k++]); pqp_variant_k2_49_7(&v[k++]);
+        pqp_variant_k1_generic(&v[k++]);
+    }
 };
-template <int IMAX, int BW> size_t v_smem(int n, int keep) {
-    return (128 + pqp::Kp2<IMAX, BW>::smem_doubles(pqp::Kp2<IMAX, BW>::dims(n, keep))) * sizeof(double);
+const Variant *variants() {
+    static const VariantTable t;
+    return t.v;
 }
-template <int IMAX, int BW> bool v_fits(int n, int keep) {
-    return keep <= 10 && pqp::Kp2<IMAX, BW>::fits(pqp::kp2_dims(n, keep));
-}
-size_t g_smem(int n, int keep) { return pqp::kp_smem_doubles(pqp::kp_dims(n, keep)) * sizeof(double); }
-bool g_fits(int, int keep) { return keep <= 10; }
-template <int IMAX, int BW, int NW> size_t v3_smem(int n, int keep) {
-    return (128 + pqp::Kp3<IMAX, BW, NW>::smem_doubles(pqp::Kp3<IMAX, BW, NW>::dims(n, keep))) * sizeof(double);
-}
-template <int IMAX, int BW, int NW> bool v3_fits(int n, int keep) { return pqp::Kp3<IMAX, BW, NW>::fits(n, keep); }
-#define PQP_VARIANT3(I, B, W) {I, B, W * 32, (const void *)pqp_kp3_solve_kernel<I, B, W>, v3_smem<I, B, W>, v3_fits<I, B, W>}
-#define PQP_VARIANT(I, B) {I, B, kNW * 32, (const void *)pqp_kp2_solve_kernel<I, B>, v_smem<I, B>, v_fits<I, B>}
-const Variant kVariants[] = {
-    PQP_VARIANT3(17, 6, 4), PQP_VARIANT3(23, 7, 4), PQP_VARIANT3(27, 7, 4), PQP_VARIANT3(37, 7, 8),
-    PQP_VARIANT(17, 6), PQP_VARIANT(10, 7), PQP_VARIANT(17, 7), PQP_VARIANT(27, 7), PQP_VARIANT(37, 7),
-    PQP_VARIANT(49, 7),
-    {0, kMaxBandGeneric, 32, (const void *)pqp_kp_solve_kernel, g_smem, g_fits},  // generic fallback (last)
-};
-constexpr int kNumVariants = (int)(sizeof(kVariants) / sizeof(kVariants[0]));
+#define kVariants (variants())
 constexpr int kMaxChunks = PQP_MAX_CHUNKS;   // host-buffer entry point: pipelined chunks per call
 
 // PQP_SKIP_VARIANTS=<bitmask> (diagnostics only): leave shape classes out of the selection, e.g. to time a
@@ -256,7 +201,7 @@ int pqp_create(pqp_handle **out, const pqp_params *params, int device, int max_b
     // fails with cudaErrorNoKernelImageForDevice / InvalidDeviceFunction on anything but sm_100
     for (int v = 0; v < kNumVariants; ++v)
         PQP_TRY(cudaFuncSetAttribute(kVariants[v].fn, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin));
-    PQP_TRY(cudaFuncSetAttribute(pqp_gen_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin));
+    PQP_TRY(cudaFuncSetAttribute(pqp_gen_kernel_fn(), cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin));
     PQP_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     PQP_TRY(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
     for (auto &e : h->ev_chunk) PQP_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -472,8 +417,11 @@ static int solve_batch_generic(pqp_handle *h, int formulation, int batch, const 
     gv.sep = (const int32_t *)(D + o_sep); gv.out_idx = (const int32_t *)(D + o_oi);
     gv.ref = h->d_ref; gv.out_states = h->d_out; gv.out_frenet = out_frenet ? h->d_frenet : nullptr;
     gv.status = h->d_status; gv.iters = h->d_iters;
-    pqp_gen_solve_kernel<<<batch, 32, smem, st>>>(h->dprm_gen[formulation == PQP_FORM_K ? 0 : 1], gv, (int)(smem / sizeof(double)));
-    PQP_CUDA(cudaGetLastError());
+    {
+        int smem_doubles = (int)(smem / sizeof(double));
+        void *args[] = {(void *)&h->dprm_gen[formulation == PQP_FORM_K ? 0 : 1], (void *)&gv, (void *)&smem_doubles};
+        PQP_CUDA(cudaLaunchKernel(pqp_gen_kernel_fn(), dim3(batch), dim3(32), args, smem, st));
+    }
     PQP_CUDA(cudaEventRecord(h->ev[2], st));
     PQP_CUDA(cudaMemcpyAsync(out_states, h->d_out, T * sizeof(pqp_state), cudaMemcpyDeviceToHost, st));
     if (out_frenet) PQP_CUDA(cudaMemcpyAsync(out_frenet, h->d_frenet, T * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));

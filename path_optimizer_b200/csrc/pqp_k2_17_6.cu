@@ -1,0 +1,3 @@
+// one kernel per translation unit: see pqp_kernels.h
+#include "pqp_kernel_tu.cuh"
+PQP_KP2_TU(17, 6)

@@ -1,0 +1,3 @@
+// one kernel per translation unit: see pqp_kernels.h
+#include "pqp_kernel_tu.cuh"
+PQP_KP3_TU(27, 7, 4, 17)

@@ -1,0 +1,51 @@
+// pqp_kernel_tu.cuh -- kernel entry templates + the macros that turn a translation unit into exactly one
+// compiled kernel and its PqpVariant record (see pqp_kernels.h for why there is one kernel per file).
+#pragma once
+#include "pqp_kernels.h"
+#include "pqp_kp_core3.cuh"
+
+// Chunked kernels: a CTA of kNW warps solves one path: all warps share the per-station phases, warp 0 runs the KKT solve.
+constexpr int kNW = 4;
+template <int IMAX, int BW>
+__global__ void __launch_bounds__(kNW * 32, 3)
+pqp_kp2_solve_kernel(const __grid_constant__ pqp::DevParams prm, const __grid_constant__ pqp::BatchView bv,
+                     const int32_t *__restrict__ order, int smem_doubles) {
+    extern __shared__ double pqp_smem[];
+    int prob = blockIdx.x;
+    if (order) prob = order[prob];
+    pqp::Cta c{pqp::Warp(), pqp::CtaSync(), (int)(threadIdx.x >> 5), kNW, pqp_smem};
+    pqp::Kp2<IMAX, BW>::solve_path(c, prm, bv, prob, pqp_smem + 128, (size_t)smem_doubles - 128);
+}
+
+#ifndef PQP_KP3_MINBLOCKS
+#define PQP_KP3_MINBLOCKS 2
+#endif
+// Thread-per-station kernels (pqp_kp_core3.cuh): NW warps per path, N <= 32*NW stations.
+template <int IMAX, int BW, int NW, int MMAX>
+__global__ void __launch_bounds__(NW * 32, NW <= 4 ? PQP_KP3_MINBLOCKS : 1)
+pqp_kp3_solve_kernel(const __grid_constant__ pqp::DevParams prm, const __grid_constant__ pqp::BatchView bv,
+                     const int32_t *__restrict__ order, int smem_doubles) {
+    extern __shared__ double pqp_smem[];
+    int prob = blockIdx.x;
+    if (order) prob = order[prob];
+    pqp::Cta c{pqp::Warp(), pqp::CtaSync(), (int)(threadIdx.x >> 5), NW, pqp_smem};
+    pqp::Kp3<IMAX, BW, NW, MMAX>::solve_path(c, prm, bv, prob, pqp_smem + 128, (size_t)smem_doubles - 128);
+}
+
+#define PQP_KP3_TU(I, B, W, MM)                                                                                   \
+    static size_t tu_smem(int n, int keep) {                                                                      \
+        return (128 + pqp::Kp3<I, B, W, MM>::smem_doubles(pqp::Kp3<I, B, W, MM>::dims(n, keep))) * sizeof(double); \
+    }                                                                                                             \
+    static bool tu_fits(int n, int keep) { return pqp::Kp3<I, B, W, MM>::fits(n, keep); }                         \
+    void pqp_variant_k3_##I##_##B##_##W##_##MM(PqpVariant *out) {                                                 \
+        *out = PqpVariant{I, B, W * 32, (const void *)pqp_kp3_solve_kernel<I, B, W, MM>, tu_smem, tu_fits};       \
+    }
+
+#define PQP_KP2_TU(I, B)                                                                                        \
+    static size_t tu_smem(int n, int keep) {                                                                    \
+        return (128 + pqp::Kp2<I, B>::smem_doubles(pqp::Kp2<I, B>::dims(n, keep))) * sizeof(double);            \
+    }                                                                                                           \
+    static bool tu_fits(int n, int keep) { return keep <= 10 && pqp::Kp2<I, B>::fits(pqp::kp2_dims(n, keep)); } \
+    void pqp_variant_k2_##I##_##B(PqpVariant *out) {                                                            \
+        *out = PqpVariant{I, B, kNW * 32, (const void *)pqp_kp2_solve_kernel<I, B>, tu_smem, tu_fits};          \
+    }

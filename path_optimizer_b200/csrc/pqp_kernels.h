@@ -1,0 +1,33 @@
+// pqp_kernels.h -- one record per compiled solve kernel ("shape class").  Every kernel lives in its own
+// translation unit (pqp_k*.cu): at the 255-register limit ptxas' allocation for one kernel changes with whatever
+// else is compiled next to it (measured: the same source ran 3x slower after unrelated instantiations were added to
+// the same file), so the kernels are compiled in isolation and only these records cross the boundary.
+#pragma once
+#include <stddef.h>
+
+struct PqpVariant {
+    int imax, bw, threads;
+    const void *fn;                      // __global__ entry, for cudaLaunchKernel / cudaFuncSetAttribute
+    size_t (*smem)(int n, int keep);     // dynamic shared memory (bytes) for a path of n stations
+    bool (*fits)(int n, int keep);
+};
+
+#define PQP_DECLARE_VARIANT(name) void pqp_variant_##name(PqpVariant *out);
+// thread-per-station kernels Kp3<IMAX, BW, NW, MMAX>
+PQP_DECLARE_VARIANT(k3_17_6_4_17)
+PQP_DECLARE_VARIANT(k3_23_7_4_17)
+PQP_DECLARE_VARIANT(k3_27_7_4_17)
+PQP_DECLARE_VARIANT(k3_17_6_8_34)
+PQP_DECLARE_VARIANT(k3_23_7_8_34)
+PQP_DECLARE_VARIANT(k3_27_7_8_34)
+PQP_DECLARE_VARIANT(k3_37_7_8_17)
+// chunked kernels Kp2<IMAX, BW>
+PQP_DECLARE_VARIANT(k2_17_6)
+PQP_DECLARE_VARIANT(k2_10_7)
+PQP_DECLARE_VARIANT(k2_17_7)
+PQP_DECLARE_VARIANT(k2_27_7)
+PQP_DECLARE_VARIANT(k2_37_7)
+PQP_DECLARE_VARIANT(k2_49_7)
+// one-warp generic KP kernel (any keep <= 10) and the generic banded-QP kernel of "K" / "KPC"
+PQP_DECLARE_VARIANT(k1_generic)
+const void *pqp_gen_kernel_fn();

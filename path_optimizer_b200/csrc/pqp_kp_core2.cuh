@@ -48,7 +48,9 @@ constexpr int kRed2 = 30;  // per separator: Sinv[9] | Off[9] | G[9] | g[3]
 // (nv <= 32 chunks of at most 52 slots); laid out at workspace + 16*offset + kWsPerPath*path.
 // (workspace layout helpers: kWsPerPath, kp2_ws_doubles, kp_ws_base, kp_ws_wold -- pqp_device.cuh)
 
-template <int IMAX, int BW>
+// TAG only separates the out-of-line helpers of different users: each kernel gets its own copies, so the register
+// needs of one kernel do not leak into another through a shared callee.
+template <int IMAX, int BW, int TAG = 0>
 struct Kp2 {
     // ---- shared-memory layout -----------------------------------------------------------------
     // Per-station fields are tiled: station i = 32*r + l lives at st[(r*kNF + f)*32 + l].  For a lane

@@ -29,12 +29,12 @@ struct Kp3Dims {
     int N, keep, ch, h, L, M, I, CS, nv, bw, nS;
 };
 
-// separators every L stations with at most 17 of them (the dense separator inverse is (3M)^2)
-PQP_HD Kp3Dims kp3_dims_raw(int N, int keep) {
+// separators every L stations with at most mmax of them (the dense separator inverse is (3M)^2)
+PQP_HD Kp3Dims kp3_dims_raw(int N, int keep, int mmax = 17) {
     const KpDims a = kp_dims(N, keep);
     Kp3Dims d;
     d.N = N; d.keep = keep; d.ch = a.ch; d.h = a.h; d.bw = a.bw;
-    int L = keep * ((N - 1) / (17 * keep) + 1);   // smallest multiple of keep with (N-1)/L < 17
+    int L = keep * ((N - 1) / (mmax * keep) + 1);   // smallest multiple of keep with (N-1)/L < mmax
     if (L < 2) L = 2;
     d.L = L;
     d.M = (N - 1) / L + 1;
@@ -45,27 +45,30 @@ PQP_HD Kp3Dims kp3_dims_raw(int N, int keep) {
     return d;
 }
 
-template <int IMAX, int BW, int NW>
+// MMAX = most separators a path may have: 17 (two CTAs of four warps per SM) or 34 for the eight-warp form, which
+// keeps the interiors of a 200-station path at 17 unknowns instead of 37 (the interior solves are the serial part).
+template <int IMAX, int BW, int NW, int MMAX = 17>
 struct Kp3 {
     static constexpr int kT = NW * 32;     // threads = max stations
-    using K2 = Kp2<IMAX, BW>;              // reuses the unrolled interior factor / solve
+    using K2 = Kp2<IMAX, BW, NW * 100 + MMAX>;   // reuses the unrolled interior factor / solve (own copies per kernel)
     // Small interiors keep a DENSE inverse (row-major, [interior][row][kRow]) in place of the band
     // factor once a refactorisation is done: y = K_I^-1 r_I then is a mat-vec spread over every thread
     // of the CTA instead of M serial banded substitutions on warp 0 (the longest phase of an iteration).
-    static constexpr bool kDense = (IMAX <= 17);
+    static constexpr bool kDense = (IMAX <= 17) && (MMAX <= 17);
+    static constexpr int kSolveT = (MMAX + 31) / 32 * 32;   // threads that run the banded interior solves (non-dense form)
     static constexpr int kRow = IMAX + 1;                // row pitch of a dense inverse (even: 128-bit loads stay aligned, 4*lane word offsets)
     static constexpr int kFacSlots = kDense ? IMAX * kRow : IMAX * (BW + 1);
 
     PQP_HD static Kp3Dims dims(int N, int keep) {
-        Kp3Dims d = kp3_dims_raw(N, keep);
+        Kp3Dims d = kp3_dims_raw(N, keep, MMAX);
         d.CS = (IMAX + 3) | 1;
         d.nv = d.M * d.CS;
         return d;
     }
     PQP_HD static bool fits(int N, int keep) {
         if (N < 2 || N > kT || keep < 1 || keep > 10) return false;
-        const Kp3Dims d = kp3_dims_raw(N, keep);
-        return d.I <= IMAX && d.bw <= BW && d.M <= 17;
+        const Kp3Dims d = kp3_dims_raw(N, keep, MMAX);
+        return d.I <= IMAX && d.bw <= BW && d.M <= MMAX && 6 * d.M <= kT && kSolveT + 3 * d.M <= kT;
     }
 
     // ---- shared memory (doubles) ---------------------------------------------------------------
@@ -190,12 +193,14 @@ struct Kp3 {
             ub.t1 = j * keep + keep - 1;
             if (ub.t1 > N - 2) ub.t1 = N - 2;
         }
-        // partition lanes (warp 0): interior after separator p
+        // partition threads (the first M): interior after separator p
         int lo = 3, cnt = 0;
-        if (wid == 0 && lane < M) {
-            const int g0 = kp_gx(ka, lane * L);
-            const int g1 = (lane + 1 < M) ? kp_gx(ka, (lane + 1) * L) : ka.nred;
-            lo = lane * d.CS + 3;
+        const bool solver = (MMAX <= 32) ? (wid == 0 && lane < M) : (tid < M);
+        const int sid = (MMAX <= 32) ? lane : tid;      // interior owned by a solver thread
+        if (solver) {
+            const int g0 = kp_gx(ka, sid * L);
+            const int g1 = (sid + 1 < M) ? kp_gx(ka, (sid + 1) * L) : ka.nred;
+            lo = sid * d.CS + 3;
             cnt = g1 - g0 - 3;
         }
         // end-heading window, solver_kp_as_input.cpp:193-201
@@ -444,7 +449,7 @@ struct Kp3 {
                 //      cpl[p] = left  (transition e -> e+1):  N0 N1 N2 ds q
                 //               right (transition e2-1 -> e2): W0 W1 W2 ds q ; + flags
                 int ok = 1;
-                if (wid == 0 && lane < M) ok = K2::local_factor(s.fac() + lane, Mst);
+                if (solver) ok = K2::local_factor(s.fac() + sid, Mst);
                 if (st.live && i >= 1) {
                     if ((i - 1) % L == 0) {          // first interior station of chunk p: owns the LEFT coupling
                         double *cp = s.cpl() + 12 * ((i - 1) / L);
@@ -620,7 +625,7 @@ struct Kp3 {
                     // ---- dense interior inverses: task (p, j) = column j of K_p^-1 from the band factor,
                     //      kept in registers until every thread is done with the factor, then written
                     //      over it row-major: kinv[(p * IMAX + k) * kRow + j] (symmetric: column j = row j).
-                    constexpr int kTasks = (IMAX * 17 + kT - 1) / kT;   // M <= 17
+                    constexpr int kTasks = (IMAX * MMAX + kT - 1) / kT;
                     double xc[kTasks][IMAX];
 #pragma unroll
                     for (int t = 0; t < kTasks; ++t) {
@@ -804,10 +809,10 @@ struct Kp3 {
                     } else {
                         dense_rows(0, yQ);
                     }
-                } else if (wid == 0) {
-                    if (lane < M) K2::local_solve2(s.tr() + lo, s.yv() + lo, s.fac() + lane, Mst);
+                } else if (tid < kSolveT) {
+                    if (solver) K2::local_solve2(s.tr() + lo, s.yv() + lo, s.fac() + sid, Mst);
                 } else {
-                    const int t = tid - 32;
+                    const int t = tid - kSolveT;
                     if (t < nS) {
                         const double *row = s.Sinv() + t;
                         const double *gS = s.gS();

@@ -35,6 +35,8 @@ void *lane_main(void *p) {
     case 5: pqp::Kp3<17, 6, 4>::solve_path(c, *a->prm, *a->bv, a->prob, sm, cap); break;
     case 6: pqp::Kp3<23, 7, 4>::solve_path(c, *a->prm, *a->bv, a->prob, sm, cap); break;
     case 7: pqp::Kp3<27, 7, 8>::solve_path(c, *a->prm, *a->bv, a->prob, sm, cap); break;
+    case 8: pqp::Kp3<17, 6, 8, 34>::solve_path(c, *a->prm, *a->bv, a->prob, sm, cap); break;
+    case 9: pqp::Kp3<23, 7, 8, 34>::solve_path(c, *a->prm, *a->bv, a->prob, sm, cap); break;
     default: pqp::kp_solve_path(w, *a->prm, *a->bv, a->prob, sm, cap);   // generic core: one warp
     }
     return nullptr;
@@ -48,7 +50,7 @@ extern "C" int kp_emu_solve_batch(const pqp_params *params, int batch, const int
                                   int32_t *status, int32_t *iters, int smem_bytes, int variant, int nwarps) {
     if (variant == 0 || nwarps < 1) nwarps = 1;
     if (variant == 5 || variant == 6) nwarps = 4;
-    if (variant == 7) nwarps = 8;
+    if (variant >= 7) nwarps = 8;
     pqp::DevParams prm = pqp::dev_params_from(*params);
     pqp::BatchView bv;
     bv.batch = batch; bv.n_points = n_points; bv.offsets = offsets; bv.ref = ref; bv.bounds = bounds;
