@@ -66,6 +66,47 @@ int pick_variant(int n, int keep) {
 
 
 extern "C" {
+static int launch_variant(pqp_handle *h, int v, const pqp::BatchView &bv, int count, const int32_t *d_order,
+                          size_t smem_bytes, cudaStream_t st);
+}
+
+int pqp_launch_kp_classes(pqp_handle *h, const pqp::BatchView &bv, int batch, const int32_t *n, const int32_t *off,
+                          const pqp_state *ref, cudaStream_t st, int *launches) {
+    std::vector<int> cls((size_t)batch);
+    size_t smem_v[kNumVariants] = {0};
+    int count_v[kNumVariants] = {0}, start_v[kNumVariants + 1];
+    for (int b = 0; b < batch; ++b) {
+        int v = kNumVariants - 1, keep = 1;
+        if (n[b] >= 2) {
+            keep = pqp_keep_control_steps(PQP_FORM_KP, ref + off[b], n[b]);
+            const int pv = pick_variant(n[b], keep);
+            if (pv >= 0) v = pv;
+        }
+        const int ke = std::min(std::max(keep, 1), 10), ne = std::max((int)n[b], 2);
+        size_t need = kVariants[v].smem(ne, ke);
+        if (need > (size_t)h->smem_optin) { v = kNumVariants - 1; need = kVariants[v].smem(2, 1); }   // reports PQP_INVALID_PROBLEM
+        cls[b] = v;
+        smem_v[v] = std::max(smem_v[v], need);
+        count_v[v]++;
+    }
+    start_v[0] = 0;
+    for (int v = 0; v < kNumVariants; ++v) start_v[v + 1] = start_v[v] + count_v[v];
+    int fill[kNumVariants];
+    for (int v = 0; v < kNumVariants; ++v) fill[v] = start_v[v];
+    for (int b = 0; b < batch; ++b) h->h_order[fill[cls[b]]++] = b;
+    for (int v = 0; v < kNumVariants; ++v)
+        std::stable_sort(h->h_order + start_v[v], h->h_order + start_v[v + 1], [&](int a, int b) { return n[a] > n[b]; });
+    PQP_CUDA(cudaMemcpyAsync(h->d_order, h->h_order, (size_t)batch * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    for (int v = 0; v < kNumVariants; ++v) {
+        if (!count_v[v]) continue;
+        int rc = launch_variant(h, v, bv, count_v[v], h->d_order + start_v[v], smem_v[v], st);
+        if (rc != PQP_OK) return rc;
+        if (launches) ++*launches;
+    }
+    return PQP_OK;
+}
+
+extern "C" {
 
 const char *pqp_last_error(void) { return g_err; }
 
@@ -604,6 +645,18 @@ int pqp_solve_batch(pqp_handle *h, int formulation, int batch, const int32_t *n_
             double sum = 0;
             for (int k = 0; k < 6; ++k) { fprintf(stderr, " %s=%.0f", names[k], tot[k] / its); sum += tot[k] / its; }
             fprintf(stderr, " | total=%.0f (%.0f iterations)\n", sum, its / batch);
+        }
+        {
+            std::vector<long long> g(4 * (size_t)batch);
+            cudaMemcpy(g.data(), bv.debug + 16 * 65536, g.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+            double sc = 0, rf = 0, ck = 0, tot = 0, loop = 0;
+            for (int b = 0; b < batch; ++b) {
+                sc += (double)g[4 * (size_t)b]; rf += (double)g[4 * (size_t)b + 1]; ck += (double)g[4 * (size_t)b + 2];
+                tot += (double)dbg[(2 * (size_t)b) * 8 + 7];
+                for (int k = 0; k < 6; ++k) loop += (double)dbg[(2 * (size_t)b) * 8 + k];
+            }
+            fprintf(stderr, "[cycles per path] kernel=%.0f  iterations(a..c)=%.0f  scaling=%.0f  refactor(all)=%.0f  check blocks(all, incl. their refactors)=%.0f\n",
+                    tot / batch, loop / batch, sc / batch, rf / batch, ck / batch);
         }
     }
 #endif

@@ -607,21 +607,21 @@ int pqp_plan_batch(pqp_handle *h, int formulation, int bounds_mode, int output_m
     rc = launch_bounds_kernel(h, e, bounds_mode, batch, max_n, st);
     if (rc != PQP_OK) return rc;
     PQP_CUDA(cudaEventRecord(e->ev[2], st));
-    // (2) QP on the unblocked prefix.  keep_control_steps depends on the first <= 9 intervals of the
-    // (possibly trimmed) path: it can only grow when a path is cut short, so the hint range is
-    // [keep(full path), keep(first interval)].
-    int k_lo = 1 << 30, k_hi = 1;
-    for (int b = 0; b < batch; ++b) {
-        if (n_points[b] < 2) continue;
-        const pqp_state *r = ref + h->h_off[b];
-        k_lo = std::min(k_lo, pqp_keep_control_steps(PQP_FORM_KP, r, n_points[b]));
-        k_hi = std::max(k_hi, pqp_keep_control_steps(PQP_FORM_KP, r, 2));
+    // (2) QP on the unblocked prefix.  The prefix lengths come back to the host (one 4-byte-per-path copy and a
+    // stream synchronisation) so that every path runs on the kernel class of its own (length, keep_control_steps),
+    // exactly as pqp_solve_batch would choose it.
+    std::vector<int32_t> nv((size_t)batch);
+    PQP_CUDA(cudaMemcpyAsync(nv.data(), e->d_nvalid, B * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    PQP_CUDA(cudaStreamSynchronize(st));
+    int qp_launches = 0;
+    {
+        pqp::BatchView bv;
+        bv.batch = batch; bv.n_points = e->d_nvalid; bv.offsets = h->d_off; bv.ref = h->d_ref; bv.bounds = h->d_bounds;
+        bv.x0 = h->d_x0; bv.end_heading = h->d_end; bv.out_states = h->d_out; bv.out_frenet = nullptr;
+        bv.status = h->d_status; bv.iters = h->d_iters; bv.workspace = h->d_ws; bv.debug = nullptr;
+        rc = pqp_launch_kp_classes(h, bv, batch, nv.data(), h->h_off, ref, st, &qp_launches);
+        if (rc != PQP_OK) return rc;
     }
-    if (k_lo > k_hi) k_lo = k_hi;
-    rc = pqp_solve_batch_device(h, PQP_FORM_KP, batch, (int)total, std::max(max_n, 2), k_lo, std::min(k_hi, 10),
-                                e->d_nvalid, h->d_off, h->d_ref, h->d_bounds, h->d_x0, h->d_end, nullptr, nullptr,
-                                h->d_out, nullptr, h->d_status, h->d_iters, st, nullptr);
-    if (rc != PQP_OK) return rc;
     PQP_CUDA(cudaEventRecord(e->ev[3], st));
     // (3) tail
     if (output_mode == PQP_OUTPUT_RAW) {
@@ -670,7 +670,7 @@ int pqp_plan_batch(pqp_handle *h, int formulation, int bounds_mode, int output_m
         stats->kernel_ms = t_b + t_q + t_t;
         stats->h2d_bytes = h2d;
         stats->d2h_bytes = d2h;
-        stats->kernel_launches = 3;
+        stats->kernel_launches = 2 + qp_launches;
         for (size_t b = 0; b < B; ++b) {
             stats->total_iters += it_dst[b];
             stats->max_iters = std::max(stats->max_iters, it_dst[b]);

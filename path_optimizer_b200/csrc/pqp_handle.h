@@ -37,6 +37,12 @@ struct pqp_handle {
     void (*env_free)(void *) = nullptr;
 };
 
+// Internal (pqp_capi.cu): launch the KP solve kernels for paths whose station counts n[b] are known on the host,
+// each path on the kernel class picked for (n[b], its keep_control_steps), longest first inside a class.  The
+// device-side counts (BatchView::n_points) must equal n.  Used by pqp_plan_batch after the bounds stage.
+int pqp_launch_kp_classes(pqp_handle *h, const pqp::BatchView &bv, int batch, const int32_t *n, const int32_t *off,
+                          const pqp_state *ref, cudaStream_t st, int *launches);
+
 // thread-local error text returned by pqp_last_error()
 extern thread_local char pqp_g_err[512];
 inline void pqp_set_err(const char *fmt, const char *a = "", const char *b = "") {

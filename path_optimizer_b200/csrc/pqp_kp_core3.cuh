@@ -54,7 +54,11 @@ struct Kp3 {
     // Small interiors keep a DENSE inverse (row-major, [interior][row][kRow]) in place of the band
     // factor once a refactorisation is done: y = K_I^-1 r_I then is a mat-vec spread over every thread
     // of the CTA instead of M serial banded substitutions on warp 0 (the longest phase of an iteration).
-    static constexpr bool kDense = (IMAX <= 17) && (MMAX <= 17);
+    // Two-level separator system (every 34-separator class): the odd separators of the block-tridiagonal Schur system
+    // are eliminated in closed form (3x3 blocks), only the even ones keep a dense inverse (<= 51 x 51 instead of
+    // 102 x 102: N = 200 runs 13.2 ms per 1024 paths instead of 22.2 ms).
+    static constexpr bool kTwoLevel = (MMAX > 17);
+    static constexpr bool kDense = (IMAX <= 17) && (MMAX <= 17);   // (at 34 separators the dense interiors would leave no L1 for the spills)
     static constexpr int kSolveT = (MMAX + 31) / 32 * 32;   // threads that run the banded interior solves (non-dense form)
     static constexpr int kRow = IMAX + 1;                // row pitch of a dense inverse (even: 128-bit loads stay aligned, 4*lane word offsets)
     static constexpr int kFacSlots = kDense ? IMAX * kRow : IMAX * (BW + 1);
@@ -82,14 +86,19 @@ struct Kp3 {
         PQP_DEV double *gS() const { return ex(7); }                      // separator rhs      [nS <= kT]
         PQP_DEV double *fac() const { return ex(8); }                     // [IMAX*(BW+1)*M]; kDense: then K_I^-1 [M][IMAX][kRow]
         PQP_DEV double *T() const { return fac() + kFacSlots * M; }       // spikes T[c][pos], c < 6: [6*nv]
-        PQP_DEV double *Sinv() const { return T() + 6 * nv; }             // [nS*nS]
-        PQP_DEV double *red() const { return Sinv() + nS * nS; }          // [kRed2*M] + blocks [27*M]
+        PQP_DEV int nSd() const { return kTwoLevel ? 3 * ((M + 1) / 2) : nS; }   // order of the dense separator inverse
+        PQP_DEV double *Sinv() const { return T() + 6 * nv; }             // [nSd*nSd]
+        PQP_DEV double *red() const { return Sinv() + nSd() * nSd(); }    // [kRed2*M] + blocks [27*M]
         PQP_DEV double *blk() const { return red() + kRed2 * M; }         // A|C|Off per chunk [27*M]
         PQP_DEV double *cpl() const { return blk() + 27 * M; }            // coupling coefs [12*M]
+        // two-level form: per separator E = Dg^-1 (odd) | PL | PR (even) | Off copy [36*M]; reduced system [kRed2*ceil(M/2)]
+        PQP_DEV double *lv() const { return cpl() + 12 * M; }
+        PQP_DEV double *red2() const { return lv() + 36 * M; }
     };
     PQP_HD static size_t smem_doubles(const Kp3Dims &d) {
         return 2 * (size_t)d.nv + 8 * (size_t)kT + (size_t)kFacSlots * d.M + 6 * (size_t)d.nv +
-               (size_t)d.nS * d.nS + (size_t)(kRed2 + 27 + 12) * d.M;
+               (kTwoLevel ? (size_t)9 * ((d.M + 1) / 2) * ((d.M + 1) / 2) : (size_t)d.nS * d.nS) +
+               (size_t)(kRed2 + 27 + 12) * d.M + (kTwoLevel ? (size_t)36 * d.M + (size_t)kRed2 * ((d.M + 1) / 2) : 0);
     }
 
 #define PQP_F(k, dd) fcol[((k) * (BW + 1) + (dd)) * Mst]
@@ -118,6 +127,10 @@ struct Kp3 {
     PQP_DEV static void solve_path(const Cta &c, const DevParams &pm, const BatchView &bv, int prob, double *smem,
                                    size_t smem_cap) {
         const int lane = c.lane(), tid = c.tid(), wid = c.wid;
+#ifdef PQP_PHASE_TIMING
+        const long long ph_kernel_t0 = clock64();
+        long long ph_refactor = 0, ph_check = 0, ph_scale = 0;
+#endif
         const int N = bv.n_points[prob];
         const int off = bv.offsets[prob];
         const pqp_state *ref = bv.ref + off;
@@ -156,6 +169,7 @@ struct Kp3 {
         Smem s;
         s.base = smem; s.nv = d.nv; s.M = d.M; s.nS = d.nS; s.ch = d.ch;
         const int M = d.M, L = d.L, ch = d.ch, nS = d.nS, Mst = d.M;
+        const int Mr = kTwoLevel ? (M + 1) / 2 : M, nSr = 3 * Mr;   // order of the dense separator inverse (reduced system)
         double *ws = kp_ws_base(bv.workspace, off, prob);  // E[9] per station, [9N..] EUB, EEnd; then D
         double *wold = kp_ws_wold(ws, N);                  // w = v - clamp(v) of the previous iterate (infeasibility check)
         const KpDims ka = kp_dims(N, keep);
@@ -258,6 +272,9 @@ struct Kp3 {
         if (invalid) {
             status = PQP_INVALID_PROBLEM;
         } else {
+#ifdef PQP_PHASE_TIMING
+            const long long ph_scale_t0 = clock64();
+#endif
             // ================= Ruiz equilibration + cost scaling (OSQP scale_data) =================
             double Da = 1, Db = 1, Dc = 1, Dsv = 1, Du = 1, Dt = 1;
             double e0 = 1, e1 = 1, e2 = 1, eKB = 1, eSB = 1, eH1 = 1, eH3 = 1, eS4 = 1, eS2 = 1, eUB = 1, eEY = 1, eEH = 1;
@@ -553,18 +570,91 @@ struct Kp3 {
                     Dg[1] += kba; Dg[3] += kba; Dg[2] += kca; Dg[6] += kca; Dg[5] += kcb; Dg[7] += kcb;
 #pragma unroll
                     for (int k = 0; k < 9; ++k) { R[k] = Dg[k]; R[9 + k] = B[18 + k]; }
+                    if constexpr (kTwoLevel) {
+#pragma unroll
+                        for (int k = 0; k < 9; ++k) s.lv()[36 * p + 27 + k] = B[18 + k];   // Off_p = S[p, p+1]
+                    }
                 }
                 c.sync();
+                if constexpr (kTwoLevel) {
+                    // ---- level 1: odd separators are eliminated.  E_p = Dg_p^-1 (p odd); for even p
+                    //      PL_p = Off_{p-1}' E_{p-1},  PR_p = Off_p E_{p+1},
+                    //      Dg'_p = Dg_p - PL_p Off_{p-1} - PR_p Off_p',   Off'_p = -PR_p Off_{p+1}   (couples p and p+2)
+                    if (tid < M && (tid & 1)) {
+                        const double *R = s.red() + kRed2 * tid;
+                        double Dg[9], E[9];
+#pragma unroll
+                        for (int k = 0; k < 9; ++k) Dg[k] = R[k];
+                        if (!(Dg[0] > 0.0)) ok = 0;
+                        inv3_spd(Dg, E);
+#pragma unroll
+                        for (int k = 0; k < 9; ++k) s.lv()[36 * tid + k] = E[k];
+                    }
+                    c.sync();
+                    if (tid < M && !(tid & 1)) {
+                        const int pe = tid;
+                        const double *R = s.red() + kRed2 * pe;
+                        double *R2 = s.red2() + kRed2 * (pe >> 1);
+                        double *lvp = s.lv() + 36 * pe;
+                        double Dg[9], PL[9], PR[9], On[9];
+#pragma unroll
+                        for (int k = 0; k < 9; ++k) { Dg[k] = R[k]; PL[k] = 0.0; PR[k] = 0.0; On[k] = 0.0; }
+                        if (pe > 0) {
+                            const double *Om = s.lv() + 36 * (pe - 1) + 27, *Em = s.lv() + 36 * (pe - 1);
+                            for (int r = 0; r < 3; ++r)
+                                for (int cc = 0; cc < 3; ++cc) {
+                                    double a = 0.0;
+                                    for (int k = 0; k < 3; ++k) a += Om[k * 3 + r] * Em[k * 3 + cc];
+                                    PL[r * 3 + cc] = a;
+                                }
+                            for (int r = 0; r < 3; ++r)
+                                for (int cc = 0; cc < 3; ++cc) {
+                                    double a = 0.0;
+                                    for (int k = 0; k < 3; ++k) a += PL[r * 3 + k] * Om[k * 3 + cc];
+                                    Dg[r * 3 + cc] -= a;
+                                }
+                        }
+                        if (pe + 1 < M) {
+                            const double *Op = s.lv() + 36 * pe + 27, *Ep = s.lv() + 36 * (pe + 1);
+                            for (int r = 0; r < 3; ++r)
+                                for (int cc = 0; cc < 3; ++cc) {
+                                    double a = 0.0;
+                                    for (int k = 0; k < 3; ++k) a += Op[r * 3 + k] * Ep[k * 3 + cc];
+                                    PR[r * 3 + cc] = a;
+                                }
+                            for (int r = 0; r < 3; ++r)
+                                for (int cc = 0; cc < 3; ++cc) {
+                                    double a = 0.0;
+                                    for (int k = 0; k < 3; ++k) a += PR[r * 3 + k] * Op[cc * 3 + k];
+                                    Dg[r * 3 + cc] -= a;
+                                }
+                            if (pe + 2 < M) {
+                                const double *Oq = s.lv() + 36 * (pe + 1) + 27;
+                                for (int r = 0; r < 3; ++r)
+                                    for (int cc = 0; cc < 3; ++cc) {
+                                        double a = 0.0;
+                                        for (int k = 0; k < 3; ++k) a += PR[r * 3 + k] * Oq[k * 3 + cc];
+                                        On[r * 3 + cc] = -a;
+                                    }
+                            }
+                        }
+#pragma unroll
+                        for (int k = 0; k < 9; ++k) { R2[k] = Dg[k]; R2[9 + k] = On[k]; lvp[9 + k] = PL[k]; lvp[18 + k] = PR[k]; }
+                    }
+                    c.sync();
+                }
+                double *const redp = kTwoLevel ? s.red2() : s.red();
+                const int Mx = kTwoLevel ? (M + 1) / 2 : M, nSx = 3 * Mx;
                 // ---- block LDL' of the separator system (one thread), as in pqp_kp_core2.cuh:
                 //      red[p] = Sinv_p | H_p = Sinv_p Off_p | G_p = Off_{p-1}' Sinv_{p-1}
                 if (tid == 0) {
                     double Sch[9], Sinv[9];
-                    for (int k = 0; k < 9; ++k) Sch[k] = s.red()[k];
-                    for (int p = 0; p < M; ++p) {
-                        double *Rp = s.red() + kRed2 * p;
+                    for (int k = 0; k < 9; ++k) Sch[k] = redp[k];
+                    for (int p = 0; p < Mx; ++p) {
+                        double *Rp = redp + kRed2 * p;
                         if (!(Sch[0] > 0.0)) ok = 0;
                         inv3_spd(Sch, Sinv);
-                        if (p + 1 < M) {
+                        if (p + 1 < Mx) {
                             double *Rn = Rp + kRed2;
                             double Off[9];
                             for (int k = 0; k < 9; ++k) Off[k] = Rp[9 + k];
@@ -591,13 +681,13 @@ struct Kp3 {
                 c.sync();
                 // ---- dense inverse of the separator system: thread t solves for unit vector e_t and
                 //      stores column t (= row t, the matrix is symmetric) as Sinv[k*nS + t]
-                if (tid < nS) {
+                if (tid < nSx) {
                     const int pt = tid / 3, rt = tid % 3;
                     double *col = s.Sinv() + tid;
                     // forward: g'_p = g_p - G_p g'_{p-1}; g is e_t  -> zero before block pt
                     double g0 = 0, g1 = 0, g2 = 0;
-                    for (int p = 0; p < M; ++p) {
-                        const double *Rp = s.red() + kRed2 * p;
+                    for (int p = 0; p < Mx; ++p) {
+                        const double *Rp = redp + kRed2 * p;
                         double n0 = (p == pt && rt == 0) ? 1.0 : 0.0, n1 = (p == pt && rt == 1) ? 1.0 : 0.0,
                                n2 = (p == pt && rt == 2) ? 1.0 : 0.0;
                         if (p > pt) {
@@ -607,17 +697,17 @@ struct Kp3 {
                         }
                         g0 = n0; g1 = n1; g2 = n2;
                         // g^ = Sinv_p g' parked in the output column
-                        col[(3 * p) * nS] = Rp[0] * g0 + Rp[1] * g1 + Rp[2] * g2;
-                        col[(3 * p + 1) * nS] = Rp[3] * g0 + Rp[4] * g1 + Rp[5] * g2;
-                        col[(3 * p + 2) * nS] = Rp[6] * g0 + Rp[7] * g1 + Rp[8] * g2;
+                        col[(3 * p) * nSx] = Rp[0] * g0 + Rp[1] * g1 + Rp[2] * g2;
+                        col[(3 * p + 1) * nSx] = Rp[3] * g0 + Rp[4] * g1 + Rp[5] * g2;
+                        col[(3 * p + 2) * nSx] = Rp[6] * g0 + Rp[7] * g1 + Rp[8] * g2;
                     }
-                    double x0 = col[(3 * (M - 1)) * nS], x1 = col[(3 * (M - 1) + 1) * nS], x2 = col[(3 * (M - 1) + 2) * nS];
-                    for (int p = M - 2; p >= 0; --p) {
-                        const double *Rp = s.red() + kRed2 * p;
-                        const double y0 = col[(3 * p) * nS] - (Rp[9] * x0 + Rp[10] * x1 + Rp[11] * x2);
-                        const double y1 = col[(3 * p + 1) * nS] - (Rp[12] * x0 + Rp[13] * x1 + Rp[14] * x2);
-                        const double y2 = col[(3 * p + 2) * nS] - (Rp[15] * x0 + Rp[16] * x1 + Rp[17] * x2);
-                        col[(3 * p) * nS] = y0; col[(3 * p + 1) * nS] = y1; col[(3 * p + 2) * nS] = y2;
+                    double x0 = col[(3 * (Mx - 1)) * nSx], x1 = col[(3 * (Mx - 1) + 1) * nSx], x2 = col[(3 * (Mx - 1) + 2) * nSx];
+                    for (int p = Mx - 2; p >= 0; --p) {
+                        const double *Rp = redp + kRed2 * p;
+                        const double y0 = col[(3 * p) * nSx] - (Rp[9] * x0 + Rp[10] * x1 + Rp[11] * x2);
+                        const double y1 = col[(3 * p + 1) * nSx] - (Rp[12] * x0 + Rp[13] * x1 + Rp[14] * x2);
+                        const double y2 = col[(3 * p + 2) * nSx] - (Rp[15] * x0 + Rp[16] * x1 + Rp[17] * x2);
+                        col[(3 * p) * nSx] = y0; col[(3 * p + 1) * nSx] = y1; col[(3 * p + 2) * nSx] = y2;
                         x0 = y0; x1 = y1; x2 = y2;
                     }
                 }
@@ -648,7 +738,12 @@ struct Kp3 {
                 return !c.any(!ok);   // (contains CTA barriers)
             };
 
+#ifdef PQP_PHASE_TIMING
+            ph_scale = clock64() - ph_scale_t0;
+            { const long long t0_ = clock64(); if (!refactor()) status = PQP_NON_CVX; ph_refactor += clock64() - t0_; }
+#else
             if (!refactor()) status = PQP_NON_CVX;
+#endif
             const double alpha = pm.alpha;
             const double d1 = pm.d1, d2 = pm.d2, d3 = pm.d3, d4 = pm.d4;
             // An iteration that ends in a termination check needs delta_y = W (w_new - w_old) (OSQP
@@ -683,8 +778,8 @@ struct Kp3 {
             // slots of the other, so what counts is the instruction total, not the balance inside one CTA.)
             auto dense_rows = [&](int q0, int q1) {
                 if constexpr (kDense) {
-                    const int nw_ = kT - nS;
-                    for (int q = q0 + (tid - nS); q < q1; q += nw_) {
+                    const int nw_ = kT - nSr;
+                    for (int q = q0 + (tid - nSr); q < q1; q += nw_) {
                         const int p = q / IMAX, k = q - p * IMAX;
                         const double *kv = s.fac() + (size_t)q * kRow;
                         const double *rI = s.tr() + p * d.CS + 3;
@@ -702,7 +797,7 @@ struct Kp3 {
 #ifdef PQP_PHASE_TIMING
             // clock64() at the phase boundaries, accumulated per warp-0 / warp-1 lead thread in shared scratch
             // (diagnostic builds only): slots 0..5 = a1, a2, b1, b2, b3, c ; 6 = iterations
-            double *ph_acc = c.scratch + 100 + 8 * (wid & 1);
+            double *ph_acc = s.ex(5) + 8 * (wid & 1);   // (row 5 is free once the scaling is done)
             if ((tid & 31) == 0 && wid < 2) for (int k = 0; k < 8; ++k) ph_acc[k] = 0.0;
             long long ph_t = 0;
 #define PQP_PH(k) if ((tid & 31) == 0 && wid < 2) { const long long now_ = clock64(); ph_acc[k] += (double)(now_ - ph_t); ph_t = now_; }
@@ -791,21 +886,35 @@ struct Kp3 {
                 }
                 c.sync();
                 PQP_PH(2)
-                // ---- (b2) x_S = Sinv g on the first 3M threads  ||  y = K_I^-1 r_I:
-                //      dense interiors: row tasks (p, k) spread over all the OTHER threads of the CTA;
-                //      otherwise M banded substitutions on the lanes of warp 0 (and Sinv g on warps 1..).
-                if constexpr (kDense) {
-                    if (tid < nS) {
-                        const double *row = s.Sinv() + tid;
+                if constexpr (kTwoLevel) {
+                    // ---- (b1') reduced right-hand side of the even separators: g'_p = g_p - PL_p g_{p-1} - PR_p g_{p+1}
+                    if (tid < nSr) {
+                        const int pr = tid / 3, r = tid - 3 * pr, pe = 2 * pr;
                         const double *gS = s.gS();
+                        const double *lvp = s.lv() + 36 * pe;
+                        double a = gS[3 * pe + r];
+                        if (pe > 0) a -= lvp[9 + 3 * r] * gS[3 * pe - 3] + lvp[10 + 3 * r] * gS[3 * pe - 2] + lvp[11 + 3 * r] * gS[3 * pe - 1];
+                        if (pe + 1 < M) a -= lvp[18 + 3 * r] * gS[3 * pe + 3] + lvp[19 + 3 * r] * gS[3 * pe + 4] + lvp[20 + 3 * r] * gS[3 * pe + 5];
+                        s.ex(4)[tid] = a;
+                    }
+                    c.sync();
+                }
+                // ---- (b2) x_S = Sinv g on the first threads  ||  y = K_I^-1 r_I:
+                //      dense interiors: row tasks (p, k) spread over all the OTHER threads of the CTA;
+                //      otherwise M banded substitutions on the first M threads (and Sinv g on the warps after them).
+                if constexpr (kDense) {
+                    if (tid < nSr) {
+                        const double *row = s.Sinv() + tid;
+                        const double *gS = kTwoLevel ? s.ex(4) : s.gS();
                         double a0 = 0, a1 = 0, a2 = 0;
 #pragma unroll 4
-                        for (int k = 0; k < nS; k += 3) {     // nS = 3M
-                            a0 += row[k * nS] * gS[k];
-                            a1 += row[(k + 1) * nS] * gS[k + 1];
-                            a2 += row[(k + 2) * nS] * gS[k + 2];
+                        for (int k = 0; k < nSr; k += 3) {
+                            a0 += row[k * nSr] * gS[k];
+                            a1 += row[(k + 1) * nSr] * gS[k + 1];
+                            a2 += row[(k + 2) * nSr] * gS[k + 2];
                         }
-                        s.ex(3)[tid] = (a0 + a1) + a2;
+                        const int xo = kTwoLevel ? 6 * (tid / 3) + (tid % 3) : tid;   // even separator 2*(t/3) in full numbering
+                        s.ex(3)[xo] = (a0 + a1) + a2;
                     } else {
                         dense_rows(0, yQ);
                     }
@@ -813,21 +922,47 @@ struct Kp3 {
                     if (solver) K2::local_solve2(s.tr() + lo, s.yv() + lo, s.fac() + sid, Mst);
                 } else {
                     const int t = tid - kSolveT;
-                    if (t < nS) {
+                    if (t < nSr) {
                         const double *row = s.Sinv() + t;
-                        const double *gS = s.gS();
+                        const double *gS = kTwoLevel ? s.ex(4) : s.gS();
                         double a0 = 0, a1 = 0, a2 = 0;
 #pragma unroll 4
-                        for (int k = 0; k < nS; k += 3) {     // nS = 3M
-                            a0 += row[k * nS] * gS[k];
-                            a1 += row[(k + 1) * nS] * gS[k + 1];
-                            a2 += row[(k + 2) * nS] * gS[k + 2];
+                        for (int k = 0; k < nSr; k += 3) {
+                            a0 += row[k * nSr] * gS[k];
+                            a1 += row[(k + 1) * nSr] * gS[k + 1];
+                            a2 += row[(k + 2) * nSr] * gS[k + 2];
                         }
-                        s.ex(3)[t] = (a0 + a1) + a2;
+                        const int xo = kTwoLevel ? 6 * (t / 3) + (t % 3) : t;
+                        s.ex(3)[xo] = (a0 + a1) + a2;
                     }
                 }
                 c.sync();
                 PQP_PH(3)
+                if constexpr (kTwoLevel) {
+                    // ---- (b2') odd separators: x_p = E_p (g_p - Off_{p-1}' x_{p-1} - Off_p x_{p+1})  (even entries are read,
+                    //      odd ones written: no hazard inside the phase)
+                    if (tid < 3 * (M / 2)) {
+                        const int po = 2 * (tid / 3) + 1, r = tid % 3;
+                        const double *gS = s.gS(), *xS = s.ex(3);
+                        const double *Om = s.lv() + 36 * (po - 1) + 27, *E = s.lv() + 36 * po;
+                        double t0 = gS[3 * po], t1 = gS[3 * po + 1], t2 = gS[3 * po + 2];
+                        {
+                            const double x0 = xS[3 * po - 3], x1 = xS[3 * po - 2], x2 = xS[3 * po - 1];
+                            t0 -= Om[0] * x0 + Om[3] * x1 + Om[6] * x2;
+                            t1 -= Om[1] * x0 + Om[4] * x1 + Om[7] * x2;
+                            t2 -= Om[2] * x0 + Om[5] * x1 + Om[8] * x2;
+                        }
+                        if (po + 1 < M) {
+                            const double *Op = s.lv() + 36 * po + 27;
+                            const double x0 = xS[3 * po + 3], x1 = xS[3 * po + 4], x2 = xS[3 * po + 5];
+                            t0 -= Op[0] * x0 + Op[1] * x1 + Op[2] * x2;
+                            t1 -= Op[3] * x0 + Op[4] * x1 + Op[5] * x2;
+                            t2 -= Op[6] * x0 + Op[7] * x1 + Op[8] * x2;
+                        }
+                        s.ex(3)[3 * po + r] = E[3 * r] * t0 + E[3 * r + 1] * t1 + E[3 * r + 2] * t2;
+                    }
+                    c.sync();
+                }
                 // ---- (b3) x-tilde: separators take x_S, interiors y - T [x_Sp ; x_Sq]
                 double ta = 0, tb = 0, tc = 0, tu = 0;
 #define PQP_TX(q) ((s.yv()[q] - (Tq[q] * xl0 + Tq[nvs + (q)] * xl1 + Tq[2 * nvs + (q)] * xl2)) \
@@ -1111,9 +1246,16 @@ struct Kp3 {
 #undef PQP_RESC
                             rho = rho_new;
                             c.sync();
+#ifdef PQP_PHASE_TIMING
+                            { const long long t0_ = clock64(); if (!refactor()) status = PQP_NON_CVX; ph_refactor += clock64() - t0_; }
+#else
                             if (!refactor()) status = PQP_NON_CVX;
+#endif
                         }
                     }
+#ifdef PQP_PHASE_TIMING
+                    ph_check += clock64() - ph_t;   // (includes a refactorisation when one happened)
+#endif
                 }
             };
             // first iteration after `it` that needs the checked form
@@ -1142,8 +1284,13 @@ struct Kp3 {
         }
 #ifdef PQP_PHASE_TIMING
         if (bv.debug && (tid & 31) == 0 && wid < 2 && status != PQP_INVALID_PROBLEM) {
-            const double *acc = c.scratch + 100 + 8 * (wid & 1);
-            for (int k = 0; k < 8; ++k) bv.debug[(2 * (size_t)prob + wid) * 8 + k] = (long long)acc[k];
+            const double *acc = s.ex(5) + 8 * (wid & 1);
+            for (int k = 0; k < 7; ++k) bv.debug[(2 * (size_t)prob + wid) * 8 + k] = (long long)acc[k];
+            bv.debug[(2 * (size_t)prob + wid) * 8 + 7] = clock64() - ph_kernel_t0;
+            if (wid == 0) {
+                long long *g = bv.debug + 16 * 65536 + 4 * (size_t)prob;
+                g[0] = ph_scale; g[1] = ph_refactor; g[2] = ph_check;
+            }
         }
 #endif
         // ---- epilogue: getOptimizedPath, solver_kp_as_input.cpp:26-43
