@@ -110,7 +110,7 @@ extern "C" {
 
 const char *pqp_last_error(void) { return g_err; }
 
-const char *pqp_version(void) { return "pqp abi 1 / sm_100a / fp64 warp-per-path ADMM"; }
+const char *pqp_version(void) { return "pqp abi 1 / sm_100a / fp64 ADMM, one CTA per path (thread per station)"; }
 
 int pqp_params_update_config(pqp_params *p) {
     if (!p) return PQP_ERR_ARG;

@@ -48,7 +48,7 @@ struct BatchView {
     double *out_frenet;                // [sum N][3] or nullptr
     int32_t *status;                   // [B]
     int32_t *iters;                    // [B] or nullptr
-    double *workspace;                 // global scratch: 16*sum(N) + 2048*B doubles
+    double *workspace;                 // global scratch: 32*sum(N) + 2048*B doubles (kp2_ws_doubles)
     long long *debug;                  // phase-timing dump (PQP_PHASE_TIMING builds only), else nullptr
 };
 
