@@ -655,6 +655,12 @@ int pqp_solve_batch(pqp_handle *h, int formulation, int batch, const int32_t *n_
                 tot += (double)dbg[(2 * (size_t)b) * 8 + 7];
                 for (int k = 0; k < 6; ++k) loop += (double)dbg[(2 * (size_t)b) * 8 + k];
             }
+            std::vector<long long> g2(8 * (size_t)batch);
+            cudaMemcpy(g2.data(), bv.debug + 20 * 65536, g2.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+            double rt[8] = {0};
+            for (int b = 0; b < batch; ++b) for (int k = 0; k < 8; ++k) rt[k] += (double)g2[8 * (size_t)b + k] / batch;
+            fprintf(stderr, "[refactor cycles per path, all refactorisations] weights=%.0f assembly=%.0f interior LDL=%.0f spikes=%.0f schur=%.0f block LDL=%.0f dense Sinv=%.0f dense interiors=%.0f\n",
+                    rt[0], rt[1], rt[2], rt[3], rt[4], rt[5], rt[6], rt[7]);
             fprintf(stderr, "[cycles per path] kernel=%.0f  iterations(a..c)=%.0f  scaling=%.0f  refactor(all)=%.0f  check blocks(all, incl. their refactors)=%.0f\n",
                     tot / batch, loop / batch, sc / batch, rf / batch, ck / batch);
         }

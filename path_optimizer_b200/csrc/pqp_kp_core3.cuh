@@ -130,6 +130,7 @@ struct Kp3 {
 #ifdef PQP_PHASE_TIMING
         const long long ph_kernel_t0 = clock64();
         long long ph_refactor = 0, ph_check = 0, ph_scale = 0;
+        long long rt_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, rt_t = 0;
 #endif
         const int N = bv.n_points[prob];
         const int off = bv.offsets[prob];
@@ -376,7 +377,15 @@ struct Kp3 {
             c.sync();
 
             // ================= (re)factorisation =====================================================
+#ifdef PQP_PHASE_TIMING
+#define PQP_RT(k) if (tid == 0) { const long long now_ = clock64(); rt_acc[k] += now_ - rt_t; rt_t = now_; }
+#else
+#define PQP_RT(k)
+#endif
             auto refactor = [&]() -> int {
+#ifdef PQP_PHASE_TIMING
+                if (tid == 0) rt_t = clock64();
+#endif
                 // ---- row weights W = rho_row E^2 from the workspace E
                 if (st.live) {
                     const double *w9 = ws + 9 * (size_t)i;
@@ -407,6 +416,7 @@ struct Kp3 {
                     s.fac()[k] = (dd == 0 && kk >= cp) ? 1.0 : 0.0;
                 }
                 c.sync();
+                PQP_RT(0)
                 // ---- assembly: every station / control thread writes its own band rows
                 double N0 = 0, N1 = 0, N2 = 0;
                 if (st.live && !st.last) { N0 = s.ex(0)[i + 1]; N1 = s.ex(1)[i + 1]; N2 = s.ex(2)[i + 1]; }
@@ -462,6 +472,7 @@ struct Kp3 {
                     PQP_F(ku, 0) = du;
                 }
                 c.sync();
+                PQP_RT(1)
                 // ---- interior LDL' (warp 0, lane p) and coupling coefficients per chunk:
                 //      cpl[p] = left  (transition e -> e+1):  N0 N1 N2 ds q
                 //               right (transition e2-1 -> e2): W0 W1 W2 ds q ; + flags
@@ -478,6 +489,7 @@ struct Kp3 {
                     }
                 }
                 c.sync();
+                PQP_RT(2)
                 // ---- spikes: thread (p, col) solves K_I t = K[I, s_col]  (col 0..2 left, 3..5 right separator)
                 const int sp_p = tid / 6, sp_c = tid % 6;
                 bool sp_act = tid < 6 * M;
@@ -525,6 +537,7 @@ struct Kp3 {
                     }
                 }
                 c.sync();
+                PQP_RT(3)
                 // ---- Schur blocks: A_p = K[S_p,I] T_left, Off_p = -(K[S_q,I] T_left)', C_p = K[S_q,I] T_right
                 if (sp_act) {
                     double tl0 = 0, tl1 = 0, tl2 = 0, tr0 = 0, tr1 = 0, tr2 = 0;
@@ -645,6 +658,7 @@ struct Kp3 {
                 }
                 double *const redp = kTwoLevel ? s.red2() : s.red();
                 const int Mx = kTwoLevel ? (M + 1) / 2 : M, nSx = 3 * Mx;
+                PQP_RT(4)
                 // ---- block LDL' of the separator system (one thread), as in pqp_kp_core2.cuh:
                 //      red[p] = Sinv_p | H_p = Sinv_p Off_p | G_p = Off_{p-1}' Sinv_{p-1}
                 if (tid == 0) {
@@ -679,6 +693,7 @@ struct Kp3 {
                     }
                 }
                 c.sync();
+                PQP_RT(5)
                 // ---- dense inverse of the separator system: thread t solves for unit vector e_t and
                 //      stores column t (= row t, the matrix is symmetric) as Sinv[k*nS + t]
                 if (tid < nSx) {
@@ -711,6 +726,7 @@ struct Kp3 {
                         x0 = y0; x1 = y1; x2 = y2;
                     }
                 }
+                PQP_RT(6)
                 if constexpr (kDense) {
                     // ---- dense interior inverses: task (p, j) = column j of K_p^-1 from the band factor,
                     //      kept in registers until every thread is done with the factor, then written
@@ -735,6 +751,7 @@ struct Kp3 {
                         }
                     }
                 }
+                PQP_RT(7)
                 return !c.any(!ok);   // (contains CTA barriers)
             };
 
@@ -1290,6 +1307,8 @@ struct Kp3 {
             if (wid == 0) {
                 long long *g = bv.debug + 16 * 65536 + 4 * (size_t)prob;
                 g[0] = ph_scale; g[1] = ph_refactor; g[2] = ph_check;
+                long long *g2 = bv.debug + 20 * 65536 + 8 * (size_t)prob;
+                for (int k = 0; k < 8; ++k) g2[k] = rt_acc[k];
             }
         }
 #endif
