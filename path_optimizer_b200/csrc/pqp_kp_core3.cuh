@@ -1054,6 +1054,20 @@ struct Kp3 {
                     const bool can_adapt = pm.adaptive_rho && pm.adaptive_rho_interval &&
                                            (iter % pm.adaptive_rho_interval == 0);
                     const bool chk = can_check || iter == pm.max_iter;
+                    // the row / column scalings (and the parked dual direction) live in the global workspace: fetch them
+                    // first, as independent loads, so that their L2 latency overlaps the barriers and the stencils below
+                    const int iw = st.live ? i : 0;
+                    double eW[9], dW[4], wo[11];
+                    {
+                        const double *w9g = ws + 9 * (size_t)iw;
+                        const double *wDg = ws + 9 * (size_t)N + ch + 2 + 4 * (size_t)iw;
+#pragma unroll
+                        for (int k = 0; k < 9; ++k) eW[k] = w9g[k];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) dW[k] = wDg[k];
+#pragma unroll
+                        for (int k = 0; k < 11; ++k) wo[k] = chk ? wold[(size_t)k * N + iw] : 0.0;
+                    }
                     // publish x (neighbours need station i-1 and the control) and read the scalings
                     c.sync();
                     if (st.live) { s.tr()[st.pos] = st.xa; s.tr()[st.pos + 1] = st.xb; s.tr()[st.pos + 2] = st.xc; }
@@ -1079,7 +1093,6 @@ struct Kp3 {
         natys = fmax(natys, cd_ * fabs(aty_));                                        \
     }
                     double yD0 = 0, yD1 = 0, yD2 = 0;
-                    const double *w9 = ws + 9 * (size_t)(st.live ? i : 0);
                     if (st.live) {
                         double aD0 = -st.xa, aD1 = -st.xb, aD2 = -st.xc;
                         if (!st.first) {
@@ -1090,17 +1103,17 @@ struct Kp3 {
                             aD2 += ct + st.dst * ut;
                         }
                         const double e4 = st.xa + d4 * st.xb, e2 = st.xa + d2 * st.xb;
-                        PQP_ROW(aD0, st.vD0, st.b0, st.b0, w9[0])
-                        PQP_ROW(aD1, st.vD1, st.b1, st.b1, w9[1])
-                        PQP_ROW(aD2, st.vD2, st.b2, st.b2, w9[2])
-                        PQP_ROW(st.xc, st.vKB, -pm.kmax, pm.kmax, w9[3])
-                        PQP_ROW(st.xs, st.vSB, 0.0, pm.margin, w9[4])
-                        PQP_ROW(st.xa + d1 * st.xb, st.vH1, st.lH1, st.uH1, w9[5])
-                        PQP_ROW(st.xa + d3 * st.xb, st.vH3, st.lH3, st.uH3, w9[6])
-                        PQP_ROW(e4 - st.xs, st.vS4m, -kOsqpInfty, st.uS4m, w9[7])
-                        PQP_ROW(e4 + st.xs, st.vS4p, st.lS4p, kOsqpInfty, w9[7])
-                        PQP_ROW(e2 - st.xs, st.vS2m, -kOsqpInfty, st.uS2m, w9[8])
-                        PQP_ROW(e2 + st.xs, st.vS2p, st.lS2p, kOsqpInfty, w9[8])
+                        PQP_ROW(aD0, st.vD0, st.b0, st.b0, eW[0])
+                        PQP_ROW(aD1, st.vD1, st.b1, st.b1, eW[1])
+                        PQP_ROW(aD2, st.vD2, st.b2, st.b2, eW[2])
+                        PQP_ROW(st.xc, st.vKB, -pm.kmax, pm.kmax, eW[3])
+                        PQP_ROW(st.xs, st.vSB, 0.0, pm.margin, eW[4])
+                        PQP_ROW(st.xa + d1 * st.xb, st.vH1, st.lH1, st.uH1, eW[5])
+                        PQP_ROW(st.xa + d3 * st.xb, st.vH3, st.lH3, st.uH3, eW[6])
+                        PQP_ROW(e4 - st.xs, st.vS4m, -kOsqpInfty, st.uS4m, eW[7])
+                        PQP_ROW(e4 + st.xs, st.vS4p, st.lS4p, kOsqpInfty, eW[7])
+                        PQP_ROW(e2 - st.xs, st.vS2m, -kOsqpInfty, st.uS2m, eW[8])
+                        PQP_ROW(e2 + st.xs, st.vS2p, st.lS2p, kOsqpInfty, eW[8])
                         if (st.last) {
                             PQP_ROW(st.xa, vEY, -1.0, 1.0, ws[9 * (size_t)N + ch])
                             PQP_ROW(st.xb, vEH, lEH, uEH, ws[9 * (size_t)N + ch + 1])
@@ -1135,11 +1148,10 @@ struct Kp3 {
                             ra += PQP_DUAL(vEY, -1.0, 1.0, WEY);
                             rb += PQP_DUAL(vEH, lEH, uEH, WEH);
                         }
-                        const double *wD = ws + 9 * (size_t)N + ch + 2 + 4 * (size_t)i;
-                        PQP_VAR(pm.w_pq * st.xa, ra, wD[0])
-                        PQP_VAR(0.0, rb, wD[1])
-                        PQP_VAR(pm.w_c * st.xc, rc, wD[2])
-                        PQP_VAR(pm.w_s * st.xs, rs, wD[3])
+                        PQP_VAR(pm.w_pq * st.xa, ra, dW[0])
+                        PQP_VAR(0.0, rb, dW[1])
+                        PQP_VAR(pm.w_c * st.xc, rc, dW[2])
+                        PQP_VAR(pm.w_s * st.xs, rs, dW[3])
                     }
                     if (ub.live) {
                         double aty = PQP_DUAL(ub.v, -kOsqpInfty, kOsqpInfty, ub.W);
@@ -1157,25 +1169,24 @@ struct Kp3 {
 #define PQP_G(V, LO, HI, WW, WO) ((WW) * (((V) - clamp2((V), (LO), (HI))) - (WO)))
 #define PQP_ACC(G, LO, HI) { const double g_ = (G); c_nrm = fmax(c_nrm, fabs(g_)); c_lhs += (HI) * fmax(g_, 0.0) + (LO) * fmin(g_, 0.0); }
                         double gD0 = 0, gD1 = 0, gD2 = 0;
-                        const double *wo = wold + (st.live ? i : 0);
                         if (st.live) {
                             gD0 = st.WD0 * ((st.vD0 - st.b0) - wo[0]);
-                            gD1 = st.WD1 * ((st.vD1 - st.b1) - wo[N]);
-                            gD2 = st.WD2 * ((st.vD2 - st.b2) - wo[2 * N]);
+                            gD1 = st.WD1 * ((st.vD1 - st.b1) - wo[1]);
+                            gD2 = st.WD2 * ((st.vD2 - st.b2) - wo[2]);
                         }
                         c.sync();   // the dual-residual pass has consumed ex(0..2)
                         if (st.live) { s.ex(0)[i] = gD0; s.ex(1)[i] = gD1; s.ex(2)[i] = gD2; }
                         c.sync();
                         if (st.live) {
-                            const double gKB = PQP_G(st.vKB, -pm.kmax, pm.kmax, st.WKB, wo[3 * N]);
-                            const double gSB = PQP_G(st.vSB, 0.0, pm.margin, st.WSB, wo[4 * N]);
-                            const double gH1 = PQP_G(st.vH1, st.lH1, st.uH1, st.WH1, wo[5 * N]);
-                            const double gH3 = PQP_G(st.vH3, st.lH3, st.uH3, st.WH3, wo[6 * N]);
+                            const double gKB = PQP_G(st.vKB, -pm.kmax, pm.kmax, st.WKB, wo[3]);
+                            const double gSB = PQP_G(st.vSB, 0.0, pm.margin, st.WSB, wo[4]);
+                            const double gH1 = PQP_G(st.vH1, st.lH1, st.uH1, st.WH1, wo[5]);
+                            const double gH3 = PQP_G(st.vH3, st.lH3, st.uH3, st.WH3, wo[6]);
                             // one-sided rows: l = -inf keeps the positive part, u = +inf the negative part
-                            const double g4m = fmax(PQP_G(st.vS4m, -kOsqpInfty, st.uS4m, st.WS4, wo[7 * N]), 0.0);
-                            const double g4p = fmin(PQP_G(st.vS4p, st.lS4p, kOsqpInfty, st.WS4, wo[8 * N]), 0.0);
-                            const double g2m = fmax(PQP_G(st.vS2m, -kOsqpInfty, st.uS2m, st.WS2, wo[9 * N]), 0.0);
-                            const double g2p = fmin(PQP_G(st.vS2p, st.lS2p, kOsqpInfty, st.WS2, wo[10 * N]), 0.0);
+                            const double g4m = fmax(PQP_G(st.vS4m, -kOsqpInfty, st.uS4m, st.WS4, wo[7]), 0.0);
+                            const double g4p = fmin(PQP_G(st.vS4p, st.lS4p, kOsqpInfty, st.WS4, wo[8]), 0.0);
+                            const double g2m = fmax(PQP_G(st.vS2m, -kOsqpInfty, st.uS2m, st.WS2, wo[9]), 0.0);
+                            const double g2p = fmin(PQP_G(st.vS2p, st.lS2p, kOsqpInfty, st.WS2, wo[10]), 0.0);
                             PQP_ACC(gD0, st.b0, st.b0) PQP_ACC(gD1, st.b1, st.b1) PQP_ACC(gD2, st.b2, st.b2)
                             PQP_ACC(gKB, -pm.kmax, pm.kmax) PQP_ACC(gSB, 0.0, pm.margin)
                             PQP_ACC(gH1, st.lH1, st.uH1) PQP_ACC(gH3, st.lH3, st.uH3)
