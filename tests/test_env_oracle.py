@@ -249,3 +249,35 @@ def test_plan_chain_oracle(field):
     lo = b["offsets"][i]
     k = r["n_out"][i]
     assert np.abs(q["states"]["x"][:k] - r["states"]["x"][lo:lo + k]).max() == 0.0
+
+
+def _golden_env():
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "env_small.npz"))
+    field = dict(distance=g["map_distance"], rows=g["map_distance"].shape[0], cols=g["map_distance"].shape[1],
+                 resolution=float(g["map_geo"][0]), center_x=float(g["map_geo"][1]), center_y=float(g["map_geo"][2]))
+    b = dict(n_points=g["n_points"], ref=g["ref"], x0=g["x0"], end_heading=g["end_heading"])
+    b["offsets"] = np.concatenate([[0], np.cumsum(b["n_points"])]).astype(np.int32)
+    spl = dict(n_knots=g["n_points"], knots=g["knots"], x_coef=g["x_coef"], y_coef=g["y_coef"])
+    return g, field, b, spl
+
+
+def test_golden_env_fixture_is_reproduced():
+    """The committed fixture (tests/golden/make_golden_env.py) is what the oracle computes today, and the product's
+    per-thread device source (host build) reproduces its map lookups, bounds and collision flags."""
+    g, field, b, spl = _golden_env()
+    p = oracle.default_params()
+    assert (oracle.map_distance(field, g["xy"]) == g["xy_distance"]).all()
+    assert (emu.map_distance(field, g["xy"]) == g["xy_distance"]).all()
+    for mode, tag in ((planner.BOUNDS_SIMPLE, "simple"), (planner.BOUNDS_IMPROVED, "improved")):
+        sp = spl if mode == planner.BOUNDS_IMPROVED else None
+        r = oracle.update_bounds(p, field, b, mode=mode, splines=sp)
+        e = emu.update_bounds(p, field, b, mode=mode, splines=sp)
+        assert (r["n_valid"] == g[f"n_valid_{tag}"]).all() and (e["n_valid"] == g[f"n_valid_{tag}"]).all()
+        assert r["bounds"].tobytes() == g[f"bounds_{tag}"].tobytes()
+        assert e["bounds"].tobytes() == g[f"bounds_{tag}"].tobytes()
+    assert (oracle.check_states(p, field, b["ref"]) == g["collision_free"]).all()
+    assert (emu.check_states(p, field, b["ref"]) == g["collision_free"]).all()
+    pl = oracle.plan(p, field, b, bounds_mode=planner.BOUNDS_SIMPLE)
+    assert (pl["status"] == g["plan_simple_raw_status"]).all() and (pl["iters"] == g["plan_simple_raw_iters"]).all()
+    assert set(g["plan_simple_raw_status"].tolist()) >= {1, -3}

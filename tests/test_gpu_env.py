@@ -246,3 +246,40 @@ def test_cpp_planner_mirror(field, tmp_path):
     assert ok0 == one["ok"][0] and n0 == one["n_out"][0]
     p0 = np.frombuffer(raw, dtype=STATE_DTYPE, count=n0, offset=o + 8)
     assert np.abs(p0["x"] - one["states"]["x"][:n0]).max(initial=0.0) <= FRENET_TOL
+
+
+def test_golden_env_fixture(tmp_path):
+    """The committed fixture tests/golden/env_small.npz (oracle outputs, generator committed) without the oracle in
+    the loop: lookups, both bounds variants, collision flags and all four chain variants."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "env_small.npz"))
+    field = dict(distance=g["map_distance"], rows=g["map_distance"].shape[0], cols=g["map_distance"].shape[1],
+                 resolution=float(g["map_geo"][0]), center_x=float(g["map_geo"][1]), center_y=float(g["map_geo"][2]))
+    b = dict(n_points=g["n_points"], ref=g["ref"], x0=g["x0"], end_heading=g["end_heading"])
+    b["offsets"] = np.concatenate([[0], np.cumsum(b["n_points"])]).astype(np.int32)
+    spl = dict(n_knots=g["n_points"], knots=g["knots"], x_coef=g["x_coef"], y_coef=g["y_coef"])
+    p = planner.PathPlanner(max_batch=16, max_total_points=16 * 128)
+    p.set_map(field)
+    assert (p.map_distance(g["xy"]) == g["xy_distance"]).all()
+    assert (p.check_states(b["ref"]) == g["collision_free"]).all()
+    for mode, tag in ((planner.BOUNDS_SIMPLE, "simple"), (planner.BOUNDS_IMPROVED, "improved")):
+        sp = spl if mode == planner.BOUNDS_IMPROVED else None
+        r = p.update_bounds(b, mode=mode, splines=sp)
+        assert (r["n_valid"] == g[f"n_valid_{tag}"]).all()
+        G, W = r["bounds"].view(np.float64).reshape(-1, 8), g[f"bounds_{tag}"].view(np.float64).reshape(-1, 8)
+        assert np.abs(G - W).max() <= FP_TOL
+        for om, otag in ((planner.OUTPUT_RAW, "raw"), (planner.OUTPUT_DENSIFY, "dense")):
+            r = p.plan(b, bounds_mode=mode, splines=sp, output_mode=om, max_out=128)
+            k = f"plan_{tag}_{otag}_"
+            assert (r["status"] == g[k + "status"]).all() and (r["iters"] == g[k + "iters"]).all()
+            assert (r["n_out"] == g[k + "n_out"]).all() and (r["ok"] == g[k + "ok"]).all()
+            for i in range(len(b["n_points"])):
+                n = r["n_out"][i]
+                if om == planner.OUTPUT_RAW:
+                    lo = b["offsets"][i]
+                    a, w = r["states"][lo:lo + n], g[k + "states"][lo:lo + n]
+                else:
+                    a, w = r["states"][i, :n], g[k + "states"][i, :n]
+                for f in ("x", "y", "z", "k", "s"):
+                    assert np.abs(a[f] - w[f]).max(initial=0.0) <= FRENET_TOL
+    p.close()
