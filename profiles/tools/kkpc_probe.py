@@ -1,7 +1,7 @@
 """Diagnostic: K / KPC throughput on the generic kernel (1024 x 100)."""
 import os
 import sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 from path_optimizer_b200 import synth
 from path_optimizer_b200.solver import BatchPathSolver

@@ -2,7 +2,7 @@
 libpqp.so selected with PQP_LIB=...; prints to stderr from inside pqp_solve_batch)."""
 import os
 import sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from path_optimizer_b200 import synth
 from path_optimizer_b200.solver import BatchPathSolver
 batch = int(sys.argv[1]) if len(sys.argv) > 1 else 1024

@@ -1,4 +1,4 @@
-import sys; sys.path.insert(0,'/root/repo')
+import os, sys; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 from path_optimizer_b200 import synth, planner
 pl = planner.PathPlanner(max_batch=64, max_total_points=64*300)

@@ -1,7 +1,7 @@
 """Diagnostic: device time of the solve kernel for the eight 1024-path shards of the multi-GPU bench."""
 import os
 import sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from path_optimizer_b200 import synth
 from path_optimizer_b200.solver import BatchPathSolver
 s = BatchPathSolver(max_batch=1024, max_total_points=1024 * 100)
