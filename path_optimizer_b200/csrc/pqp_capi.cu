@@ -412,7 +412,6 @@ static int solve_batch_generic(pqp_handle *h, int formulation, int batch, const 
            o_oi = al(o_sep + B * 128), o_end = al(o_oi + T * 12);
     if (o_end > h->gen_cap) {
         cudaFree(h->d_gen); cudaFreeHost(h->h_gen);
-    if (h->env && h->env_free) h->env_free(h->env);
         h->d_gen = nullptr; h->h_gen = nullptr; h->gen_cap = 0;
         PQP_CUDA(cudaMalloc(&h->d_gen, o_end));
         PQP_CUDA(cudaMallocHost(&h->h_gen, o_end));

@@ -283,3 +283,22 @@ def test_golden_env_fixture(tmp_path):
                 for f in ("x", "y", "z", "k", "s"):
                     assert np.abs(a[f] - w[f]).max(initial=0.0) <= FRENET_TOL
     p.close()
+
+
+def test_map_survives_generic_solves(field):
+    """Regression: a K / KPC solve grows the handle's generic staging buffers; the uploaded map and the scratch of the
+    map-based stages belong to the same handle and must be untouched by that."""
+    prm = oracle.default_params()
+    p = planner.PathPlanner(max_batch=64, max_total_points=64 * 100)
+    p.set_map(field)
+    xy = np.array([[0.0, 0.0], [-20.0, 1.0], [35.0, -3.0]])
+    before = p.map_distance(xy)
+    b = synth.curvy_corridors(4, 40)
+    assert (p.solve(b, "K")["status"] == oracle.solve_batch(prm, 1, b)["status"]).all()
+    b2 = synth.curvy_corridors(48, 100)              # larger batch: the staging buffers grow again
+    p.solve(b2, "K")
+    assert (p.map_distance(xy) == before).all()
+    assert (before == oracle.map_distance(field, xy)).all()
+    r = p.plan(synth.map_reference_paths(4, 60))
+    assert len(r["status"]) == 4
+    p.close()
