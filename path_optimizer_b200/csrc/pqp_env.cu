@@ -277,7 +277,7 @@ int upload_paths(pqp_handle *h, EnvState *e, int batch, const int32_t *n_points,
             pqp_set_err("PQP_BOUNDS_IMPROVED needs the reference splines (n_knots, knots, x_coef, y_coef)");
             return PQP_ERR_ARG;
         }
-        // knot offsets go through the pinned order scratch (same size class)
+        // knot offsets (a small host vector; see the note on pageable copies below)
         std::vector<int32_t> koff(B + 1, 0);
         for (int b = 0; b < batch; ++b) {
             if (n_knots[b] < 3) { pqp_set_err("a reference spline needs >= 3 knots"); return PQP_ERR_ARG; }
