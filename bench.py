@@ -286,7 +286,7 @@ def run_ours(args, rank, world, local_rank):
             "gpu_launches": args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src,
-                         "kernel": "pqp_kp3_solve_kernel<17,6,4>", "algorithmic_bytes_per_launch": B * io_bytes_per_solve(N),
+                         "kernel": "pqp_kp3_solve_kernel<17,6,4,17>", "algorithmic_bytes_per_launch": B * io_bytes_per_solve(N),
                          "note": "state is SM-resident by design: compulsory HBM traffic is I/O only (SURVEY 8d); the kernel is "
                                  "bound by dependent-issue latency at 8 warps/SM, see profiles/r01_phase_cycles.md"},
             "clocks": clocks, "solved_fraction": int(solved.item()) / (world * B), "wall_ms_per_step": wall_ms / args.steps,
