@@ -66,7 +66,44 @@ class ClockSampler:
         self._stop = threading.Event()
         self._t = None
 
+    def _nvml_handle(self):
+        """NVML handle of CUDA device `index` (matched by UUID: CUDA_VISIBLE_DEVICES may reorder), or None."""
+        try:
+            import pynvml
+            import torch
+            pynvml.nvmlInit()
+            try:
+                uuid = str(torch.cuda.get_device_properties(self.index).uuid)
+                if not uuid.startswith("GPU-"):
+                    uuid = "GPU-" + uuid
+                return pynvml, pynvml.nvmlDeviceGetHandleByUUID(uuid.encode())
+            except Exception:
+                return pynvml, pynvml.nvmlDeviceGetHandleByIndex(self.index)
+        except Exception:
+            return None, None
+
     def _run(self):
+        nv, hdl = self._nvml_handle()
+        if hdl is not None:
+            # NVML in-process: a sample every few milliseconds (the timed region is only ~0.2 s long)
+            bits = {0x8: 2, 0x40: 3, 0x20: 4, 0x4: 5}    # hw_slowdown, hw_thermal, sw_thermal, sw_power_cap -> column
+            try:
+                mx = nv.nvmlDeviceGetMaxClockInfo(hdl, nv.NVML_CLOCK_SM)
+                while not self._stop.is_set():
+                    sm = nv.nvmlDeviceGetClockInfo(hdl, nv.NVML_CLOCK_SM)
+                    try:
+                        r = nv.nvmlDeviceGetCurrentClocksEventReasons(hdl)
+                    except Exception:
+                        r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(hdl)
+                    row = [str(sm), str(mx), "Not Active", "Not Active", "Not Active", "Not Active"]
+                    for bit, col in bits.items():
+                        if r & bit:
+                            row[col] = "Active"
+                    self.samples.append(row)
+                    self._stop.wait(0.005)
+                return
+            except Exception:
+                pass   # fall through to the command-line poller
         while not self._stop.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
