@@ -62,6 +62,7 @@ struct Kp3 {
     static constexpr int kSolveT = (MMAX + 31) / 32 * 32;   // threads that run the banded interior solves (non-dense form)
     static constexpr int kRow = IMAX + 1;                // row pitch of a dense inverse (even: 128-bit loads stay aligned, 4*lane word offsets)
     static constexpr int kFacSlots = kDense ? IMAX * kRow : IMAX * (BW + 1);
+    static_assert(!kDense || IMAX * kRow >= IMAX * (BW + 1) + kRed2 + 27 + 12, "refactorisation scratch must fit behind the band factor");
 
     PQP_HD static Kp3Dims dims(int N, int keep) {
         Kp3Dims d = kp3_dims_raw(N, keep, MMAX);
@@ -88,17 +89,21 @@ struct Kp3 {
         PQP_DEV double *T() const { return fac() + kFacSlots * M; }       // spikes T[c][pos], c < 6: [6*nv]
         PQP_DEV int nSd() const { return kTwoLevel ? 3 * ((M + 1) / 2) : nS; }   // order of the dense separator inverse
         PQP_DEV double *Sinv() const { return T() + 6 * nv; }             // [nSd*nSd]
-        PQP_DEV double *red() const { return Sinv() + nSd() * nSd(); }    // [kRed2*M] + blocks [27*M]
+        // refactorisation scratch [kRed2*M] + blocks [27*M] + couplings [12*M].  With dense interiors it lives in the
+        // part of the fac / kinv region the band factor does not use (free until the dense inverses are written, which
+        // is the last step of a refactorisation): two CTAs then need < 196 KB and the SM keeps 60 KB of L1 for the spills.
+        PQP_DEV double *red() const { return kDense ? fac() + IMAX * (BW + 1) * M : Sinv() + nSd() * nSd(); }
         PQP_DEV double *blk() const { return red() + kRed2 * M; }         // A|C|Off per chunk [27*M]
         PQP_DEV double *cpl() const { return blk() + 27 * M; }            // coupling coefs [12*M]
         // two-level form: per separator E = Dg^-1 (odd) | PL | PR (even) | Off copy [36*M]; reduced system [kRed2*ceil(M/2)]
-        PQP_DEV double *lv() const { return cpl() + 12 * M; }
+        PQP_DEV double *lv() const { return kDense ? Sinv() + nSd() * nSd() : cpl() + 12 * M; }
         PQP_DEV double *red2() const { return lv() + 36 * M; }
     };
     PQP_HD static size_t smem_doubles(const Kp3Dims &d) {
         return 2 * (size_t)d.nv + 8 * (size_t)kT + (size_t)kFacSlots * d.M + 6 * (size_t)d.nv +
                (kTwoLevel ? (size_t)9 * ((d.M + 1) / 2) * ((d.M + 1) / 2) : (size_t)d.nS * d.nS) +
-               (size_t)(kRed2 + 27 + 12) * d.M + (kTwoLevel ? (size_t)36 * d.M + (size_t)kRed2 * ((d.M + 1) / 2) : 0);
+               (kDense ? 0 : (size_t)(kRed2 + 27 + 12) * d.M) +
+               (kTwoLevel ? (size_t)36 * d.M + (size_t)kRed2 * ((d.M + 1) / 2) : 0);
     }
 
 #define PQP_F(k, dd) fcol[((k) * (BW + 1) + (dd)) * Mst]
