@@ -281,3 +281,43 @@ def test_golden_env_fixture_is_reproduced():
     pl = oracle.plan(p, field, b, bounds_mode=planner.BOUNDS_SIMPLE)
     assert (pl["status"] == g["plan_simple_raw_status"]).all() and (pl["iters"] == g["plan_simple_raw_iters"]).all()
     assert set(g["plan_simple_raw_status"].tolist()) >= {1, -3}
+
+
+def _config1():
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "config1_benchmark_map.npz"))
+    field = dict(distance=g["map_distance"], rows=int(g["image_shape"][0]), cols=int(g["image_shape"][1]),
+                 resolution=float(g["map_geo"][0]), center_x=float(g["map_geo"][1]), center_y=float(g["map_geo"][2]))
+    b = dict(n_points=g["n_points"], ref=g["ref"], x0=g["x0"], end_heading=g["end_heading"])
+    b["offsets"] = np.array([0, int(g["n_points"][0])], dtype=np.int32)
+    spl = dict(n_knots=np.array([len(g["knots"])], dtype=np.int32), knots=g["knots"], x_coef=g["x_coef"], y_coef=g["y_coef"])
+    return g, field, b, spl
+
+
+def test_config1_reference_benchmark_case():
+    """BASELINE config 1: the reference's own benchmark inputs (obstacles_for_benchmark.png, the 100-point polyline and
+    poses of path_optimizer_benchmark.cpp:47-82; fixture generated by tests/golden/make_golden_config1.py).  The map
+    is the reference's: 495 x 497 px at 0.2 m, 7 % occupied; the oracle reproduces the committed outputs,
+    and the product's kernel sources (host builds) reproduce bounds and QP."""
+    g, field, b, spl = _config1()
+    assert tuple(g["image_shape"]) == (495, 497) and abs(float(g["occupied_fraction"]) - 0.07) < 0.005
+    assert 125 <= int(g["n_points"][0]) <= 135                       # 39.56 m at 0.3 m
+    p = oracle.default_params()
+    for mode, tag in ((planner.BOUNDS_IMPROVED, "improved"), (planner.BOUNDS_SIMPLE, "simple")):
+        sp = spl if mode == planner.BOUNDS_IMPROVED else None
+        r = oracle.update_bounds(p, field, b, mode=mode, splines=sp)
+        assert r["bounds"].tobytes() == g[f"bounds_{tag}"].tobytes() and (r["n_valid"] == g[f"n_valid_{tag}"]).all()
+        e = emu.update_bounds(p, field, b, mode=mode, splines=sp)
+        assert e["bounds"].tobytes() == g[f"bounds_{tag}"].tobytes()
+    pl = oracle.plan(p, field, b, bounds_mode=planner.BOUNDS_IMPROVED, splines=spl)
+    assert pl["status"][0] == g["plan_improved_status"][0] == 1 and pl["iters"][0] == g["plan_improved_iters"][0]
+    assert pl["ok"][0] == 1 and pl["n_out"][0] == g["n_points"][0]
+    assert np.abs(pl["states"]["x"] - g["plan_improved_states"]["x"]).max() == 0.0
+    # the QP of the chain on the kernel source (eight-warp class: 132 stations)
+    qb = dict(b)
+    qb["bounds"] = g["bounds_improved"]
+    k = emu.solve_batch(p, qb, variant=8)
+    assert k["status"][0] == 1 and k["iters"][0] == g["plan_improved_iters"][0]
+    assert np.abs(k["states"]["x"] - g["plan_improved_states"]["x"]).max() <= 1e-9
+    # the optimized path stays clear of the obstacles and inside the corridor it was given
+    assert oracle.check_states(p, field, pl["states"]).all()

@@ -302,3 +302,27 @@ def test_map_survives_generic_solves(field):
     r = p.plan(synth.map_reference_paths(4, 60))
     assert len(r["status"]) == 4
     p.close()
+
+
+def test_config1_reference_benchmark_case():
+    """BASELINE config 1 (the reference's own benchmark inputs, tests/golden/config1_benchmark_map.npz): bounds on the
+    reference's obstacle map -> KP QP -> collision-checked output through pqp_plan_batch, against the committed
+    oracle outputs."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "config1_benchmark_map.npz"))
+    field = dict(distance=g["map_distance"], rows=int(g["image_shape"][0]), cols=int(g["image_shape"][1]),
+                 resolution=float(g["map_geo"][0]), center_x=float(g["map_geo"][1]), center_y=float(g["map_geo"][2]))
+    b = dict(n_points=g["n_points"], ref=g["ref"], x0=g["x0"], end_heading=g["end_heading"])
+    b["offsets"] = np.array([0, int(g["n_points"][0])], dtype=np.int32)
+    spl = dict(n_knots=np.array([len(g["knots"])], dtype=np.int32), knots=g["knots"], x_coef=g["x_coef"], y_coef=g["y_coef"])
+    p = planner.PathPlanner(max_batch=1, max_total_points=256)
+    p.set_map(field)
+    for mode, tag in ((planner.BOUNDS_IMPROVED, "improved"), (planner.BOUNDS_SIMPLE, "simple")):
+        sp = spl if mode == planner.BOUNDS_IMPROVED else None
+        r = p.plan(b, bounds_mode=mode, splines=sp, want_bounds=True)
+        assert r["status"][0] == g[f"plan_{tag}_status"][0] == SOLVED and r["iters"][0] == g[f"plan_{tag}_iters"][0]
+        assert r["n_out"][0] == g[f"plan_{tag}_n_out"][0] and r["ok"][0] == 1
+        assert np.abs(r["bounds"].view(np.float64) - g[f"bounds_{tag}"].view(np.float64)).max() <= FP_TOL
+        for f in ("x", "y", "z", "k", "s"):
+            assert np.abs(r["states"][f] - g[f"plan_{tag}_states"][f]).max() <= FRENET_TOL
+    p.close()
