@@ -13,7 +13,13 @@ pqp_kp_solve_kernel(const __grid_constant__ pqp::DevParams prm, const __grid_con
     pqp::kp_solve_path(w, prm, bv, prob, pqp_smem, (size_t)smem_doubles);
 }
 
-static size_t g_smem(int n, int keep) { return pqp::kp_smem_doubles(pqp::kp_dims(n, keep)) * sizeof(double); }
+// Shared memory for a path: with the scalings on chip when that fits the 227 KB a CTA can opt into, else with the
+// scalings in the global workspace (the kernel makes the same choice from the size it is launched with).
+static size_t g_smem(int n, int keep) {
+    const pqp::KpDims d = pqp::kp_dims(n, keep);
+    const size_t full = pqp::kp_smem_doubles(d) * sizeof(double);
+    return full <= 232448 ? full : pqp::kp_smem_doubles(d, true) * sizeof(double);
+}
 static bool g_fits(int, int keep) { return keep <= 10; }
 void pqp_variant_k1_generic(PqpVariant *out) {
     *out = PqpVariant{0, pqp::kMaxBand, 32, (const void *)pqp_kp_solve_kernel, g_smem, g_fits};

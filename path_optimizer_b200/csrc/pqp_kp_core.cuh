@@ -90,34 +90,46 @@ PQP_HD int kp_gu(const KpDims &d, int j) {
 //   2 arrays of ch   : vUB EUB ; 4 scalars: vEnd[2] EEnd[2]
 //   band [(bw+1)*nred] ; red [kRedStride*32]
 constexpr int kRedStride = 48;
-constexpr int kKpNrArrays = 5;
-constexpr int kKpNArrays = 39;
+// Shared-memory layout.  The Ruiz scalings (row factors E of the 9 per-station row kinds, column factors D) are read
+// at scaling time, in the row weights and at residual checks; they normally sit in shared memory next to the rest, but
+// for paths too long for that (N > ~340 stations) they move to the path's global workspace (`in_ws`), which takes the
+// one-warp kernel to ~420 stations.
+constexpr int kKpNrArrays = 4;    // xr, tr, tmp, sgr            [nred each]
+constexpr int kKpNArrays = 29;    // per-station arrays kept in shared memory in both layouts
+constexpr int kKpEArrays = 10;    // ED[3], EKB, ESB, EH1, EH3, ES4, ES2, Dsl   [N each]  (+ Dr [nred])
 struct KpSmem {
     double *base;
+    double *ebase;   // E arrays + Dsl: shared memory or workspace
+    double *drbase;  // Dr
     int N, ch, nred, bwp1;
+    bool in_ws;
 #define PQP_F_NR(name, k) \
     PQP_DEV double *name() const { return base + (k) * nred; }
 #define PQP_F_N(name, k) \
     PQP_DEV double *name() const { return base + kKpNrArrays * nred + (k) * N; }
+#define PQP_F_E(name, k) \
+    PQP_DEV double *name() const { return ebase + (k) * N; }
     PQP_F_NR(xr, 0)   // iterate, reduced unknowns in g-order
     PQP_F_NR(tr, 1)   // rhs / x-tilde
     PQP_F_NR(tmp, 2)  // second vector (interior correction solve, scratch)
-    PQP_F_NR(Dr, 3)   // Ruiz D
-    PQP_F_NR(sgr, 4)  // sigma / D^2
+    PQP_F_NR(sgr, 3)  // sigma / D^2
+    PQP_DEV double *Dr() const { return drbase; }   // Ruiz D
     PQP_F_N(xs, 0) PQP_F_N(ts, 1)
     PQP_F_N(vD, 2)    // [3][N] v = z + w of the dynamics rows
     PQP_F_N(vKB, 5) PQP_F_N(vSB, 6) PQP_F_N(vH1, 7) PQP_F_N(vH3, 8)
     PQP_F_N(vS4m, 9) PQP_F_N(vS4p, 10) PQP_F_N(vS2m, 11) PQP_F_N(vS2p, 12)
-    PQP_F_N(ED, 13)   // [3][N] Ruiz E of the dynamics rows
-    PQP_F_N(EKB, 16) PQP_F_N(ESB, 17) PQP_F_N(EH1, 18) PQP_F_N(EH3, 19) PQP_F_N(ES4, 20) PQP_F_N(ES2, 21)
-    PQP_F_N(Dsl, 22) PQP_F_N(sgs, 23)
-    PQP_F_N(ds, 24) PQP_F_N(q10, 25) PQP_F_N(kds, 26)  // ds_i, -kappa_i^2 ds_i, ds_i kappa_i
-    PQP_F_N(lH1, 27) PQP_F_N(uH1, 28) PQP_F_N(lH3, 29) PQP_F_N(uH3, 30)
-    PQP_F_N(uS4m, 31) PQP_F_N(lS4p, 32) PQP_F_N(uS2m, 33) PQP_F_N(lS2p, 34)
-    PQP_F_N(gD, 35)   // [3][N] weighted dynamics-row values for the A' gather
-    PQP_F_N(ksinv, 38)
+    PQP_F_E(ED, 0)    // [3][N] Ruiz E of the dynamics rows
+    PQP_F_E(EKB, 3) PQP_F_E(ESB, 4) PQP_F_E(EH1, 5) PQP_F_E(EH3, 6) PQP_F_E(ES4, 7) PQP_F_E(ES2, 8)
+    PQP_F_E(Dsl, 9)
+    PQP_F_N(sgs, 13)
+    PQP_F_N(ds, 14) PQP_F_N(q10, 15) PQP_F_N(kds, 16)  // ds_i, -kappa_i^2 ds_i, ds_i kappa_i
+    PQP_F_N(lH1, 17) PQP_F_N(uH1, 18) PQP_F_N(lH3, 19) PQP_F_N(uH3, 20)
+    PQP_F_N(uS4m, 21) PQP_F_N(lS4p, 22) PQP_F_N(uS2m, 23) PQP_F_N(lS2p, 24)
+    PQP_F_N(gD, 25)   // [3][N] weighted dynamics-row values for the A' gather
+    PQP_F_N(ksinv, 28)
 #undef PQP_F_NR
 #undef PQP_F_N
+#undef PQP_F_E
     PQP_DEV double *tail() const { return base + kKpNrArrays * nred + kKpNArrays * N; }
     PQP_DEV double *vUB() const { return tail(); }
     PQP_DEV double *EUB() const { return tail() + ch; }
@@ -125,15 +137,21 @@ struct KpSmem {
     PQP_DEV double *EEnd() const { return tail() + 2 * ch + 2; }
     PQP_DEV double *band() const { return tail() + 2 * ch + 4; }
     PQP_DEV double *red() const { return band() + bwp1 * nred; }
+    PQP_DEV double *escr() const { return red() + kRedStride * 32; }   // E arrays + Dr when they stay in shared memory
 };
 
-PQP_HD size_t kp_smem_doubles(const KpDims &d) {
+PQP_HD size_t kp_smem_doubles(const KpDims &d, bool in_ws = false) {
     return (size_t)kKpNrArrays * d.nred + (size_t)kKpNArrays * d.N + 2 * (size_t)d.ch + 4 +
-           (size_t)(d.bw + 1) * d.nred + (size_t)kRedStride * 32;
+           (size_t)(d.bw + 1) * d.nred + (size_t)kRedStride * 32 +
+           (in_ws ? 0 : (size_t)kKpEArrays * d.N + (size_t)d.nred);
 }
 
-PQP_DEV void kp_smem_carve(const KpDims &d, double *base, KpSmem &s) {
+// `ws` = the path's workspace region (kp_ws_base); used for the scalings when in_ws
+PQP_DEV void kp_smem_carve(const KpDims &d, double *base, KpSmem &s, bool in_ws, double *ws) {
     s.base = base; s.N = d.N; s.ch = d.ch; s.nred = d.nred; s.bwp1 = d.bw + 1;
+    s.in_ws = in_ws;
+    s.ebase = in_ws ? ws : s.escr();
+    s.drbase = s.ebase + (size_t)kKpEArrays * d.N;
 }
 
 // ---- per-problem context ------------------------------------------------------------------------
@@ -693,7 +711,9 @@ PQP_DEV void kp_solve_path(Warp &w, const DevParams &prm, const BatchView &bv, i
     KpCtx cx;
     cx.pm = &prm;
     cx.d = kp_dims(N < 2 ? 2 : N, keep > 10 ? 10 : keep);
-    if (!bad && kp_smem_doubles(cx.d) > smem_doubles) bad = 1;
+    // long paths: the scalings go to the workspace (needs one: 10 N + nred <= 16 N + kWsPerPath doubles)
+    const bool in_ws = !bad && kp_smem_doubles(cx.d) > smem_doubles && bv.workspace != nullptr;
+    if (!bad && kp_smem_doubles(cx.d, in_ws) > smem_doubles) bad = 1;
     if (bad) {
         if (lane == 0) {
             bv.status[prob] = PQP_INVALID_PROBLEM;
@@ -711,7 +731,7 @@ PQP_DEV void kp_solve_path(Warp &w, const DevParams &prm, const BatchView &bv, i
         return;
     }
     const KpDims &d = cx.d;
-    kp_smem_carve(d, smem, cx.s);
+    kp_smem_carve(d, smem, cx.s, in_ws, bv.workspace ? kp_ws_base(bv.workspace, off, prob) : nullptr);
     KpSmem &s = cx.s;
     const int ch = d.ch;
     const DevParams &pm = *cx.pm;

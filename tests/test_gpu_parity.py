@@ -302,3 +302,32 @@ def test_parameter_sweep(case):
     assert np.array_equal(rk["status"], ok_["status"]) and np.array_equal(rk["iters"], ok_["iters"])
     np.testing.assert_allclose(rk["frenet"], ok_["frenet"], rtol=0, atol=FRENET_TOL)
     s.close()
+
+
+def test_config5_mixed_lengths_up_to_400(solver, oracle_params):
+    """BASELINE config 5 shape: path lengths drawn from 50..400 stations.  Every length has a kernel class (4-warp and
+    8-warp thread-per-station classes up to 256, the one-warp kernel beyond -- with its scalings in the global
+    workspace above ~340 stations); shards of equal total station count (parallel.shard_by_work) give the same results
+    as the whole batch."""
+    from path_optimizer_b200 import parallel
+    rng = np.random.default_rng(31)
+    n_points = rng.integers(50, 401, size=48)
+    n_points[:4] = [400, 399, 344, 343]
+    b = synth.curvy_corridors(48, n_points=n_points)
+    res = solver.solve(b)
+    ref = oracle.solve_batch(oracle_params, 0, b, threads=8)
+    _compare(res, ref)
+    assert (res["status"] == SOLVED).all()
+    parts = parallel.shard_by_work(n_points, 2)                     # index sets of (nearly) equal station totals
+    assert sorted(np.concatenate(parts).tolist()) == list(range(48))
+    assert abs(int(n_points[parts[0]].sum()) - int(n_points[parts[1]].sum())) <= int(n_points.max())
+    o = b["offsets"]
+    for idx in parts:
+        sub = dict(n_points=n_points[idx].astype(np.int32),
+                   ref=np.concatenate([b["ref"][o[i]:o[i + 1]] for i in idx]),
+                   bounds=np.concatenate([b["bounds"][o[i]:o[i + 1]] for i in idx]),
+                   x0=b["x0"][idx], end_heading=b["end_heading"][idx])
+        part = solver.solve(sub)
+        assert np.array_equal(part["iters"], res["iters"][idx]) and np.array_equal(part["status"], res["status"][idx])
+        want = np.concatenate([res["frenet"][o[i]:o[i + 1]] for i in idx])
+        assert part["frenet"].tobytes() == want.tobytes()
