@@ -84,7 +84,12 @@ int pqp_launch_kp_classes(pqp_handle *h, const pqp::BatchView &bv, int batch, co
         }
         const int ke = std::min(std::max(keep, 1), 10), ne = std::max((int)n[b], 2);
         size_t need = kVariants[v].smem(ne, ke);
-        if (need > (size_t)h->smem_optin) { v = kNumVariants - 1; need = kVariants[v].smem(2, 1); }   // reports PQP_INVALID_PROBLEM
+        if (need > (size_t)h->smem_optin) {
+            // too long for this class: the one-warp kernel takes it if it fits there, else it reports PQP_INVALID_PROBLEM
+            v = kNumVariants - 1;
+            need = (ke <= 10) ? kVariants[v].smem(ne, ke) : (size_t)h->smem_optin + 1;
+            if (need > (size_t)h->smem_optin) need = kVariants[v].smem(2, 1);
+        }
         cls[b] = v;
         smem_v[v] = std::max(smem_v[v], need);
         count_v[v]++;
@@ -529,9 +534,10 @@ int pqp_solve_batch(pqp_handle *h, int formulation, int batch, const int32_t *n_
         const int ke = std::min(std::max(keep, 1), 10), ne = std::max(n, 2);
         size_t need = kVariants[v].smem(ne, ke);
         if (need > (size_t)h->smem_optin) {
-            // too long for this class: the generic kernel reports PQP_INVALID_PROBLEM for it
+            // too long for this class: the one-warp kernel takes it if it fits there, else it reports PQP_INVALID_PROBLEM
             v = kNumVariants - 1;
-            need = kVariants[v].smem(2, 1);
+            need = (ke <= 10) ? kVariants[v].smem(ne, ke) : (size_t)h->smem_optin + 1;
+            if (need > (size_t)h->smem_optin) need = kVariants[v].smem(2, 1);
         }
         cls[b] = v;
         need_b[b] = need;
