@@ -1,28 +1,38 @@
 #!/usr/bin/env python
 """bench.py -- batched path-QP solves/s on B200 (BASELINE.json metric), one rank per GPU.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config 2|3|4|5]
 
-A "step" is one pass of the hot path (QP assembly -> ADMM solve -> state extraction) over one batch
-of synthetic corridor paths: BASELINE config 2 = 1024 paths x 100 stations per GPU (weak scaling:
-every rank solves its own 1024-path shard; at N > 1 each step ends with ONE NCCL all-gather of the
-solved Frenet states, BASELINE config 4).  Prints one JSON line on rank 0.
+A "step" is one pass of the hot path (QP assembly -> ADMM solve -> state extraction) over one batch of
+synthetic corridor paths.  The default workload is BASELINE config 2 (1024 paths x 100 stations per GPU);
+--config selects configs 3, 4, 5 at their named sizes (path_optimizer_b200/workloads.py).  Weak scaling:
+every rank solves its own shard; at N > 1 each step ends with ONE NCCL all-gather of the solved Frenet
+states.  Rank 0 prints one JSON line.
 
-  value        solves/s with the inputs already resident in HBM (pqp_solve_batch_device), timed with
-               CUDA events on the launching stream, L2 flushed between timed steps, max over ranks.
-  e2e          the same metric through the host-buffer C-ABI call (pqp_solve_batch): pinned host
-               inputs, H2D + kernel + D2H inside the timed region every step.
-  roofline     dominant kernel's algorithmic HBM bytes (52 N + 32 B per solve) / its
-               average launch time, against the measured HBM copy bandwidth.
-  cpu_baseline the CPU oracle (OSQP-algorithm restatement, oracle/) on the host cores, bounded sample.
+  value        solves/s with the inputs already resident in HBM (pqp_solve_batch_device, or
+               pqp_solve_batch_device_classes for the mixed-length config 5), CUDA events on the launching
+               stream, L2 flushed between timed steps, max over ranks.
+  e2e          the same metric through the host-buffer C-ABI call (pqp_solve_batch): pinned host inputs,
+               H2D + kernels + D2H inside the call, timed by host wall clock around the call
+               (time.perf_counter; the library's own event spans are reported beside it as a breakdown).
+  roofline     dominant kernel's algorithmic HBM bytes (52 N + 32 B per solve) / its average
+               launch time against the measured HBM copy bandwidth, plus the second figure SURVEY 8d
+               mandates: the per-iteration working set W_iter = 944 N B streamed at the measured
+               iteration rate, labelled ON-CHIP (the ADMM state never leaves the SM).
+  cpu_baseline the CPU oracle (restatement of the reference's assembly + OSQP recurrence, oracle/) on the
+               host's physical cores, bounded sample, min / median of repetitions.
+  extras       default run only (config 2, one GPU): short measurements of configs 3, 4 and 5 at their
+               named per-GPU sizes (QP-only, and config 3 through the chained planner iteration too).
 
---impl reference times the CPU oracle (the reference's own OSQP-based path cannot be built here:
-no Eigen/OSQP/osqp-eigen in the image) on all host cores, same workload, same JSON contract.
+--impl reference times the CPU oracle on the host cores (the reference's own OSQP-based binary cannot be
+built here: no Eigen / OSQP / osqp-eigen / glog / gflags in the image), same `config` object, same JSON
+contract; each step is a bounded sample of the workload (stated in cpu_baseline.sample).
 """
 import argparse
 import ctypes as C
 import json
 import os
+import statistics
 import subprocess
 import sys
 import threading
@@ -33,18 +43,22 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-from path_optimizer_b200 import synth  # noqa: E402
+from path_optimizer_b200 import synth, workloads  # noqa: E402
 from path_optimizer_b200.abi import BOUNDS_DTYPE, STATE_DTYPE, Stats  # noqa: E402
 
-PATHS_PER_GPU = 1024
-N_POINTS = 100
 METRIC = "path_qp_solves_per_sec"
 UNIT = "solves/s"
+CPU_SAMPLE_PATHS = 1024      # paths per CPU step for configs whose shard is larger than that
 
 
 def io_bytes_per_solve(n):
     """SURVEY.md 8(d) contract figure B_io(N) = 52 N + 32 (fp32-packed compulsory I/O)."""
     return 52 * n + 32
+
+
+def w_iter_bytes(n):
+    """SURVEY.md 8(d) per-iteration working set W_iter(N) = 236 N floats = 944 N bytes."""
+    return 944 * n
 
 
 def measured_peak_gbs():
@@ -56,7 +70,7 @@ def measured_peak_gbs():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clock / throttle reasons sampled DURING the timed region (NVML in-process, nvidia-smi fallback)."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -85,7 +99,6 @@ class ClockSampler:
     def _run(self):
         nv, hdl = self._nvml_handle()
         if hdl is not None:
-            # NVML in-process: a sample every few milliseconds (the timed region is only ~0.2 s long)
             bits = {0x8: 2, 0x40: 3, 0x20: 4, 0x4: 5}    # hw_slowdown, hw_thermal, sw_thermal, sw_power_cap -> column
             try:
                 mx = nv.nvmlDeviceGetMaxClockInfo(hdl, nv.NVML_CLOCK_SM)
@@ -131,250 +144,453 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(self.samples)}
 
 
-def cpu_threads():
+# ----------------------------------------------------------------------------------------------------
+# CPU arm
+# ----------------------------------------------------------------------------------------------------
+
+def host_cores():
+    """(threads usable by this process, physical cores among them).  The CPU arm runs one thread per physical
+    core: the oracle's sparse triangular solves are latency bound and gain nothing from the second hyper-thread,
+    while oversubscribing a cgroup-limited container costs a lot (round 1: 3.3 k..15 k solves/s for the same batch)."""
     try:
-        return len(os.sched_getaffinity(0))
+        cpus = sorted(os.sched_getaffinity(0))
     except Exception:
-        return os.cpu_count() or 1
+        cpus = list(range(os.cpu_count() or 1))
+    cores = set()
+    for c in cpus:
+        try:
+            with open(f"/sys/devices/system/cpu/cpu{c}/topology/thread_siblings_list") as f:
+                cores.add(f.read().strip())
+        except Exception:
+            cores.add(str(c))
+    n_log, n_phys = len(cpus), max(1, len(cores))
+    quota = None
+    try:   # cgroup v2 CPU quota
+        with open("/sys/fs/cgroup/cpu.max") as f:
+            q, p = f.read().split()
+            if q != "max":
+                quota = max(1, int(float(q) / float(p)))
+    except Exception:
+        pass
+    if quota:
+        n_log, n_phys = min(n_log, quota), min(n_phys, quota)
+    return n_log, n_phys
 
 
-def best_cpu_threads(oracle, params, batch, cores):
-    """The box may expose more hardware threads than it lets a container use (cgroup quota) and the
-    oracle is memory-allocation heavy: probe a few thread counts on a small sample, keep the fastest."""
-    sample = synth.slice_batch(batch, 0, min(len(batch["n_points"]), 256))
-    oracle.solve_batch(params, 0, synth.slice_batch(batch, 0, 8), threads=1)   # builds the symbolic cache
-    best, best_rate = 1, 0.0
-    for t in sorted({cores, max(1, cores // 2), max(1, cores // 4), max(1, cores // 8), 32, 16, 8}):
-        if t > cores:
-            continue
-        r = oracle.solve_batch(params, 0, sample, threads=t)
-        rate = len(sample["n_points"]) / r["seconds"]
-        if rate > best_rate:
-            best, best_rate = t, rate
-    return best
+def oracle_bounds_fn(oracle, params):
+    field = synth.disc_field_map()
+
+    def fn(cand):
+        r = oracle.update_bounds(params, field, cand, mode=1)
+        return r["bounds"], r["n_valid"]
+    return fn
+
+
+def cpu_sample(config, oracle, params):
+    """The bounded per-step sample of a config for the CPU arm + a description of it."""
+    c = workloads.CONFIGS[config]
+    if c["paths_per_gpu"] <= CPU_SAMPLE_PATHS:
+        return workloads.build(config), f"the whole {c['paths_per_gpu']}-path shard of rank 0 per step"
+    if config == 3:
+        batch = workloads.build(3, paths=CPU_SAMPLE_PATHS, bounds_fn=oracle_bounds_fn(oracle, params))
+        return batch, f"the first {CPU_SAMPLE_PATHS} unblocked paths of rank 0's config-3 shard per step (bounds by the oracle's clearance stage, untimed)"
+    if config == 5:
+        full = workloads.build(5)
+        idx = np.arange(0, len(full["n_points"]), len(full["n_points"]) // CPU_SAMPLE_PATHS)[:CPU_SAMPLE_PATHS]
+        return synth.take_paths(full, idx), f"every {len(full['n_points']) // CPU_SAMPLE_PATHS}th path of rank 0's {len(full['n_points'])}-path shard ({CPU_SAMPLE_PATHS} paths, same length distribution) per step"
+    return workloads.build(config, paths=CPU_SAMPLE_PATHS), f"the first {CPU_SAMPLE_PATHS} paths of rank 0's {c['paths_per_gpu']}-path shard per step"
 
 
 def run_reference(args, rank, world):
-    """CPU arm: the oracle (port of the reference's algorithm) on the host cores."""
+    """CPU arm: the oracle (port of the reference's algorithm) on the host's physical cores."""
     if rank != 0:
         return
     from oracle import oracle
     params = oracle.default_params()
-    cores = cpu_threads()
-    batch = synth.straight_corridors(PATHS_PER_GPU, N_POINTS)
-    threads = best_cpu_threads(oracle, params, batch, cores)
+    n_log, n_phys = host_cores()
+    threads = args.cpu_threads or n_phys
+    batch, sample_text = cpu_sample(args.config, oracle, params)
+    B = len(batch["n_points"])
+    oracle.solve_batch(params, 0, synth.slice_batch(batch, 0, min(B, 8)), threads=1)   # builds the symbolic cache
     for _ in range(args.warmup):
-        oracle.solve_batch(params, 0, synth.slice_batch(batch, 0, min(PATHS_PER_GPU, 4 * threads)), threads=threads)
-    secs = 0.0
+        oracle.solve_batch(params, 0, synth.slice_batch(batch, 0, min(B, 4 * threads)), threads=threads)
+    step_s = []
     solved = 0
     for _ in range(args.steps):
         r = oracle.solve_batch(params, 0, batch, threads=threads)
-        secs += r["seconds"]
+        step_s.append(r["seconds"])
         solved += int((r["status"] == 1).sum())
-    value = PATHS_PER_GPU * args.steps / secs
+    secs = sum(step_s)
+    value = B * args.steps / secs
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"BASELINE config 2: {PATHS_PER_GPU} paths x {N_POINTS} stations, straight corridors, KP",
-                   "paths_per_step": PATHS_PER_GPU, "n_points": N_POINTS,
-                   "note": "CPU arm: fp64 C restatement of the reference's assembly + OSQP recurrence (oracle/); "
-                           "the reference's own binary needs Eigen/OSQP/osqp-eigen, absent from this image"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "hardware_threads_visible": cores,
-                         "sample": f"{args.steps} x {PATHS_PER_GPU} paths (whole batch per step), thread count = fastest of a probe"},
+        "config": workloads.describe(args.config, args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "hardware_threads_visible": n_log, "physical_cores_visible": n_phys,
+                         "sample": sample_text, "paths_per_step": B,
+                         "best_step_value": B / min(step_s), "median_step_value": B / statistics.median(step_s),
+                         "note": "fp64 C restatement of the reference's assembly + OSQP recurrence (oracle/): the reference's "
+                                 "own binary needs Eigen/OSQP/osqp-eigen, absent from this image; one thread per physical core, "
+                                 "paths handed out dynamically, per-thread scratch arena"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "solved_fraction": solved / (PATHS_PER_GPU * args.steps), "gpu_launches": 0,
+        "solved_fraction": solved / (B * args.steps), "gpu_launches": 0,
+        "iters_per_solve_mean": float(r["iters"].mean()),
     }
     print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------------
+
+class GpuWorkload:
+    """One config's shard resident on one GPU + the two timed calls (device-resident, host-buffer)."""
+
+    def __init__(self, config, rank, world, local_rank, torch):
+        from path_optimizer_b200 import _lib, planner
+        self.torch = torch
+        self.config, self.rank, self.world = config, rank, world
+        self.L = _lib.load()
+        self._lib = _lib
+        self.dev = torch.device("cuda", local_rank)
+        c = workloads.CONFIGS[config]
+        self.field = None
+        if config == 3:
+            self.field = synth.disc_field_map()
+            pl = planner.PathPlanner(device=local_rank, max_batch=c["paths_per_gpu"] + 1024,
+                                     max_total_points=(c["paths_per_gpu"] + 1024) * 200)
+            pl.set_map(self.field)
+
+            def fn(cand):
+                r = pl.update_bounds(cand)
+                return r["bounds"], r["n_valid"]
+            self.batch = workloads.build(3, rank, world, bounds_fn=fn)
+            pl.close()
+        else:
+            self.batch = workloads.build(config, rank, world)
+        b = self.batch
+        self.B = len(b["n_points"])
+        self.total = int(b["offsets"][-1])
+        self.nmax = int(b["n_points"].max())
+        self.solver = planner.PathPlanner(device=local_rank, max_batch=self.B, max_total_points=self.total)
+        off = b["offsets"]
+        self.keep = np.array([self.L.pqp_keep_control_steps(0, np.ascontiguousarray(b["ref"][off[i]:off[i + 1]]).ctypes.data_as(C.c_void_p),
+                                                            int(b["n_points"][i])) for i in range(self.B)], dtype=np.int32)
+        self.uniform = bool((b["n_points"] == b["n_points"][0]).all() and (self.keep == self.keep[0]).all())
+
+        def dev_bytes(arr):
+            t = torch.from_numpy(np.frombuffer(np.ascontiguousarray(arr).tobytes(), dtype=np.uint8).copy())
+            return t.to(self.dev)
+        self.d = dict(n=dev_bytes(b["n_points"]), off=dev_bytes(b["offsets"]), ref=dev_bytes(b["ref"]),
+                      bounds=dev_bytes(b["bounds"]), x0=dev_bytes(b["x0"]), end=dev_bytes(b["end_heading"]))
+        self.d_out = torch.zeros(self.total * STATE_DTYPE.itemsize, dtype=torch.uint8, device=self.dev)
+        self.d_status = torch.zeros(self.B, dtype=torch.int32, device=self.dev)
+        self.d_iters = torch.zeros(self.B, dtype=torch.int32, device=self.dev)
+        # the all-gather needs equal counts per rank: pad the Frenet buffer to the largest shard
+        self.gather_rows = self.total
+        if world > 1:
+            import torch.distributed as dist
+            t = torch.tensor([self.total], dtype=torch.int64, device=self.dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            self.gather_rows = int(t.item())
+        self.d_frenet = torch.zeros(self.gather_rows * 3, dtype=torch.float64, device=self.dev)
+        self.gathered = torch.zeros(world * self.gather_rows * 3, dtype=torch.float64, device=self.dev) if world > 1 else None
+        self.h_n = np.ascontiguousarray(b["n_points"], dtype=np.int32)
+        self._pinned = None
+
+    # ---- device-resident call (asynchronous on `stream`)
+    def solve_device(self, stream, stats=None):
+        d = self.d
+        sp = C.c_void_p(stream.cuda_stream)
+        st = C.byref(stats) if stats is not None else None
+        if self.uniform:
+            k = int(self.keep[0])
+            rc = self.L.pqp_solve_batch_device(self.solver._h, 0, self.B, self.total, self.nmax, k, k, d["n"].data_ptr(),
+                                               d["off"].data_ptr(), d["ref"].data_ptr(), d["bounds"].data_ptr(),
+                                               d["x0"].data_ptr(), d["end"].data_ptr(), None, None, self.d_out.data_ptr(),
+                                               self.d_frenet.data_ptr(), self.d_status.data_ptr(), self.d_iters.data_ptr(), sp, st)
+        else:
+            rc = self.L.pqp_solve_batch_device_classes(self.solver._h, 0, self.B, self.total, self.h_n.ctypes.data_as(C.c_void_p),
+                                                       self.keep.ctypes.data_as(C.c_void_p), d["n"].data_ptr(), d["off"].data_ptr(),
+                                                       d["ref"].data_ptr(), d["bounds"].data_ptr(), d["x0"].data_ptr(),
+                                                       d["end"].data_ptr(), None, None, self.d_out.data_ptr(),
+                                                       self.d_frenet.data_ptr(), self.d_status.data_ptr(),
+                                                       self.d_iters.data_ptr(), sp, st)
+        assert rc == 0, self._lib.last_error()
+
+    def gather(self):
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_gather_into_tensor(self.gathered, self.d_frenet)
+
+    # ---- host-buffer call (synchronous)
+    def _pin(self):
+        torch, b = self.torch, self.batch
+        pin = lambda a: torch.from_numpy(np.frombuffer(np.ascontiguousarray(a).tobytes(), dtype=np.uint8).copy()).pin_memory()  # noqa: E731
+        self._pinned = dict(ref=pin(b["ref"]), bounds=pin(b["bounds"]), x0=pin(b["x0"]), end=pin(b["end_heading"]),
+                            n=pin(b["n_points"]),
+                            out=torch.zeros(self.total * STATE_DTYPE.itemsize, dtype=torch.uint8).pin_memory(),
+                            frenet=torch.zeros(self.total * 3, dtype=torch.float64).pin_memory(),
+                            status=torch.zeros(self.B, dtype=torch.int32).pin_memory(),
+                            iters=torch.zeros(self.B, dtype=torch.int32).pin_memory())
+
+    def solve_host(self, stats):
+        if self._pinned is None:
+            self._pin()
+        p = self._pinned
+        rc = self.L.pqp_solve_batch(self.solver._h, 0, self.B, p["n"].data_ptr(), p["ref"].data_ptr(), p["bounds"].data_ptr(),
+                                    p["x0"].data_ptr(), p["end"].data_ptr(), None, None, p["out"].data_ptr(),
+                                    p["frenet"].data_ptr(), p["status"].data_ptr(), p["iters"].data_ptr(), C.byref(stats))
+        assert rc == 0, self._lib.last_error()
+
+    def class_mix(self):
+        """{kernel name: paths} as the library selects classes for this shard."""
+        mix = {}
+        v, t, s = C.c_int(), C.c_int(), C.c_int64()
+        if self.uniform:
+            self.L.pqp_device_class_info(self.nmax, int(self.keep[0]), int(self.keep[0]), 0, C.byref(v), C.byref(t), C.byref(s))
+            return {self.L.pqp_class_name(v.value).decode(): self.B}
+        for n, k in zip(self.h_n, self.keep):
+            self.L.pqp_class_info(int(n), int(k), 0, C.byref(v), C.byref(t), C.byref(s))
+            name = self.L.pqp_class_name(v.value).decode()
+            mix[name] = mix.get(name, 0) + 1
+        return mix
+
+    def close(self):
+        self.solver.close()
+
+
+def time_workload(w, torch, steps, warmup, flush, stream, barrier, with_e2e=True):
+    """Device-resident and host-buffer timings of one workload on this rank (not yet reduced over ranks)."""
+    st = Stats()
+    w.solve_device(stream, st)           # synchronising call with stats: launches per step
+    launches = int(st.kernel_launches)
+    for _ in range(max(0, warmup - 1)):
+        w.solve_device(stream)
+        w.gather()
+    barrier()
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(steps)]
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(steps):
+        flush.fill_(k & 0xFF)            # L2 flush between timed steps (outside the events)
+        ev[k][0].record(stream)
+        w.solve_device(stream)
+        ev[k][1].record(stream)
+        w.gather()
+        ev[k][2].record(stream)
+    barrier()
+    wall = time.perf_counter() - t0
+    solve_ms = [a.elapsed_time(b) for a, b, _ in ev]
+    gather_ms = [b.elapsed_time(c) for _, b, c in ev]
+    step_ms = [a.elapsed_time(c) for a, _, c in ev]
+    res = dict(launches_per_step=launches, dev_ms=sum(step_ms), solve_ms=sum(solve_ms), gather_ms=sum(gather_ms),
+               wall_ms=wall * 1e3, status=w.d_status.cpu().numpy(), iters=w.d_iters.cpu().numpy())
+    if with_e2e:
+        for _ in range(warmup):
+            w.solve_host(st)
+        barrier()
+        e2e_wall = e2e_span = kern = 0.0
+        for _ in range(steps):
+            flush.fill_(1)
+            torch.cuda.synchronize()
+            t1 = time.perf_counter()
+            w.solve_host(st)             # synchronous: returns when the results are in the caller's host buffers
+            e2e_wall += time.perf_counter() - t1
+            e2e_span += st.h2d_ms + st.kernel_ms + st.d2h_ms
+            kern += st.kernel_ms
+        barrier()
+        res.update(e2e_ms=e2e_wall * 1e3, e2e_span_ms=e2e_span, e2e_kernel_ms=kern, h2d=int(st.h2d_bytes), d2h=int(st.d2h_bytes),
+                   e2e_launches=int(st.kernel_launches))
+    return res
+
+
+def profile_units():
+    """Measured unit utilisations of the dominant kernel from the committed ncu capture (NOT this run)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f)
+    except Exception:
+        return {}
 
 
 def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
-    from path_optimizer_b200 import _lib
-    from path_optimizer_b200.solver import BatchPathSolver
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    B, N = PATHS_PER_GPU, N_POINTS
-    batch = synth.straight_corridors(B, N, first_path=rank * B)  # this rank's shard of the global batch
-    total = B * N
-    solver = BatchPathSolver(device=local_rank, max_batch=B, max_total_points=total)
-    L = _lib.load()
-    KEEP = int(L.pqp_keep_control_steps(0, np.ascontiguousarray(batch["ref"][:N]).ctypes.data_as(C.c_void_p), N))
-
-    def dev_bytes(arr):
-        t = torch.from_numpy(np.frombuffer(np.ascontiguousarray(arr).tobytes(), dtype=np.uint8).copy())
-        return t.to(dev)
-
-    d_n = dev_bytes(batch["n_points"]); d_off = dev_bytes(batch["offsets"])
-    d_ref = dev_bytes(batch["ref"]); d_bounds = dev_bytes(batch["bounds"])
-    d_x0 = dev_bytes(batch["x0"]); d_end = dev_bytes(batch["end_heading"])
-    d_out = torch.zeros(total * STATE_DTYPE.itemsize, dtype=torch.uint8, device=dev)
-    d_frenet = torch.zeros(total * 3, dtype=torch.float64, device=dev)
-    d_status = torch.zeros(B, dtype=torch.int32, device=dev)
-    d_iters = torch.zeros(B, dtype=torch.int32, device=dev)
-    gathered = torch.zeros(world * total * 3, dtype=torch.float64, device=dev) if world > 1 else None
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
     stream = torch.cuda.Stream(device=dev)  # non-default: the ABI treats a NULL stream as 'the handle's own'
     torch.cuda.set_stream(stream)
-
-    def device_step():
-        rc = L.pqp_solve_batch_device(solver._h, 0, B, total, N, KEEP, KEEP, d_n.data_ptr(), d_off.data_ptr(), d_ref.data_ptr(),
-                                      d_bounds.data_ptr(), d_x0.data_ptr(), d_end.data_ptr(), None, None,
-                                      d_out.data_ptr(), d_frenet.data_ptr(), d_status.data_ptr(),
-                                      d_iters.data_ptr(), C.c_void_p(stream.cuda_stream), None)
-        assert rc == 0, _lib.last_error()
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, d_frenet)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident arm ("value")
-    for _ in range(args.warmup):
-        device_step()
-    barrier()
+    w = GpuWorkload(args.config, rank, world, local_rank, torch)
     sampler = ClockSampler(local_rank)
+    # warm-up of both arms happens inside time_workload; the clock sampler covers the timed regions
     if rank == 0:
         sampler.start()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    barrier()
-    t_wall0 = time.perf_counter()
-    for k in range(args.steps):
-        flush.fill_(k & 0xFF)          # L2 flush between timed steps (outside the events)
-        ev[k][0].record(stream)
-        device_step()
-        ev[k][1].record(stream)
-    barrier()
-    wall = time.perf_counter() - t_wall0
-    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
-    status = d_status.cpu().numpy()
-    iters = d_iters.cpu().numpy()
-
-    # ---- end-to-end arm ("e2e"): host buffers through pqp_solve_batch
-    pin = lambda a: torch.from_numpy(np.frombuffer(np.ascontiguousarray(a).tobytes(), dtype=np.uint8).copy()).pin_memory()  # noqa: E731
-    h_ref, h_bounds = pin(batch["ref"]), pin(batch["bounds"])
-    h_x0, h_end, h_n = pin(batch["x0"]), pin(batch["end_heading"]), pin(batch["n_points"])
-    h_out = torch.zeros(total * STATE_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
-    h_frenet = torch.zeros(total * 3, dtype=torch.float64).pin_memory()
-    h_status = torch.zeros(B, dtype=torch.int32).pin_memory()
-    h_iters = torch.zeros(B, dtype=torch.int32).pin_memory()
-    stats = Stats()
-
-    def e2e_step():
-        rc = L.pqp_solve_batch(solver._h, 0, B, h_n.data_ptr(), h_ref.data_ptr(), h_bounds.data_ptr(),
-                               h_x0.data_ptr(), h_end.data_ptr(), None, None, h_out.data_ptr(),
-                               h_frenet.data_ptr(), h_status.data_ptr(), h_iters.data_ptr(), C.byref(stats))
-        assert rc == 0, _lib.last_error()
-
-    for _ in range(args.warmup):
-        e2e_step()
-    barrier()
-    e2e_ms = 0.0
-    h2d = d2h = 0
-    kern_ms = 0.0
-    for _ in range(args.steps):
-        flush.fill_(1)
-        torch.cuda.synchronize()
-        e2e_step()  # synchronous; its own CUDA events bracket H2D + kernel + D2H on the handle's stream
-        e2e_ms += stats.h2d_ms + stats.kernel_ms + stats.d2h_ms
-        kern_ms += stats.kernel_ms
-        h2d, d2h = stats.h2d_bytes, stats.d2h_bytes
-    barrier()
+    r = time_workload(w, torch, args.steps, args.warmup, flush, stream, barrier)
     clocks = sampler.stop() if rank == 0 else None
 
-    # max over ranks
-    t = torch.tensor([dev_ms, e2e_ms, wall * 1e3], dtype=torch.float64, device=dev)
+    # ---- reduce over ranks: step time = max over ranks; per-rank breakdown gathered as it is
+    t = torch.tensor([r["dev_ms"], r["e2e_ms"], r["wall_ms"]], dtype=torch.float64, device=dev)
+    per_rank = torch.tensor([r["solve_ms"] / args.steps, r["gather_ms"] / args.steps, float(r["iters"].mean()),
+                             float(r["iters"].max()), float(w.B), float(w.total)], dtype=torch.float64, device=dev)
+    all_ranks = per_rank.clone().unsqueeze(0)
+    paths_total = torch.tensor([w.B, int((r["status"] == 1).sum())], dtype=torch.int64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        all_ranks = torch.zeros(world, per_rank.numel(), dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(all_ranks.view(-1), per_rank)
+        dist.all_reduce(paths_total)
     dev_ms, e2e_ms, wall_ms = [float(x) for x in t.cpu()]
-    solved = torch.tensor([int((status == 1).sum())], device=dev)
-    if world > 1:
-        dist.all_reduce(solved)
+    all_ranks = all_ranks.cpu().numpy()
+    n_paths, n_solved = [int(x) for x in paths_total.cpu()]
+
+    control = None
+    if world > 1 and args.config in (2, 4):
+        # control run: every rank solves shard 0 (identical work) -- separates data-dependent tails from the collective
+        w0 = GpuWorkload(args.config, 0, 1, local_rank, torch)
+        w0.world, w0.gathered, w0.gather_rows = world, w.gathered, w.gather_rows
+        w0.d_frenet = w.d_frenet
+        rc_ = time_workload(w0, torch, max(3, args.steps // 4), 2, flush, stream, barrier, with_e2e=False)
+        tc = torch.tensor([rc_["dev_ms"] / max(3, args.steps // 4)], dtype=torch.float64, device=dev)
+        dist.all_reduce(tc, op=dist.ReduceOp.MAX)
+        control = {"what": "every rank solves rank 0's shard (identical work), all-gather as usual",
+                   "ms_per_step": float(tc.item())}
+        w0.close()
+
     if rank == 0:
-        total_solves = world * B * args.steps
-        value = total_solves / (dev_ms * 1e-3)
-        e2e_value = total_solves / (e2e_ms * 1e-3)
+        steps = args.steps
+        value = n_paths * steps / (dev_ms * 1e-3)
+        e2e_value = n_paths * steps / (e2e_ms * 1e-3)
         peak, peak_src = measured_peak_gbs()
-        avg_launch_s = (dev_ms / args.steps) * 1e-3   # the device-resident arm is exactly one launch of the solve kernel per step
-        achieved = B * io_bytes_per_solve(N) / avg_launch_s / 1e9
-        traffic = None
-        try:
-            with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-                traffic = json.load(f).get("dram_bytes_per_launch")
-        except Exception:
-            pass
+        mix = w.class_mix()
+        dominant = max(mix, key=lambda k: mix[k])
+        mean_n = w.total / w.B
+        launch_s = (r["solve_ms"] / steps) * 1e-3            # all of this rank's solve kernels of one step
+        alg_bytes = sum(io_bytes_per_solve(int(n)) for n in w.h_n)
+        achieved = alg_bytes / launch_s / 1e9
+        iters_mean = float(r["iters"].mean())
+        it_per_s = float(r["iters"].sum()) / launch_s
+        prof = profile_units()
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps,
+            "warmup": args.warmup, "ms_per_step": dev_ms / steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"BASELINE config 2: {B} paths x {N} stations per GPU, straight corridors, KP, "
-                                   f"OSQP defaults (eps 1e-3, adaptive rho every 25 it)",
-                       "paths_per_gpu": B, "n_points": N, "l2": "flushed between timed steps (256 MiB fill)",
-                       "multi_gpu": "independent shards + one NCCL all-gather of Frenet states per step" if world > 1 else "single GPU",
-                       "iters_per_solve_mean": float(iters.mean()), "iters_per_solve_max": int(iters.max())},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": e2e_ms / args.steps},
-            "gpu_launches": args.steps,
+            "config": workloads.describe(args.config, world),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"],
+                    "ms_per_step": e2e_ms / steps, "timer": "host wall clock (time.perf_counter) around pqp_solve_batch, max over ranks",
+                    "library_event_span_ms_per_step": r["e2e_span_ms"] / steps, "kernel_span_ms_per_step": r["e2e_kernel_ms"] / steps,
+                    "kernel_launches_per_step": r["e2e_launches"]},
+            "gpu_launches": r["launches_per_step"] * steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src,
-                         "kernel": "pqp_kp3_solve_kernel<17,6,4,17>", "algorithmic_bytes_per_launch": B * io_bytes_per_solve(N),
-                         "note": "state is SM-resident by design: compulsory HBM traffic is I/O only (SURVEY 8d); the kernel is "
-                                 "bound by dependent-issue latency at 8 warps/SM, see profiles/r01_phase_cycles.md"},
-            "clocks": clocks, "solved_fraction": int(solved.item()) / (world * B), "wall_ms_per_step": wall_ms / args.steps,
+                         "traffic": prof.get("dram_bytes_per_launch") if args.config == 2 else None,
+                         "traffic_source": prof.get("source", "profiles/traffic.json") + " (ncu --set full capture of the same kernel on the same batch; not measured in this run)" if args.config == 2 else None,
+                         "peak_source": peak_src, "kernel": dominant, "kernel_classes": mix,
+                         "algorithmic_bytes_per_launch": alg_bytes,
+                         "on_chip": {"what": "SURVEY 8d second figure: per-iteration working set W_iter = 944 N bytes streamed at the measured "
+                                             "ADMM iteration rate; the state is SM-resident, so this is ON-CHIP traffic-equivalent, NOT HBM",
+                                     "w_iter_bytes": int(w_iter_bytes(mean_n)), "iterations_per_s": it_per_s,
+                                     "equivalent_GBps": it_per_s * w_iter_bytes(mean_n) / 1e9,
+                                     "vs_hbm_peak": it_per_s * w_iter_bytes(mean_n) / 1e9 / peak},
+                         "units": prof.get("units"),
+                         "note": "state is SM-resident by design: compulsory HBM traffic is I/O only (SURVEY 8d); the kernel is bound by "
+                                 "dependent-issue latency and the shared-memory pipe, see profiles/"},
+            "clocks": clocks, "solved_fraction": n_solved / n_paths, "wall_ms_per_step": wall_ms / steps,
+            "iters_per_solve_mean": iters_mean, "iters_per_solve_max": int(r["iters"].max()),
+            "per_rank": {"solve_kernel_ms": [float(x) for x in all_ranks[:, 0]], "allgather_ms": [float(x) for x in all_ranks[:, 1]],
+                         "iters_mean": [float(x) for x in all_ranks[:, 2]], "iters_max": [float(x) for x in all_ranks[:, 3]],
+                         "paths": [int(x) for x in all_ranks[:, 4]], "stations": [int(x) for x in all_ranks[:, 5]],
+                         "note": "CUDA events on each rank's stream: solve kernels, then the NCCL all-gather (which also waits for the slowest rank)"},
         }
+        if control:
+            line["scaling_control"] = control
         if world == 1:
-            # CPU baseline, bounded sample: the oracle on all host cores, then on one core
-            from oracle import oracle
-            cores = cpu_threads()
-            threads = best_cpu_threads(oracle, oracle.default_params(), batch, cores)
-            sample = synth.slice_batch(batch, 0, B)
-            r = oracle.solve_batch(oracle.default_params(), 0, sample, threads=threads)
-            one = synth.slice_batch(batch, 0, 32)
-            r1 = oracle.solve_batch(oracle.default_params(), 0, one, threads=1)
-            line["cpu_baseline"] = {"value": len(sample["n_points"]) / r["seconds"], "unit": UNIT, "cores": threads,
-                                    "hardware_threads_visible": cores,
-                                    "kind": "port", "sample": f"the same {len(sample['n_points'])}-path batch once, fastest thread count of a probe",
-                                    "single_thread_value": 32 / r1["seconds"],
-                                    "reference_logged_ms_per_qp": "7.09-12.79 ms at N=188-244 (BASELINE.md)"}
-            line["extras"] = {"plan_chain": plan_chain_extra(local_rank)}
+            line["cpu_baseline"] = cpu_baseline(args)
+            if args.config == 2 and not args.no_extras:
+                line["extras"] = {"configs": extras_configs(torch, local_rank, flush, stream, barrier)}
         print(json.dumps(line), flush=True)
+    w.close()
     if world > 1:
         dist.destroy_process_group()
 
 
-def plan_chain_extra(device, paths=1024, n=200, reps=3):
-    """Context line (not the headline metric): one whole planner iteration per path -- clearance bounds on a
-    distance map -> KP QP -> collision-checked raw output (solveWithoutSmoothing, path_optimizer.cpp:87-117) --
-    for a config-3 shaped batch through pqp_plan_batch with host buffers."""
-    try:
-        from path_optimizer_b200 import planner
-        field = synth.disc_field_map()
-        b = synth.map_reference_paths(paths, n)
-        pl = planner.PathPlanner(device=device, max_batch=paths, max_total_points=paths * n)
-        pl.set_map(field)
-        pl.plan(b)
-        best = None
-        for _ in range(reps):
-            r = pl.plan(b)
-            ms = r["stats"].h2d_ms + r["stats"].kernel_ms + r["stats"].d2h_ms
-            best = ms if best is None else min(best, ms)
-        rb = pl.update_bounds(b)
-        out = {"workload": f"{paths} paths x {n} stations on a 220 m x 50 m, 0.2 m distance map with 300 discs: "
-                           "updateBounds -> KP QP -> raw tail with collision check",
-               "ms_per_call": best, "planner_iterations_per_sec": paths / (best * 1e-3),
-               "bounds_kernel_ms": rb["stats"].kernel_ms, "qp_solved": int(r["solved"].sum()),
-               "ok": int(r["ok"].sum()), "blocked_paths": int((rb["n_valid"] < n).sum()),
-               "iters_per_solve_mean": float(r["iters"].mean())}
-        pl.close()
-        return out
-    except Exception as e:  # context only: never fail the bench line on it
-        return {"error": str(e)[:200]}
+def cpu_baseline(args):
+    """Bounded CPU sample on rank 0: the oracle on the physical cores (3 repetitions), then on one core."""
+    from oracle import oracle
+    params = oracle.default_params()
+    n_log, n_phys = host_cores()
+    threads = args.cpu_threads or n_phys
+    batch, sample_text = cpu_sample(args.config, oracle, params)
+    B = len(batch["n_points"])
+    oracle.solve_batch(params, 0, synth.slice_batch(batch, 0, 8), threads=1)
+    oracle.solve_batch(params, 0, synth.slice_batch(batch, 0, min(B, 4 * threads)), threads=threads)
+    secs = [oracle.solve_batch(params, 0, batch, threads=threads)["seconds"] for _ in range(3)]
+    one = synth.slice_batch(batch, 0, 32)
+    r1 = oracle.solve_batch(params, 0, one, threads=1)
+    return {"value": B / statistics.median(secs), "unit": UNIT, "cores": threads, "hardware_threads_visible": n_log,
+            "physical_cores_visible": n_phys, "kind": "port",
+            "sample": sample_text.replace("per step", "per repetition") + "; 3 repetitions, median",
+            "best_value": B / min(secs), "single_thread_value": 32 / r1["seconds"],
+            "reference_logged_ms_per_qp": "7.09-12.79 ms at N=188-244 (BASELINE.md)"}
+
+
+def extras_configs(torch, local_rank, flush, stream, barrier):
+    """Configs 3, 4, 5 at their named per-GPU sizes, a few steps each (context for the default line)."""
+    out = {}
+    for cfg in (3, 4, 5):
+        try:
+            w = GpuWorkload(cfg, 0, 1, local_rank, torch)
+            r = time_workload(w, torch, 3, 2, flush, stream, barrier)
+            stations = float(r["iters"].astype(np.float64) @ w.h_n.astype(np.float64))
+            e = {"workload": workloads.CONFIGS[cfg]["text"], "paths": w.B, "stations": w.total,
+                 "solves_per_sec": w.B * 3 / (r["dev_ms"] * 1e-3), "ms_per_step": r["dev_ms"] / 3,
+                 "e2e_solves_per_sec": w.B * 3 / (r["e2e_ms"] * 1e-3), "e2e_ms_per_step": r["e2e_ms"] / 3,
+                 "iters_per_solve_mean": float(r["iters"].mean()), "iters_per_solve_max": int(r["iters"].max()),
+                 "solved_fraction": float((r["status"] == 1).mean()),
+                 "ns_per_station_iteration": (r["solve_ms"] / 3) * 1e6 / stations,
+                 "kernel_classes": w.class_mix(), "kernel_launches_per_step": r["launches_per_step"]}
+            if cfg == 3:
+                e["plan_chain"] = plan_chain(w, local_rank)
+            out[str(cfg)] = e
+            w.close()
+            del w
+            torch.cuda.empty_cache()
+        except Exception as ex:  # context only: never fail the bench line on it
+            out[str(cfg)] = {"error": repr(ex)[:300]}
+    return out
+
+
+def plan_chain(w, device, reps=3):
+    """Config 3 through the chained planner iteration (pqp_plan_batch: clearance bounds on the distance map ->
+    KP QP -> collision-checked raw output = solveWithoutSmoothing, path_optimizer.cpp:87-117), host buffers."""
+    from path_optimizer_b200 import planner
+    pl = planner.PathPlanner(device=device, max_batch=w.B, max_total_points=w.total)
+    pl.set_map(w.field)
+    b = dict(w.batch)
+    pl.plan(b)
+    best = None
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        r = pl.plan(b)
+        ms = (time.perf_counter() - t0) * 1e3
+        best = ms if best is None else min(best, ms)
+    out = {"what": "updateBounds -> KP QP -> raw tail with collision check, host buffers, host wall clock, best of 3",
+           "ms_per_call": best, "planner_iterations_per_sec": w.B / (best * 1e-3),
+           "library_event_span_ms": r["stats"].h2d_ms + r["stats"].kernel_ms + r["stats"].d2h_ms,
+           "qp_solved": int(r["solved"].sum()), "ok": int(r["ok"].sum())}
+    pl.close()
+    return out
 
 
 def main():
@@ -383,7 +599,11 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--config", type=int, choices=[2, 3, 4, 5], default=2)
+    ap.add_argument("--cpu-threads", type=int, default=0, help="CPU arm thread count (default: physical cores)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the config 3/4/5 context measurements of the default run")
     args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

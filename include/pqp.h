@@ -215,7 +215,9 @@ int pqp_solve_batch(pqp_handle *h, int formulation, int batch,
  * exclusive prefix sum of n_points with offsets[batch] = sum.  The host cannot see the device-side
  * n_points, so the caller states upper bounds used to size shared memory: `max_n_points` >= every
  * n_points[b], and `min_keep` <= keep_control_steps <= `max_keep` for every path (pass 0, 0 for
- * "unknown": 1..4 is assumed).  A path that exceeds them reports PQP_INVALID_PROBLEM.  Asynchronous on `stream`
+ * "unknown": 1..4 is assumed).  ONE kernel class is chosen that takes every (n_points, keep) inside those bounds
+ * (PQP_ERR_UNSUPPORTED when no single class does: tighten them, or use pqp_solve_batch_device_classes); only a path
+ * that exceeds the stated bounds reports PQP_INVALID_PROBLEM.  Asynchronous on `stream`
  * (a cudaStream_t, or NULL for the handle's own stream); no host synchronisation is done
  * unless `stats` is non-NULL.  No reference counterpart (the reference has no device). */
 int pqp_solve_batch_device(pqp_handle *h, int formulation, int batch, int total_points,
@@ -234,15 +236,52 @@ int pqp_solve_batch_device(pqp_handle *h, int formulation, int batch, int total_
                            void *stream,
                            pqp_stats *stats);
 
+/* Device-resident solve of a MIXED-LENGTH batch: as pqp_solve_batch_device, but the caller passes HOST copies of the
+ * per-path station counts (`h_n_points`, equal to the device-side d_n_points) and keep_control_steps (`h_keep`, from
+ * pqp_keep_control_steps), so that every path runs on the kernel class of its own (length, keep) -- what
+ * pqp_solve_batch does for host buffers -- instead of one class sized for the longest path.  The classes are launched
+ * on internal lanes forked from / joined into `stream`, the class of the longest paths first (BASELINE config 5:
+ * "length-bucketed").  The class plan is cached while (h_n_points, h_keep) stay the same; when they change the call
+ * synchronises `stream` once before re-planning.  No reference counterpart. */
+int pqp_solve_batch_device_classes(pqp_handle *h, int formulation, int batch, int total_points,
+                                   const int32_t *h_n_points, const int32_t *h_keep,
+                                   const int32_t *d_n_points, const int32_t *d_offsets,
+                                   const pqp_state *d_ref,
+                                   const pqp_station_bounds *d_bounds,
+                                   const double *d_x0,
+                                   const double *d_end_heading,
+                                   const double *d_max_k,
+                                   const double *d_max_kp,
+                                   pqp_state *d_out_states,
+                                   double *d_out_frenet,
+                                   int32_t *d_status,
+                                   int32_t *d_iters,
+                                   void *stream,
+                                   pqp_stats *stats);
+
 /* Last error text for this thread (CUDA error strings etc.); never NULL. */
 const char *pqp_last_error(void);
 
 /* "pqp <abi> sm_100a <build info>" */
 const char *pqp_version(void);
 
-/* Largest n_points the kernels can take on this device for a formulation (shared-memory
- * bound; one path must fit one SM's shared memory). */
+/* Largest n_points a path may have on this device (one path must fit one SM's shared memory; longer paths report
+ * PQP_INVALID_PROBLEM).  The limit depends on keep_control_steps: pqp_max_points_keep gives it for one value
+ * (1..10; e.g. 408 at keep = 3 on the thread-per-station classes, then the one-warp kernel up to 414), pqp_max_points
+ * the minimum over keep = 1..10, i.e. a length every spacing can take.  KP only (0 otherwise: K / KPC paths are
+ * bounded by the generic kernel's shared memory, which depends on the assembled band). */
 int pqp_max_points(pqp_handle *h, int formulation);
+int pqp_max_points_keep(pqp_handle *h, int formulation, int keep);
+
+/* Diagnostics (no device needed): which kernel class the library selects.  pqp_class_info: for ONE path of
+ * (n_points, keep) as pqp_solve_batch / pqp_solve_batch_device_classes / pqp_plan_batch choose it -- index into the
+ * class table (order of preference), CTA size and dynamic shared memory; PQP_ERR_UNSUPPORTED when no class takes the
+ * path (it would report PQP_INVALID_PROBLEM).  pqp_device_class_info: the single class pqp_solve_batch_device picks for
+ * the caller's bounds.  smem_optin = the device's opt-in shared memory per block (0: B200's 232448). */
+int pqp_class_info(int n_points, int keep, int smem_optin, int *variant, int *threads, int64_t *smem_bytes);
+const char *pqp_class_name(int variant);   /* kernel name of a class-table index, as profilers print it ("" if out of range) */
+int pqp_device_class_info(int max_n_points, int min_keep, int max_keep, int smem_optin, int *variant, int *threads,
+                          int64_t *smem_bytes);
 
 #ifdef __cplusplus
 } /* extern "C" */

@@ -4,6 +4,8 @@
  * pthread batch loop used as the CPU baseline.  PARITY UNPINNED -- see pqp_oracle.h.
  */
 #include "pqp_oracle.h"
+#define PQP_ORACLE_ARENA_IMPL   /* this file keeps the C library allocator; it only drives the arena */
+#include "pqp_oracle_arena.h"
 
 #include <math.h>
 #include <pthread.h>
@@ -44,11 +46,18 @@ typedef struct {
     pqp_state *out;
     double *frenet;
     int32_t *status, *iters;
+    int *next;   /* shared work counter */
 } job;
 
+/* Paths are handed out one at a time from a shared counter (iteration counts differ by 2x between paths, so a
+ * static split leaves threads idle), and every thread solves out of its own scratch arena (pqp_oracle_arena.h). */
 static void *worker(void *arg) {
     job *j = (job *)arg;
-    for (int b = j->begin; b < j->end; ++b) {
+    oa_begin((size_t)64 << 20);
+    for (;;) {
+        const int b = __atomic_fetch_add(j->next, 1, __ATOMIC_RELAXED);
+        if (b >= j->end) break;
+        oa_reset();
         const int off = j->offsets[b], n = j->n_points[b];
         oqp_info info;
         int st = oracle_solve_path(j->prm, j->formulation, n, j->ref + off, j->bounds + off,
@@ -59,6 +68,7 @@ static void *worker(void *arg) {
         if (j->status) j->status[b] = st;
         if (j->iters) j->iters[b] = info.iters;
     }
+    oa_end();
     return NULL;
 }
 
@@ -77,6 +87,7 @@ double oracle_solve_batch(const pqp_params *prm, int formulation, int batch, con
         offsets[b + 1] = offsets[b] + n_points[b];
         ch_offsets[b + 1] = ch_offsets[b] + (n_points[b] + 4 - 2) / 4; /* KPC: keep = 4 */
     }
+    int next = 0;
     struct timespec t0, t1;
     clock_gettime(CLOCK_MONOTONIC, &t0);
     pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t) * (size_t)threads);
@@ -84,8 +95,9 @@ double oracle_solve_batch(const pqp_params *prm, int formulation, int batch, con
     for (int t = 0; t < threads; ++t) {
         job *j = &jobs[t];
         j->prm = prm; j->formulation = formulation;
-        j->begin = (int)((long long)batch * t / threads);
-        j->end = (int)((long long)batch * (t + 1) / threads);
+        j->begin = 0;
+        j->end = batch;
+        j->next = &next;
         j->n_points = n_points; j->offsets = offsets; j->ch_offsets = ch_offsets;
         j->ref = ref; j->bounds = bounds; j->x0 = x0; j->end_heading = end_heading;
         j->max_k = max_k; j->max_kp = max_kp; j->out = out; j->frenet = frenet;

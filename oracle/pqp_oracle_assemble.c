@@ -13,6 +13,7 @@
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
+#include "pqp_oracle_arena.h"   /* malloc / calloc / free of this file go through the per-thread arena when it is on */
 
 #define OQP_INFTY 1e30 /* OsqpEigen::INFTY == OSQP_INFTY [upstream OSQP 0.6.x] */
 

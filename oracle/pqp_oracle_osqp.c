@@ -28,6 +28,7 @@
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
+#include "pqp_oracle_arena.h"   /* malloc / calloc / free of this file go through the per-thread arena when it is on */
 
 #define OSQP_INFTY 1e30
 #define RHO_MIN 1e-06
@@ -362,30 +363,49 @@ static void ldl_solve(ldl *F, const double *b, double *sol) {
     for (int k = 0; k < nn; ++k) sol[S->perm[k]] = w[k];
 }
 
-/* Symbolic cache.  Paths of one batch share (formulation, N, keep) and hence the sparsity pattern;
- * the analysis (ordering + elimination tree) is immutable once built, so one copy is shared by all
- * threads.  (OSQP redoes AMD + symbolic factorisation in every osqp_setup; sharing it only makes
- * the CPU baseline faster, i.e. errs on the generous side.)  Entries are never freed. */
+/* Symbolic cache.  Paths of one batch that share (formulation, N, keep, zero pattern) share the sparsity
+ * pattern; the analysis (ordering + elimination tree) is immutable once built, so one copy is shared by all
+ * threads.  (OSQP redoes AMD + symbolic factorisation in every osqp_setup; sharing it only makes the CPU
+ * baseline faster, i.e. errs on the generous side.)  A mixed-length batch (BASELINE config 5: 351 different
+ * lengths) has one pattern per length: the cache holds 1024 of them, and an analysis is BUILT OUTSIDE the
+ * lock so that threads working on different lengths do not wait for each other.  Entries are never freed. */
 #include <pthread.h>
-#define SYM_CACHE 16
+#define SYM_CACHE 1024
 static symbolic *g_sym[SYM_CACHE];
-static int g_sym_n = 0;
+static int g_sym_n = 0, g_sym_next = 0;
 static pthread_mutex_t g_sym_mu = PTHREAD_MUTEX_INITIALIZER;
 static __thread const symbolic *tls_sym = NULL;
+
+static const symbolic *symbolic_lookup_locked(const oqp_problem *qp) {
+    for (int k = 0; k < g_sym_n; ++k)
+        if (symbolic_matches(g_sym[k], qp)) return g_sym[k];
+    return NULL;
+}
 
 static const symbolic *symbolic_get(const oqp_problem *qp) {
     if (symbolic_matches(tls_sym, qp)) return tls_sym;
     pthread_mutex_lock(&g_sym_mu);
-    const symbolic *found = NULL;
-    for (int k = 0; k < g_sym_n; ++k)
-        if (symbolic_matches(g_sym[k], qp)) { found = g_sym[k]; break; }
-    if (!found) {
-        symbolic *S = symbolic_build(qp);
-        if (g_sym_n < SYM_CACHE) g_sym[g_sym_n++] = S;
-        else { g_sym[g_sym_n - 1] = S; } /* cache full: replace the last slot (old entry leaks; bounded use) */
-        found = S;
-    }
+    const symbolic *found = symbolic_lookup_locked(qp);
     pthread_mutex_unlock(&g_sym_mu);
+    if (!found) {
+        const int arena_state = oa_suspend();   /* the analysis outlives this solve and is shared by all threads */
+        symbolic *S = symbolic_build(qp);
+        oa_resume(arena_state);
+        pthread_mutex_lock(&g_sym_mu);
+        found = symbolic_lookup_locked(qp);     /* another thread may have built the same pattern meanwhile */
+        if (!found) {
+            if (g_sym_n < SYM_CACHE) g_sym[g_sym_n++] = S;
+            else { g_sym[g_sym_next] = S; g_sym_next = (g_sym_next + 1) % SYM_CACHE; } /* full: overwrite round robin (the old entry leaks; bounded use) */
+            found = S;
+            S = NULL;
+        }
+        pthread_mutex_unlock(&g_sym_mu);
+        if (S) {
+            const int st = oa_suspend();
+            symbolic_free(S);
+            oa_resume(st);
+        }
+    }
     tls_sym = found;
     return found;
 }

@@ -29,14 +29,14 @@ namespace {
 // keep_control_steps <= 4 (station spacing >= 0.24 m) maps onto one of the Kp3 / Kp2 instantiations; anything else
 // runs on the one-warp generic kernel (last).
 typedef PqpVariant Variant;
-constexpr int kNumVariants = 14;
+constexpr int kNumVariants = 15;
 struct VariantTable {
     Variant v[kNumVariants];
     VariantTable() {
         int k = 0;
         pqp_variant_k3_17_6_4_17(&v[k++]); pqp_variant_k3_23_7_4_17(&v[k++]); pqp_variant_k3_27_7_4_17(&v[k++]);
         pqp_variant_k3_17_6_8_34(&v[k++]); pqp_variant_k3_23_7_8_34(&v[k++]); pqp_variant_k3_27_7_8_34(&v[k++]);
-        pqp_variant_k3_37_7_8_17(&v[k++]);
+        pqp_variant_k3_37_7_8_17(&v[k++]); pqp_variant_k3_37_7_13_34(&v[k++]);
         pqp_variant_k2_17_6(&v[k++]); pqp_variant_k2_10_7(&v[k++]); pqp_variant_k2_17_7(&v[k++]);
         pqp_variant_k2_27_7(&v[k++]); pqp_variant_k2_37_7(&v[k++]); pqp_variant_k2_49_7(&v[k++]);
         pqp_variant_k1_generic(&v[k++]);
@@ -62,6 +62,55 @@ int pick_variant(int n, int keep) {
     return -1;
 }
 
+// Kernel class and shared-memory need of ONE path of n stations at keep_control_steps = keep, exactly as every entry
+// point that sees the lengths on the host selects it: the first class that takes (n, keep); when that class needs more
+// shared memory than the device offers, the one-warp kernel if the path fits there; else the smallest launch of the
+// one-warp kernel, which reports PQP_INVALID_PROBLEM for the path.  Returns false in that last case.
+bool class_for(const pqp_handle *h, int n, int keep, int *v_out, size_t *need_out) {
+    int v = kNumVariants - 1;
+    if (n >= 2) {
+        const int pv = pick_variant(n, keep);
+        if (pv >= 0) v = pv;
+    }
+    const int ke = std::min(std::max(keep, 1), 10), ne = std::max(n, 2);
+    size_t need = kVariants[v].smem(ne, ke);
+    bool ok = n >= 2 && keep >= 1 && keep <= 10;
+    if (need > (size_t)h->smem_optin) {
+        v = kNumVariants - 1;
+        need = (keep <= 10) ? kVariants[v].smem(ne, ke) : (size_t)h->smem_optin + 1;
+        if (need > (size_t)h->smem_optin) { need = kVariants[v].smem(2, 1); ok = false; }
+    }
+    *v_out = v;
+    *need_out = need;
+    return ok;
+}
+
+// One class for a whole device-resident batch of which the host only knows bounds: it must take EVERY (n, keep) with
+// 2 <= n <= nmax, k_lo <= keep <= k_hi (neither fits() nor the shared-memory need is monotone in n: the separator and
+// interior counts change with it), and is launched with the largest shared-memory need over that range.
+bool device_class(pqp_handle *h, int nmax, int k_lo, int k_hi, int *v_out, size_t *smem_out) {
+    if (h->dc_nmax == nmax && h->dc_klo == k_lo && h->dc_khi == k_hi && h->dc_skip == (int)skip_mask()) {
+        *v_out = h->dc_v; *smem_out = h->dc_smem;
+        return h->dc_v >= 0;
+    }
+    int v = -1;
+    size_t smem = 0;
+    for (int cand = 0; cand < kNumVariants && v < 0; ++cand) {
+        if ((skip_mask() >> cand) & 1u) continue;
+        bool all = true;
+        size_t need = 0;
+        for (int k = k_lo; k <= k_hi && all; ++k)
+            for (int n = 2; n <= nmax && all; ++n) {
+                if (!kVariants[cand].fits(n, k)) all = false;
+                else need = std::max(need, kVariants[cand].smem(n, k));
+            }
+        if (all && need <= (size_t)h->smem_optin) { v = cand; smem = need; }
+    }
+    h->dc_nmax = nmax; h->dc_klo = k_lo; h->dc_khi = k_hi; h->dc_skip = (int)skip_mask(); h->dc_v = v; h->dc_smem = smem;
+    *v_out = v; *smem_out = smem;
+    return v >= 0;
+}
+
 }  // namespace
 
 
@@ -71,44 +120,73 @@ static int launch_variant(pqp_handle *h, int v, const pqp::BatchView &bv, int co
 }
 
 int pqp_launch_kp_classes(pqp_handle *h, const pqp::BatchView &bv, int batch, const int32_t *n, const int32_t *off,
-                          const pqp_state *ref, cudaStream_t st, int *launches) {
-    std::vector<int> cls((size_t)batch);
-    size_t smem_v[kNumVariants] = {0};
-    int count_v[kNumVariants] = {0}, start_v[kNumVariants + 1];
-    for (int b = 0; b < batch; ++b) {
-        int v = kNumVariants - 1, keep = 1;
-        if (n[b] >= 2) {
-            keep = pqp_keep_control_steps(PQP_FORM_KP, ref + off[b], n[b]);
-            const int pv = pick_variant(n[b], keep);
-            if (pv >= 0) v = pv;
+                          const pqp_state *ref, const int32_t *keep_in, cudaStream_t st, int *launches) {
+    static_assert(kNumVariants <= PQP_MAX_VARIANTS, "class plan arrays");
+    // keep_control_steps per path
+    std::vector<int32_t> keepv((size_t)batch);
+    for (int b = 0; b < batch; ++b)
+        keepv[b] = keep_in ? keep_in[b] : (n[b] >= 2 ? pqp_keep_control_steps(PQP_FORM_KP, ref + off[b], n[b]) : 1);
+    // The plan (class per path, longest-first order inside a class) only depends on (n, keep): a caller that solves
+    // batches of the same shape back to back reuses it, and the order array already on the device with it.
+    pqp_handle::ClassPlan &pl = h->plan;
+    const bool same = pl.valid && pl.skip == (int)skip_mask() && pl.n.size() == (size_t)batch &&
+                      std::equal(pl.n.begin(), pl.n.end(), n) && pl.keep == keepv;
+    if (!same) {
+        // the pinned order array may still be the source of an earlier asynchronous upload
+        PQP_CUDA(cudaStreamSynchronize(st));
+        if (pl.stream && pl.stream != st) PQP_CUDA(cudaStreamSynchronize(pl.stream));
+        pl.valid = false;
+        std::vector<int> cls((size_t)batch);
+        for (int v = 0; v < kNumVariants; ++v) { pl.count_v[v] = 0; pl.smem_v[v] = 0; }
+        for (int b = 0; b < batch; ++b) {
+            int v;
+            size_t need;
+            class_for(h, n[b], keepv[b], &v, &need);
+            cls[b] = v;
+            pl.smem_v[v] = std::max(pl.smem_v[v], need);
+            pl.count_v[v]++;
         }
-        const int ke = std::min(std::max(keep, 1), 10), ne = std::max((int)n[b], 2);
-        size_t need = kVariants[v].smem(ne, ke);
-        if (need > (size_t)h->smem_optin) {
-            // too long for this class: the one-warp kernel takes it if it fits there, else it reports PQP_INVALID_PROBLEM
-            v = kNumVariants - 1;
-            need = (ke <= 10) ? kVariants[v].smem(ne, ke) : (size_t)h->smem_optin + 1;
-            if (need > (size_t)h->smem_optin) need = kVariants[v].smem(2, 1);
-        }
-        cls[b] = v;
-        smem_v[v] = std::max(smem_v[v], need);
-        count_v[v]++;
+        pl.start_v[0] = 0;
+        for (int v = 0; v < kNumVariants; ++v) pl.start_v[v + 1] = pl.start_v[v] + pl.count_v[v];
+        int fill[kNumVariants];
+        for (int v = 0; v < kNumVariants; ++v) fill[v] = pl.start_v[v];
+        for (int b = 0; b < batch; ++b) h->h_order[fill[cls[b]]++] = b;
+        for (int v = 0; v < kNumVariants; ++v)
+            std::stable_sort(h->h_order + pl.start_v[v], h->h_order + pl.start_v[v + 1], [&](int a, int b) { return n[a] > n[b]; });
+        PQP_CUDA(cudaMemcpyAsync(h->d_order, h->h_order, (size_t)batch * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        pl.n.assign(n, n + batch);
+        pl.keep = keepv;
+        pl.skip = (int)skip_mask();
+        pl.stream = st;
+        pl.valid = true;
     }
-    start_v[0] = 0;
-    for (int v = 0; v < kNumVariants; ++v) start_v[v + 1] = start_v[v] + count_v[v];
-    int fill[kNumVariants];
-    for (int v = 0; v < kNumVariants; ++v) fill[v] = start_v[v];
-    for (int b = 0; b < batch; ++b) h->h_order[fill[cls[b]]++] = b;
-    for (int v = 0; v < kNumVariants; ++v)
-        std::stable_sort(h->h_order + start_v[v], h->h_order + start_v[v + 1], [&](int a, int b) { return n[a] > n[b]; });
-    PQP_CUDA(cudaMemcpyAsync(h->d_order, h->h_order, (size_t)batch * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-    for (int v = 0; v < kNumVariants; ++v) {
+    const int *count_v = pl.count_v, *start_v = pl.start_v;
+    const size_t *smem_v = pl.smem_v;
+    // One launch per class.  A mixed batch has several: they go out on the handle's class lanes (forked from and joined
+    // back into `st`), the class of the longest paths first, so that the CTAs of the next class fill the SMs the tail
+    // of the previous one leaves idle instead of waiting for its last path.
+    int n_cls = 0;
+    for (int v = 0; v < kNumVariants; ++v) n_cls += count_v[v] > 0;
+    const bool fork = n_cls > 1;
+    if (fork) PQP_CUDA(cudaEventRecord(h->ev_fork, st));
+    int lane = 0, rc = PQP_OK;
+    for (int v = kNumVariants - 1; v >= 0 && rc == PQP_OK; --v) {
         if (!count_v[v]) continue;
-        int rc = launch_variant(h, v, bv, count_v[v], h->d_order + start_v[v], smem_v[v], st);
-        if (rc != PQP_OK) return rc;
-        if (launches) ++*launches;
+        cudaStream_t cs = st;
+        if (fork) {
+            cs = h->cls_stream[lane % PQP_CLASS_LANES];
+            if (lane < PQP_CLASS_LANES) PQP_CUDA(cudaStreamWaitEvent(cs, h->ev_fork, 0));
+            ++lane;
+        }
+        rc = launch_variant(h, v, bv, count_v[v], h->d_order + start_v[v], smem_v[v], cs);
+        if (rc == PQP_OK && launches) ++*launches;
     }
-    return PQP_OK;
+    if (fork)   // join every lane that was used, also after a failed launch: `st` must not run ahead of them
+        for (int k = 0; k < std::min(lane, PQP_CLASS_LANES); ++k) {
+            PQP_CUDA(cudaEventRecord(h->ev_cls[k], h->cls_stream[k]));
+            PQP_CUDA(cudaStreamWaitEvent(st, h->ev_cls[k], 0));
+        }
+    return rc;
 }
 
 extern "C" {
@@ -200,6 +278,9 @@ void pqp_destroy(pqp_handle *h) {
     if (h->env && h->env_free) h->env_free(h->env);
     for (auto &e : h->ev) if (e) cudaEventDestroy(e);
     for (auto &e : h->ev_chunk) if (e) cudaEventDestroy(e);
+    for (auto &e : h->ev_cls) if (e) cudaEventDestroy(e);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    for (auto &q : h->cls_stream) if (q) cudaStreamDestroy(q);
     if (h->stream) cudaStreamDestroy(h->stream);
     if (h->stream2) cudaStreamDestroy(h->stream2);
     delete h;
@@ -251,6 +332,9 @@ int pqp_create(pqp_handle **out, const pqp_params *params, int device, int max_b
     PQP_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     PQP_TRY(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
     for (auto &e : h->ev_chunk) PQP_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (auto &q : h->cls_stream) PQP_TRY(cudaStreamCreateWithFlags(&q, cudaStreamNonBlocking));
+    for (auto &e : h->ev_cls) PQP_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    PQP_TRY(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
     for (auto &e : h->ev) PQP_TRY(cudaEventCreate(&e));
     const size_t B = (size_t)max_batch, T = (size_t)max_total_points;
     PQP_TRY(cudaMalloc(&h->d_n, B * sizeof(int32_t)));
@@ -273,14 +357,58 @@ int pqp_create(pqp_handle **out, const pqp_params *params, int device, int max_b
     return PQP_OK;
 }
 
-int pqp_max_points(pqp_handle *h, int formulation) {
-    if (!h || formulation != PQP_FORM_KP) return 0;
+const char *pqp_class_name(int variant) {
+    return (variant >= 0 && variant < kNumVariants) ? kVariants[variant].name : "";
+}
+
+int pqp_class_info(int n_points, int keep, int smem_optin, int *variant, int *threads, int64_t *smem_bytes) {
+    pqp_handle fake;
+    fake.smem_optin = smem_optin > 0 ? smem_optin : 232448;
+    int v;
+    size_t need;
+    const bool ok = class_for(&fake, n_points, keep, &v, &need);
+    if (variant) *variant = v;
+    if (threads) *threads = kVariants[v].threads;
+    if (smem_bytes) *smem_bytes = (int64_t)need;
+    return ok ? PQP_OK : PQP_ERR_UNSUPPORTED;
+}
+
+int pqp_device_class_info(int max_n_points, int min_keep, int max_keep, int smem_optin, int *variant, int *threads,
+                          int64_t *smem_bytes) {
+    pqp_handle fake;
+    fake.smem_optin = smem_optin > 0 ? smem_optin : 232448;
+    int v = -1;
+    size_t need = 0;
+    const bool ok = device_class(&fake, max_n_points, min_keep, max_keep, &v, &need);
+    if (variant) *variant = v;
+    if (threads) *threads = ok ? kVariants[v].threads : 0;
+    if (smem_bytes) *smem_bytes = (int64_t)need;
+    if (!ok) return PQP_ERR_UNSUPPORTED;
+    // every (n, keep) inside the bounds must pass the checks the kernel itself makes
+    for (int k = min_keep; k <= max_keep; ++k)
+        for (int n = 2; n <= max_n_points; ++n)
+            if (!kVariants[v].fits(n, k) || kVariants[v].smem(n, k) > need) return PQP_ERR_ARG;
+    return PQP_OK;
+}
+
+int pqp_max_points_keep(pqp_handle *h, int formulation, int keep) {
+    if (!h || formulation != PQP_FORM_KP || keep < 1 || keep > 10) return 0;
+    // mirrors the per-path selection of pqp_solve_batch (class_for): preferred class, else the one-warp kernel
     int best = 0;
     for (int n = 2; n <= 4096; ++n) {
-        // keep = 4 (ds = 0.3 m stations give 3, the reference's dense 0.25 m spacing gives 4)
-        const int v = pick_variant(n, 4);
-        if (v >= 0 && kVariants[v].smem(n, 4) <= (size_t)h->smem_optin) best = n;
+        int v;
+        size_t need;
+        if (class_for(h, n, keep, &v, &need)) best = n;
         else break;
+    }
+    return best;
+}
+
+int pqp_max_points(pqp_handle *h, int formulation) {
+    int best = 0;
+    for (int keep = 1; keep <= 10; ++keep) {
+        const int m = pqp_max_points_keep(h, formulation, keep);
+        best = (keep == 1) ? m : std::min(best, m);
     }
     return best;
 }
@@ -333,17 +461,9 @@ int pqp_solve_batch_device(pqp_handle *h, int formulation, int batch, int total_
     const int k_lo = (min_keep >= 1) ? std::min(min_keep, k_hi) : 1;
     int v = -1;
     size_t smem = 0;
-    for (int cand = 0; cand < kNumVariants && v < 0; ++cand) {
-        bool all = !((skip_mask() >> cand) & 1u);
-        size_t need = 0;
-        for (int k = k_lo; k <= k_hi; ++k) {
-            if (!kVariants[cand].fits(nmax, k)) { all = false; break; }
-            need = std::max(need, kVariants[cand].smem(nmax, k));
-        }
-        if (all && need <= (size_t)h->smem_optin) { v = cand; smem = need; }
-    }
-    if (v < 0) {
-        set_err("no kernel shape class fits (max_n_points, max_keep)");
+    if (!device_class(h, nmax, k_lo, k_hi, &v, &smem)) {
+        set_err("no single kernel shape class takes every (n_points <= max_n_points, min_keep..max_keep): "
+                "tighten the bounds or use pqp_solve_batch_device_classes");
         return PQP_ERR_UNSUPPORTED;
     }
     if (stats) PQP_CUDA(cudaEventRecord(h->ev[0], st));
@@ -355,6 +475,48 @@ int pqp_solve_batch_device(pqp_handle *h, int formulation, int batch, int total_
         PQP_CUDA(cudaEventSynchronize(h->ev[1]));
         PQP_CUDA(cudaEventElapsedTime(&stats->kernel_ms, h->ev[0], h->ev[1]));
         stats->kernel_launches = 1;
+    }
+    return PQP_OK;
+}
+
+int pqp_solve_batch_device_classes(pqp_handle *h, int formulation, int batch, int total_points,
+                                   const int32_t *h_n_points, const int32_t *h_keep,
+                                   const int32_t *d_n_points, const int32_t *d_offsets, const pqp_state *d_ref,
+                                   const pqp_station_bounds *d_bounds, const double *d_x0, const double *d_end_heading,
+                                   const double *d_max_k, const double *d_max_kp, pqp_state *d_out_states,
+                                   double *d_out_frenet, int32_t *d_status, int32_t *d_iters, void *stream,
+                                   pqp_stats *stats) {
+    (void)d_max_k; (void)d_max_kp;
+    if (!h || batch < 0 || !h_n_points || !h_keep || !d_n_points || !d_offsets || !d_ref || !d_bounds || !d_x0 ||
+        !d_end_heading || !d_out_states || !d_status) {
+        set_err("pqp_solve_batch_device_classes: bad argument");
+        return PQP_ERR_ARG;
+    }
+    if (formulation != PQP_FORM_KP) {
+        set_err("K / KPC are assembled on the host: use pqp_solve_batch (host buffers) for them");
+        return PQP_ERR_UNSUPPORTED;
+    }
+    if (batch == 0) return PQP_OK;
+    if (batch > h->max_batch || total_points > h->max_total) {
+        set_err("batch / total_points exceed what the handle was created for (workspace size)");
+        return PQP_ERR_CAPACITY;
+    }
+    PQP_CUDA(cudaSetDevice(h->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    pqp::BatchView bv;
+    bv.batch = batch; bv.n_points = d_n_points; bv.offsets = d_offsets; bv.ref = d_ref; bv.bounds = d_bounds;
+    bv.x0 = d_x0; bv.end_heading = d_end_heading; bv.out_states = d_out_states; bv.out_frenet = d_out_frenet;
+    bv.status = d_status; bv.iters = d_iters; bv.workspace = h->d_ws; bv.debug = nullptr;
+    if (stats) PQP_CUDA(cudaEventRecord(h->ev[0], st));
+    int launches = 0;
+    int rc = pqp_launch_kp_classes(h, bv, batch, h_n_points, nullptr, nullptr, h_keep, st, &launches);
+    if (rc != PQP_OK) return rc;
+    if (stats) {
+        memset(stats, 0, sizeof(*stats));
+        PQP_CUDA(cudaEventRecord(h->ev[1], st));
+        PQP_CUDA(cudaEventSynchronize(h->ev[1]));
+        PQP_CUDA(cudaEventElapsedTime(&stats->kernel_ms, h->ev[0], h->ev[1]));
+        stats->kernel_launches = launches;
     }
     return PQP_OK;
 }
@@ -525,20 +687,10 @@ int pqp_solve_batch(pqp_handle *h, int formulation, int batch, const int32_t *n_
         total += n;
         if (total > h->max_total) { set_err("station count exceeds the handle's max_total_points"); return PQP_ERR_CAPACITY; }
         h->h_off[b + 1] = (int32_t)total;
-        int v = kNumVariants - 1, keep = 1;
-        if (n >= 2) {
-            keep = pqp_keep_control_steps(formulation, ref + h->h_off[b], n);
-            const int pv = pick_variant(n, keep);
-            if (pv >= 0) v = pv;
-        }
-        const int ke = std::min(std::max(keep, 1), 10), ne = std::max(n, 2);
-        size_t need = kVariants[v].smem(ne, ke);
-        if (need > (size_t)h->smem_optin) {
-            // too long for this class: the one-warp kernel takes it if it fits there, else it reports PQP_INVALID_PROBLEM
-            v = kNumVariants - 1;
-            need = (ke <= 10) ? kVariants[v].smem(ne, ke) : (size_t)h->smem_optin + 1;
-            if (need > (size_t)h->smem_optin) need = kVariants[v].smem(2, 1);
-        }
+        const int keep = (n >= 2) ? pqp_keep_control_steps(formulation, ref + h->h_off[b], n) : 1;
+        int v;
+        size_t need;
+        class_for(h, n, keep, &v, &need);
         cls[b] = v;
         need_b[b] = need;
     }
@@ -555,6 +707,7 @@ int pqp_solve_batch(pqp_handle *h, int formulation, int batch, const int32_t *n_
         while (b < batch && h->h_off[b] < target) ++b;
         cb[k] = (k == n_chunks) ? batch : std::max(b, cb[k - 1]);
     }
+    h->plan.valid = false;   // (this call rewrites the order array the class plan of the device entry points refers to)
     // per chunk: per-class longest-first order (written into the pinned order array at the chunk's range)
     int count_cv[kMaxChunks][kNumVariants];
     int start_cv[kMaxChunks][kNumVariants + 1];
@@ -595,6 +748,19 @@ int pqp_solve_batch(pqp_handle *h, int formulation, int batch, const int32_t *n_
     if (!it_dst && stats) { iters_local.resize(B); it_dst = iters_local.data(); }
     cudaStream_t sts[2] = {h->stream, h->stream2};
     int launches = 0;
+    bool ev1_done = false;
+    // Once copies into the caller's buffers are in flight, no error return may leave them running: both lanes are
+    // drained first (PQP_CUDA_DRAIN = PQP_CUDA with that drain).
+    auto drain = [&]() { cudaStreamSynchronize(sts[0]); cudaStreamSynchronize(sts[1]); };
+#define PQP_CUDA_DRAIN(call)                                                 \
+    do {                                                                     \
+        cudaError_t e_ = (call);                                             \
+        if (e_ != cudaSuccess) {                                             \
+            pqp_set_err("%s failed: %s", #call, cudaGetErrorString(e_));     \
+            drain();                                                         \
+            return PQP_ERR_CUDA;                                             \
+        }                                                                    \
+    } while (0)
     // ev[0] start | ev[1] first kernel may start | ev[2] last kernel done | ev[3] all done
     PQP_CUDA(cudaEventRecord(h->ev[0], sts[0]));
     PQP_CUDA(cudaStreamWaitEvent(sts[1], h->ev[0], 0));
@@ -608,33 +774,35 @@ int pqp_solve_batch(pqp_handle *h, int formulation, int batch, const int32_t *n_
         const int pb = cb[k], pe = cb[k + 1];
         if (pe == pb) continue;
         const size_t o0 = (size_t)h->h_off[pb], nT = (size_t)h->h_off[pe] - o0, nB = (size_t)(pe - pb);
-        PQP_CUDA(cudaMemcpyAsync(h->d_n + pb, n_points + pb, nB * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-        PQP_CUDA(cudaMemcpyAsync(h->d_ref + o0, ref + o0, nT * sizeof(pqp_state), cudaMemcpyHostToDevice, st));
-        PQP_CUDA(cudaMemcpyAsync(h->d_bounds + o0, bounds + o0, nT * sizeof(pqp_station_bounds), cudaMemcpyHostToDevice, st));
-        PQP_CUDA(cudaMemcpyAsync(h->d_x0 + 3 * (size_t)pb, x0 + 3 * (size_t)pb, nB * 3 * sizeof(double), cudaMemcpyHostToDevice, st));
-        PQP_CUDA(cudaMemcpyAsync(h->d_end + pb, end_heading + pb, nB * sizeof(double), cudaMemcpyHostToDevice, st));
-        if (k == 0) PQP_CUDA(cudaEventRecord(h->ev[1], st));
+        PQP_CUDA_DRAIN(cudaMemcpyAsync(h->d_n + pb, n_points + pb, nB * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        PQP_CUDA_DRAIN(cudaMemcpyAsync(h->d_ref + o0, ref + o0, nT * sizeof(pqp_state), cudaMemcpyHostToDevice, st));
+        PQP_CUDA_DRAIN(cudaMemcpyAsync(h->d_bounds + o0, bounds + o0, nT * sizeof(pqp_station_bounds), cudaMemcpyHostToDevice, st));
+        PQP_CUDA_DRAIN(cudaMemcpyAsync(h->d_x0 + 3 * (size_t)pb, x0 + 3 * (size_t)pb, nB * 3 * sizeof(double), cudaMemcpyHostToDevice, st));
+        PQP_CUDA_DRAIN(cudaMemcpyAsync(h->d_end + pb, end_heading + pb, nB * sizeof(double), cudaMemcpyHostToDevice, st));
+        if (!ev1_done) { PQP_CUDA_DRAIN(cudaEventRecord(h->ev[1], st)); ev1_done = true; }
         for (int v = 0; v < kNumVariants; ++v) {
             if (!count_cv[k][v]) continue;
             int rc = launch_variant(h, v, bv, count_cv[k][v], h->d_order + start_cv[k][v], smem_cv[k][v], st);
-            if (rc != PQP_OK) return rc;
+            if (rc != PQP_OK) { drain(); return rc; }
             ++launches;
         }
-        PQP_CUDA(cudaEventRecord(h->ev_chunk[1 + k], st));   // this chunk's kernels done
-        PQP_CUDA(cudaMemcpyAsync(out_states + o0, h->d_out + o0, nT * sizeof(pqp_state), cudaMemcpyDeviceToHost, st));
+        PQP_CUDA_DRAIN(cudaEventRecord(h->ev_chunk[1 + k], st));   // this chunk's kernels done
+        PQP_CUDA_DRAIN(cudaMemcpyAsync(out_states + o0, h->d_out + o0, nT * sizeof(pqp_state), cudaMemcpyDeviceToHost, st));
         if (out_frenet)
-            PQP_CUDA(cudaMemcpyAsync(out_frenet + 3 * o0, h->d_frenet + 3 * o0, nT * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
-        PQP_CUDA(cudaMemcpyAsync(status + pb, h->d_status + pb, nB * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-        if (it_dst) PQP_CUDA(cudaMemcpyAsync(it_dst + pb, h->d_iters + pb, nB * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+            PQP_CUDA_DRAIN(cudaMemcpyAsync(out_frenet + 3 * o0, h->d_frenet + 3 * o0, nT * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
+        PQP_CUDA_DRAIN(cudaMemcpyAsync(status + pb, h->d_status + pb, nB * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        if (it_dst) PQP_CUDA_DRAIN(cudaMemcpyAsync(it_dst + pb, h->d_iters + pb, nB * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     }
+    if (!ev1_done) PQP_CUDA_DRAIN(cudaEventRecord(h->ev[1], sts[0]));   // (every chunk was empty)
     // join: stream 0 waits for every chunk's kernels (ev[2]) and then for stream 1's copies (ev[3])
     for (int k = 0; k < n_chunks; ++k)
-        if (cb[k + 1] > cb[k] && (k & 1)) PQP_CUDA(cudaStreamWaitEvent(sts[0], h->ev_chunk[1 + k], 0));
-    PQP_CUDA(cudaEventRecord(h->ev[2], sts[0]));
-    PQP_CUDA(cudaEventRecord(h->ev_chunk[kMaxChunks + 1], sts[1]));
-    PQP_CUDA(cudaStreamWaitEvent(sts[0], h->ev_chunk[kMaxChunks + 1], 0));
-    PQP_CUDA(cudaEventRecord(h->ev[3], sts[0]));
+        if (cb[k + 1] > cb[k] && (k & 1)) PQP_CUDA_DRAIN(cudaStreamWaitEvent(sts[0], h->ev_chunk[1 + k], 0));
+    PQP_CUDA_DRAIN(cudaEventRecord(h->ev[2], sts[0]));
+    PQP_CUDA_DRAIN(cudaEventRecord(h->ev_chunk[kMaxChunks + 1], sts[1]));
+    PQP_CUDA_DRAIN(cudaStreamWaitEvent(sts[0], h->ev_chunk[kMaxChunks + 1], 0));
+    PQP_CUDA_DRAIN(cudaEventRecord(h->ev[3], sts[0]));
     PQP_CUDA(cudaStreamSynchronize(sts[0]));
+#undef PQP_CUDA_DRAIN
 #ifdef PQP_PHASE_TIMING
     {
         std::vector<long long> dbg(16 * (size_t)batch);

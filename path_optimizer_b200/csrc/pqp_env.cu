@@ -619,7 +619,7 @@ int pqp_plan_batch(pqp_handle *h, int formulation, int bounds_mode, int output_m
         bv.batch = batch; bv.n_points = e->d_nvalid; bv.offsets = h->d_off; bv.ref = h->d_ref; bv.bounds = h->d_bounds;
         bv.x0 = h->d_x0; bv.end_heading = h->d_end; bv.out_states = h->d_out; bv.out_frenet = nullptr;
         bv.status = h->d_status; bv.iters = h->d_iters; bv.workspace = h->d_ws; bv.debug = nullptr;
-        rc = pqp_launch_kp_classes(h, bv, batch, nv.data(), h->h_off, ref, st, &qp_launches);
+        rc = pqp_launch_kp_classes(h, bv, batch, nv.data(), h->h_off, ref, nullptr, st, &qp_launches);
         if (rc != PQP_OK) return rc;
     }
     PQP_CUDA(cudaEventRecord(e->ev[3], st));

@@ -5,10 +5,14 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <vector>
+
 #include "../../include/pqp.h"
 #include "pqp_device.cuh"
 
 #define PQP_MAX_CHUNKS 4
+#define PQP_CLASS_LANES 4
+#define PQP_MAX_VARIANTS 24
 
 struct pqp_handle {
     int device = 0;
@@ -22,6 +26,20 @@ struct pqp_handle {
     cudaStream_t stream2 = nullptr;                 // second lane of the host-buffer pipeline
     cudaEvent_t ev_chunk[PQP_MAX_CHUNKS + 2] = {};  // [0] shared arrays uploaded, [1+k] chunk k kernels done, [last] lane 2 drained
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaStream_t cls_stream[PQP_CLASS_LANES] = {};  // lanes for the per-class launches of a mixed-length batch
+    cudaEvent_t ev_fork = nullptr, ev_cls[PQP_CLASS_LANES] = {};
+    // cached choice of pqp_solve_batch_device for (max_n_points, min_keep, max_keep)
+    int dc_nmax = -1, dc_klo = -1, dc_khi = -1, dc_skip = -1, dc_v = -1;
+    size_t dc_smem = 0;
+    // class plan of the last pqp_launch_kp_classes call (reused while the batch shape stays the same)
+    struct ClassPlan {
+        bool valid = false;
+        int skip = 0;
+        cudaStream_t stream = nullptr;
+        std::vector<int32_t> n, keep;
+        int count_v[PQP_MAX_VARIANTS] = {}, start_v[PQP_MAX_VARIANTS + 1] = {};
+        size_t smem_v[PQP_MAX_VARIANTS] = {};
+    } plan;
     // device buffers for the host-pointer entry point
     int32_t *d_n = nullptr, *d_off = nullptr, *d_order = nullptr, *d_status = nullptr, *d_iters = nullptr;
     pqp_state *d_ref = nullptr, *d_out = nullptr;
@@ -39,9 +57,11 @@ struct pqp_handle {
 
 // Internal (pqp_capi.cu): launch the KP solve kernels for paths whose station counts n[b] are known on the host,
 // each path on the kernel class picked for (n[b], its keep_control_steps), longest first inside a class.  The
-// device-side counts (BatchView::n_points) must equal n.  Used by pqp_plan_batch after the bounds stage.
+// device-side counts (BatchView::n_points) must equal n.  keep[b] = keep_control_steps per path, or NULL to derive
+// them from the host copy `ref` of the reference states.  Used by pqp_plan_batch after the bounds stage and by
+// pqp_solve_batch_device_classes.
 int pqp_launch_kp_classes(pqp_handle *h, const pqp::BatchView &bv, int batch, const int32_t *n, const int32_t *off,
-                          const pqp_state *ref, cudaStream_t st, int *launches);
+                          const pqp_state *ref, const int32_t *keep, cudaStream_t st, int *launches);
 
 // thread-local error text returned by pqp_last_error()
 extern thread_local char pqp_g_err[512];

@@ -22,5 +22,5 @@ static size_t g_smem(int n, int keep) {
 }
 static bool g_fits(int, int keep) { return keep <= 10; }
 void pqp_variant_k1_generic(PqpVariant *out) {
-    *out = PqpVariant{0, pqp::kMaxBand, 32, (const void *)pqp_kp_solve_kernel, g_smem, g_fits};
+    *out = PqpVariant{0, pqp::kMaxBand, 32, (const void *)pqp_kp_solve_kernel, g_smem, g_fits, "pqp_kp_solve_kernel"};
 }

@@ -21,24 +21,34 @@ pqp_kp2_solve_kernel(const __grid_constant__ pqp::DevParams prm, const __grid_co
 #define PQP_KP3_MINBLOCKS 2
 #endif
 // Thread-per-station kernels (pqp_kp_core3.cuh): NW warps per path, N <= 32*NW stations.
+#ifndef PQP_KP3_MAXNREG
+#define PQP_KP3_MAXNREG 0
+#endif
 template <int IMAX, int BW, int NW, int MMAX>
-__global__ void __launch_bounds__(NW * 32, NW <= 4 ? PQP_KP3_MINBLOCKS : 1)
+__global__ void
+#if PQP_KP3_MAXNREG
+__maxnreg__(PQP_KP3_MAXNREG)   // (thirteen warps: 65536 / 416 = 157 -> 152; __launch_bounds__(416) settles on 128)
+#else
+__launch_bounds__(NW * 32, NW <= 4 ? PQP_KP3_MINBLOCKS : 1)
+#endif
 pqp_kp3_solve_kernel(const __grid_constant__ pqp::DevParams prm, const __grid_constant__ pqp::BatchView bv,
                      const int32_t *__restrict__ order, int smem_doubles) {
     extern __shared__ double pqp_smem[];
     int prob = blockIdx.x;
     if (order) prob = order[prob];
     pqp::Cta c{pqp::Warp(), pqp::CtaSync(), (int)(threadIdx.x >> 5), NW, pqp_smem};
-    pqp::Kp3<IMAX, BW, NW, MMAX>::solve_path(c, prm, bv, prob, pqp_smem + 128, (size_t)smem_doubles - 128);
+    constexpr int kRes = pqp::Kp3<IMAX, BW, NW, MMAX>::kCtaScratch;
+    pqp::Kp3<IMAX, BW, NW, MMAX>::solve_path(c, prm, bv, prob, pqp_smem + kRes, (size_t)smem_doubles - kRes);
 }
 
 #define PQP_KP3_TU(I, B, W, MM)                                                                                   \
     static size_t tu_smem(int n, int keep) {                                                                      \
-        return (128 + pqp::Kp3<I, B, W, MM>::smem_doubles(pqp::Kp3<I, B, W, MM>::dims(n, keep))) * sizeof(double); \
+        return (pqp::Kp3<I, B, W, MM>::kCtaScratch + pqp::Kp3<I, B, W, MM>::smem_doubles(pqp::Kp3<I, B, W, MM>::dims(n, keep))) * sizeof(double); \
     }                                                                                                             \
     static bool tu_fits(int n, int keep) { return pqp::Kp3<I, B, W, MM>::fits(n, keep); }                         \
     void pqp_variant_k3_##I##_##B##_##W##_##MM(PqpVariant *out) {                                                 \
-        *out = PqpVariant{I, B, W * 32, (const void *)pqp_kp3_solve_kernel<I, B, W, MM>, tu_smem, tu_fits};       \
+        *out = PqpVariant{I, B, W * 32, (const void *)pqp_kp3_solve_kernel<I, B, W, MM>, tu_smem, tu_fits,        \
+                          "pqp_kp3_solve_kernel<" #I "," #B "," #W "," #MM ">"};                                  \
     }
 
 #define PQP_KP2_TU(I, B)                                                                                        \
@@ -47,5 +57,6 @@ pqp_kp3_solve_kernel(const __grid_constant__ pqp::DevParams prm, const __grid_co
     }                                                                                                           \
     static bool tu_fits(int n, int keep) { return keep <= 10 && pqp::Kp2<I, B>::fits(pqp::kp2_dims(n, keep)); } \
     void pqp_variant_k2_##I##_##B(PqpVariant *out) {                                                            \
-        *out = PqpVariant{I, B, kNW * 32, (const void *)pqp_kp2_solve_kernel<I, B>, tu_smem, tu_fits};          \
+        *out = PqpVariant{I, B, kNW * 32, (const void *)pqp_kp2_solve_kernel<I, B>, tu_smem, tu_fits,           \
+                          "pqp_kp2_solve_kernel<" #I "," #B ">"};                                               \
     }

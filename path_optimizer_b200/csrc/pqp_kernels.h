@@ -10,6 +10,7 @@ struct PqpVariant {
     const void *fn;                      // __global__ entry, for cudaLaunchKernel / cudaFuncSetAttribute
     size_t (*smem)(int n, int keep);     // dynamic shared memory (bytes) for a path of n stations
     bool (*fits)(int n, int keep);
+    const char *name;                    // kernel name as profilers print it
 };
 
 #define PQP_DECLARE_VARIANT(name) void pqp_variant_##name(PqpVariant *out);
@@ -21,6 +22,7 @@ PQP_DECLARE_VARIANT(k3_17_6_8_34)
 PQP_DECLARE_VARIANT(k3_23_7_8_34)
 PQP_DECLARE_VARIANT(k3_27_7_8_34)
 PQP_DECLARE_VARIANT(k3_37_7_8_17)
+PQP_DECLARE_VARIANT(k3_37_7_13_34)
 // chunked kernels Kp2<IMAX, BW>
 PQP_DECLARE_VARIANT(k2_17_6)
 PQP_DECLARE_VARIANT(k2_10_7)

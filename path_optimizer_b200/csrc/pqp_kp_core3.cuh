@@ -58,11 +58,20 @@ struct Kp3 {
     // are eliminated in closed form (3x3 blocks), only the even ones keep a dense inverse (<= 51 x 51 instead of
     // 102 x 102: N = 200 runs 13.2 ms per 1024 paths instead of 22.2 ms).
     static constexpr bool kTwoLevel = (MMAX > 17);
-    static constexpr bool kDense = (IMAX <= 17) && (MMAX <= 17);   // (at 34 separators the dense interiors would leave no L1 for the spills)
+    static constexpr bool kDense = (IMAX <= 17);   // (17-unknown interiors: 2 x 95 KB at 17 separators, 181 KB at 34 -- one CTA per SM either way)
     static constexpr int kSolveT = (MMAX + 31) / 32 * 32;   // threads that run the banded interior solves (non-dense form)
     static constexpr int kRow = IMAX + 1;                // row pitch of a dense inverse (even: 128-bit loads stay aligned, 4*lane word offsets)
     static constexpr int kFacSlots = kDense ? IMAX * kRow : IMAX * (BW + 1);
     static_assert(!kDense || IMAX * kRow >= IMAX * (BW + 1) + kRed2 + 27 + 12, "refactorisation scratch must fit behind the band factor");
+    // Long-path classes (more than eight warps: up to 416 stations, 37-unknown interiors) need every byte of the
+    // 227 KB a CTA can opt into: their refactorisation scratch is overlaid on the rhs / y vectors (free while a
+    // refactorisation runs; both are zeroed again at its end so that the padded entries stay finite).
+    static constexpr bool kScratchOnVec = !kDense && (NW > 8);
+    static_assert(!kScratchOnVec || (kTwoLevel && 2 * ((IMAX + 3) | 1) >= kRed2 + 27 + 12), "scratch must fit in the two solve vectors");
+    // exchange rows of kT doubles: 0..5, ds, separator rhs; the long-path classes park the separator rhs in row 5
+    // (only the Ruiz sweeps and diagnostic builds use that row otherwise)
+    static constexpr int kExRows = kScratchOnVec ? 7 : 8;
+    static constexpr int kCtaScratch = (NW <= 8) ? 128 : 256;   // doubles reserved ahead of the layout for the CTA reductions (16 per warp)
 
     PQP_HD static Kp3Dims dims(int N, int keep) {
         Kp3Dims d = kp3_dims_raw(N, keep, MMAX);
@@ -84,25 +93,25 @@ struct Kp3 {
         PQP_DEV double *yv() const { return base + nv; }                  // K_I^-1 r_I         [nv]
         PQP_DEV double *ex(int k) const { return base + 2 * nv + k * kT; }  // 6 exchange rows of kT
         PQP_DEV double *dsS() const { return ex(6); }                     // ds per station     [kT]
-        PQP_DEV double *gS() const { return ex(7); }                      // separator rhs      [nS <= kT]
-        PQP_DEV double *fac() const { return ex(8); }                     // [IMAX*(BW+1)*M]; kDense: then K_I^-1 [M][IMAX][kRow]
+        PQP_DEV double *gS() const { return ex(kScratchOnVec ? 5 : 7); }     // separator rhs      [nS <= kT]
+        PQP_DEV double *fac() const { return ex(kExRows); }               // [IMAX*(BW+1)*M]; kDense: then K_I^-1 [M][IMAX][kRow]
         PQP_DEV double *T() const { return fac() + kFacSlots * M; }       // spikes T[c][pos], c < 6: [6*nv]
         PQP_DEV int nSd() const { return kTwoLevel ? 3 * ((M + 1) / 2) : nS; }   // order of the dense separator inverse
         PQP_DEV double *Sinv() const { return T() + 6 * nv; }             // [nSd*nSd]
         // refactorisation scratch [kRed2*M] + blocks [27*M] + couplings [12*M].  With dense interiors it lives in the
         // part of the fac / kinv region the band factor does not use (free until the dense inverses are written, which
         // is the last step of a refactorisation): two CTAs then need < 196 KB and the SM keeps 60 KB of L1 for the spills.
-        PQP_DEV double *red() const { return kDense ? fac() + IMAX * (BW + 1) * M : Sinv() + nSd() * nSd(); }
+        PQP_DEV double *red() const { return kDense ? fac() + IMAX * (BW + 1) * M : (kScratchOnVec ? base : Sinv() + nSd() * nSd()); }
         PQP_DEV double *blk() const { return red() + kRed2 * M; }         // A|C|Off per chunk [27*M]
         PQP_DEV double *cpl() const { return blk() + 27 * M; }            // coupling coefs [12*M]
         // two-level form: per separator E = Dg^-1 (odd) | PL | PR (even) | Off copy [36*M]; reduced system [kRed2*ceil(M/2)]
-        PQP_DEV double *lv() const { return kDense ? Sinv() + nSd() * nSd() : cpl() + 12 * M; }
+        PQP_DEV double *lv() const { return (kDense || kScratchOnVec) ? Sinv() + nSd() * nSd() : cpl() + 12 * M; }
         PQP_DEV double *red2() const { return lv() + 36 * M; }
     };
     PQP_HD static size_t smem_doubles(const Kp3Dims &d) {
-        return 2 * (size_t)d.nv + 8 * (size_t)kT + (size_t)kFacSlots * d.M + 6 * (size_t)d.nv +
+        return 2 * (size_t)d.nv + (size_t)kExRows * kT + (size_t)kFacSlots * d.M + 6 * (size_t)d.nv +
                (kTwoLevel ? (size_t)9 * ((d.M + 1) / 2) * ((d.M + 1) / 2) : (size_t)d.nS * d.nS) +
-               (kDense ? 0 : (size_t)(kRed2 + 27 + 12) * d.M) +
+               ((kDense || kScratchOnVec) ? 0 : (size_t)(kRed2 + 27 + 12) * d.M) +
                (kTwoLevel ? (size_t)36 * d.M + (size_t)kRed2 * ((d.M + 1) / 2) : 0);
     }
 
@@ -757,6 +766,10 @@ struct Kp3 {
                     }
                 }
                 PQP_RT(7)
+                if constexpr (kScratchOnVec) {
+                    c.sync();   // every reader of the scratch is done: give the two vectors back, padded entries zero
+                    for (int g = tid; g < d.nv; g += kT) { s.tr()[g] = 0.0; s.yv()[g] = 0.0; }
+                }
                 return !c.any(!ok);   // (contains CTA barriers)
             };
 
@@ -817,6 +830,7 @@ struct Kp3 {
             };
             const int yQ = IMAX * M;
 #ifdef PQP_PHASE_TIMING
+            static_assert(!kScratchOnVec, "phase timing uses exchange row 5, which the long-path classes give to the separator rhs");
             // clock64() at the phase boundaries, accumulated per warp-0 / warp-1 lead thread in shared scratch
             // (diagnostic builds only): slots 0..5 = a1, a2, b1, b2, b3, c ; 6 = iterations
             double *ph_acc = s.ex(5) + 8 * (wid & 1);   // (row 5 is free once the scaling is done)

@@ -113,12 +113,14 @@ class OsqpSolver:
                            bounds=np.ascontiguousarray(bounds, dtype=BOUNDS_DTYPE)[:self.horizon],
                            x0=np.array([[init_error[0], init_error[1], start_k]], dtype=np.float64),
                            end_heading=np.array([end_heading], dtype=np.float64))
+        # One shared handle per device, sized for the longest path the kernels take; the parameter snapshot is
+        # (re)applied before every solve (the reference re-reads FLAGS_* on every solve), so an instance never
+        # inherits another instance's parameters.
+        self.params = params if params is not None else default_params()
         key = device
         if key not in OsqpSolver._shared:
-            OsqpSolver._shared[key] = BatchPathSolver(params, device=device, max_batch=1, max_total_points=4096)
+            OsqpSolver._shared[key] = BatchPathSolver(self.params, device=device, max_batch=1, max_total_points=8192)
         self._solver = OsqpSolver._shared[key]
-        if params is not None:
-            self._solver.set_params(params)
 
     @staticmethod
     def create(type_, ref_states, bounds, init_error, start_k, end_heading, horizon, params=None, device=0):
@@ -130,7 +132,12 @@ class OsqpSolver:
 
     def solve(self, optimized_path):
         """Fills `optimized_path` (a list) with horizon State records; returns the reference's bool."""
-        res = self._solver.solve(self._batch, self.formulation)
+        self._solver.set_params(self.params)
+        try:
+            res = self._solver.solve(self._batch, self.formulation)
+        except PqpError as e:   # the reference's solve() reports every failure through its bool
+            log.error("QP failed: %s", e)
+            return False
         if not bool(res["ok"][0]):
             return False
         optimized_path.clear()

@@ -89,12 +89,14 @@ def straight_corridors(batch, n=100, seed=BASE_SEED, first_path=0, config=2, wid
     return _pack(np.full(batch, n), ref.reshape(-1), bounds.reshape(-1), x0, end_heading)
 
 
-def curvy_corridors(batch, n=100, seed=BASE_SEED, first_path=0, config=3, n_points=None):
+def curvy_corridors(batch, n=100, seed=BASE_SEED, first_path=0, config=3, n_points=None, path_ids=None):
     """Analytic curved corridors (config 5 / "config 3-lite"): kappa_ref(s) = A sin(2 pi s / L),
     A ~ U(0, 0.05), L ~ U(30, 80) m integrated to (x, y, heading); corridor centre follows a smooth
     lateral wave c(s) of amplitude U(0, 0.6) m, half widths per circle U(0.6, 1.6) quantised to
     0.1 m, so bounds differ per station and per circle (some above the 1.3 m soft margin).
-    `n_points` (int array [batch]) gives mixed lengths; otherwise every path has n stations."""
+    `n_points` (int array [batch]) gives mixed lengths; otherwise every path has n stations.  `path_ids` (int array
+    [batch]) names the global ids of the paths to generate (a rank's shard of a work-balanced split); default
+    first_path .. first_path + batch - 1."""
     if n_points is None:
         n_points = np.full(batch, n, dtype=np.int32)
     n_points = np.asarray(n_points, dtype=np.int32)
@@ -106,7 +108,7 @@ def curvy_corridors(batch, n=100, seed=BASE_SEED, first_path=0, config=3, n_poin
     off = 0
     for b in range(batch):
         nb = int(n_points[b])
-        pid = np.uint64(first_path + b)
+        pid = np.uint64(first_path + b if path_ids is None else int(path_ids[b]))
         s = _accumulate_s(nb)
         A = 0.05 * uniform(seed, config, pid, 1)
         L = 30.0 + 50.0 * uniform(seed, config, pid, 2)
@@ -132,6 +134,25 @@ def curvy_corridors(batch, n=100, seed=BASE_SEED, first_path=0, config=3, n_poin
         end_heading[b] = theta[-1]
         off += nb
     return _pack(n_points, ref, bounds, x0, end_heading)
+
+
+def mixed_lengths(batch, lo=50, hi=400, seed=BASE_SEED, first_path=0, config=5):
+    """BASELINE config 5 station counts: N ~ U{lo..hi} per global path id."""
+    pid = np.arange(first_path, first_path + batch, dtype=np.uint64)
+    return (lo + np.floor((hi - lo + 1) * uniform(seed, config, pid, 30))).astype(np.int32)
+
+
+def take_paths(batch, idx):
+    """Paths `idx` (index array) of a batch as a new batch (copies)."""
+    o = batch["offsets"]
+    idx = np.asarray(idx, dtype=np.int64)
+    sel = np.concatenate([np.arange(o[i], o[i + 1]) for i in idx]) if len(idx) else np.zeros(0, dtype=np.int64)
+    out = dict(n_points=batch["n_points"][idx].copy(), ref=batch["ref"][sel].copy(), bounds=batch["bounds"][sel].copy(),
+               x0=batch["x0"][idx].copy(), end_heading=batch["end_heading"][idx].copy())
+    offsets = np.zeros(len(idx) + 1, dtype=np.int32)
+    np.cumsum(out["n_points"], out=offsets[1:])
+    out["offsets"] = offsets
+    return out
 
 
 def slice_batch(batch, begin, end):

@@ -25,8 +25,9 @@ void *lane_main(void *p) {
     LaneArgs *a = (LaneArgs *)p;
     pqp::Warp w{a->lane, a->sh};
     pqp::Cta c{w, pqp::CtaSync{a->cta}, a->wid, a->nw, a->smem};
-    double *sm = a->smem + 128;                // first 128 doubles: CTA reduction scratch
-    const size_t cap = a->smem_doubles - 128;
+    const int res = a->nw > 8 ? 256 : 128;     // leading doubles: CTA reduction scratch (16 per warp)
+    double *sm = a->smem + res;
+    const size_t cap = a->smem_doubles - res;
     switch (a->variant) {
     case 1: pqp::Kp2<17, 6>::solve_path(c, *a->prm, *a->bv, a->prob, sm, cap); break;
     case 2: pqp::Kp2<10, 7>::solve_path(c, *a->prm, *a->bv, a->prob, sm, cap); break;
@@ -37,6 +38,7 @@ void *lane_main(void *p) {
     case 7: pqp::Kp3<27, 7, 8>::solve_path(c, *a->prm, *a->bv, a->prob, sm, cap); break;
     case 8: pqp::Kp3<17, 6, 8, 34>::solve_path(c, *a->prm, *a->bv, a->prob, sm, cap); break;
     case 9: pqp::Kp3<23, 7, 8, 34>::solve_path(c, *a->prm, *a->bv, a->prob, sm, cap); break;
+    case 10: pqp::Kp3<37, 7, 13, 34>::solve_path(c, *a->prm, *a->bv, a->prob, sm, cap); break;
     default: pqp::kp_solve_path(w, *a->prm, *a->bv, a->prob, sm, cap);   // generic core: one warp
     }
     return nullptr;
@@ -51,6 +53,7 @@ extern "C" int kp_emu_solve_batch(const pqp_params *params, int batch, const int
     if (variant == 0 || nwarps < 1) nwarps = 1;
     if (variant == 5 || variant == 6) nwarps = 4;
     if (variant >= 7) nwarps = 8;
+    if (variant == 10) nwarps = 13;
     pqp::DevParams prm = pqp::dev_params_from(*params);
     pqp::BatchView bv;
     bv.batch = batch; bv.n_points = n_points; bv.offsets = offsets; bv.ref = ref; bv.bounds = bounds;
@@ -65,13 +68,13 @@ extern "C" int kp_emu_solve_batch(const pqp_params *params, int batch, const int
         // poison the scratch so that reads of uninitialised shared memory show up as NaN
         for (size_t k = 0; k < smem_doubles; ++k) smem[k] = nan("");
         const int nth = 32 * nwarps;
-        pqp::EmuShared sh[8];
+        pqp::EmuShared sh[16];
         pqp::EmuCta cta;
         cta.nthreads = nth;
         pthread_barrier_init(&cta.bar, nullptr, nth);
         for (int k = 0; k < nwarps; ++k) pthread_barrier_init(&sh[k].bar, nullptr, 32);
-        pthread_t th[256];
-        LaneArgs args[256];
+        pthread_t th[512];
+        LaneArgs args[512];
         for (int t = 0; t < nth; ++t) {
             args[t] = LaneArgs{&sh[t / 32], &cta, t % 32, t / 32, nwarps, &prm, &bv, prob, smem, smem_doubles, variant};
             pthread_create(&th[t], nullptr, lane_main, &args[t]);

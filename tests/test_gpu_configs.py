@@ -1,0 +1,158 @@
+"""GPU tests of BASELINE configs 3, 4, 5 AT THEIR NAMED PER-GPU SIZES (run with -m gpu on the B200 box): the whole
+shard is solved through the C ABI, a >= 64-path sample of it is compared with the oracle (identical status, identical
+ADMM iteration count, 1e-8 on the Frenet and Cartesian states), and the device-resident entry points are checked
+against the host-buffer one bit for bit."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from oracle import oracle
+from path_optimizer_b200 import synth, workloads
+from path_optimizer_b200.abi import BOUNDS_DTYPE, STATE_DTYPE, SOLVED
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-8
+SAMPLE = 64
+
+
+def _solver(B, total):
+    from path_optimizer_b200.planner import PathPlanner
+    return PathPlanner(max_batch=B, max_total_points=total)
+
+
+def _sample_vs_oracle(batch, res, oracle_params, idx):
+    sub = synth.take_paths(batch, idx)
+    ref = oracle.solve_batch(oracle_params, 0, sub, threads=8)
+    o = batch["offsets"]
+    sel = np.concatenate([np.arange(o[i], o[i + 1]) for i in idx])
+    assert np.array_equal(res["status"][idx], ref["status"])
+    assert np.array_equal(res["iters"][idx], ref["iters"])
+    np.testing.assert_allclose(res["frenet"][sel], ref["frenet"], rtol=0, atol=TOL)
+    for f in "xyzks":
+        np.testing.assert_allclose(res["states"][f][sel], ref["states"][f], rtol=0, atol=TOL)
+    return ref
+
+
+def test_config4_full_shard_sampled(oracle_params):
+    """8192 x 100 straight corridors (one GPU's shard of the 65 536-path config 4)."""
+    batch = workloads.build(4)
+    s = _solver(8192, 8192 * 100)
+    res = s.solve(batch)
+    assert (res["status"] == SOLVED).all()
+    idx = np.arange(17, 8192, 8192 // SAMPLE)[:SAMPLE]
+    _sample_vs_oracle(batch, res, oracle_params, idx)
+    s.close()
+
+
+def test_config3_full_shard_sampled(oracle_params):
+    """8192 x 200 with clearance bounds from the random-obstacle distance map (bounds by the GPU clearance stage)."""
+    field = synth.disc_field_map()
+    s = _solver(8192 + 1024, (8192 + 1024) * 200)
+    s.set_map(field)
+
+    def fn(cand):
+        r = s.update_bounds(cand)
+        return r["bounds"], r["n_valid"]
+    batch = workloads.build(3, bounds_fn=fn)
+    assert len(batch["n_points"]) == 8192 and (batch["n_points"] == 200).all()
+    res = s.solve(batch)
+    idx = np.arange(5, 8192, 8192 // SAMPLE)[:SAMPLE]
+    # the sample's bounds from the oracle's clearance stage: the two agree bit for bit
+    sub = synth.take_paths(batch, idx)
+    ob = oracle.update_bounds(oracle_params, field, sub, mode=1)
+    assert (ob["n_valid"] == 200).all()
+    for f in BOUNDS_DTYPE.names:
+        assert np.array_equal(ob["bounds"][f], sub["bounds"][f])
+    ref = _sample_vs_oracle(batch, res, oracle_params, idx)
+    assert (ref["status"] == SOLVED).sum() >= SAMPLE // 2
+    # whole planner iteration on the same reference lines: same QP statuses and iteration counts as QP-only
+    pr = s.plan(batch)
+    assert np.array_equal(pr["status"], res["status"]) and np.array_equal(pr["iters"], res["iters"])
+    s.close()
+
+
+def _device_call(s, batch, classes):
+    """Device-resident entry points through raw device buffers (torch only moves the bytes)."""
+    import torch
+    from path_optimizer_b200 import _lib
+    L = _lib.load()
+    dev = torch.device("cuda", 0)
+    B, total = len(batch["n_points"]), int(batch["offsets"][-1])
+
+    def up(a):
+        return torch.from_numpy(np.frombuffer(np.ascontiguousarray(a).tobytes(), dtype=np.uint8).copy()).to(dev)
+    d_n, d_off, d_ref, d_bnd = up(batch["n_points"]), up(batch["offsets"]), up(batch["ref"]), up(batch["bounds"])
+    d_x0, d_end = up(batch["x0"]), up(batch["end_heading"])
+    d_out = torch.zeros(total * STATE_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+    d_fr = torch.zeros(total * 3, dtype=torch.float64, device=dev)
+    d_st = torch.zeros(B, dtype=torch.int32, device=dev)
+    d_it = torch.zeros(B, dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()
+    off = batch["offsets"]
+    keep = np.array([L.pqp_keep_control_steps(0, np.ascontiguousarray(batch["ref"][off[i]:off[i + 1]]).ctypes.data_as(C.c_void_p),
+                                              int(batch["n_points"][i])) for i in range(B)], dtype=np.int32)
+    if classes:
+        hn = np.ascontiguousarray(batch["n_points"], dtype=np.int32)
+        rc = L.pqp_solve_batch_device_classes(s._h, 0, B, total, hn.ctypes.data_as(C.c_void_p), keep.ctypes.data_as(C.c_void_p),
+                                              d_n.data_ptr(), d_off.data_ptr(), d_ref.data_ptr(), d_bnd.data_ptr(),
+                                              d_x0.data_ptr(), d_end.data_ptr(), None, None, d_out.data_ptr(), d_fr.data_ptr(),
+                                              d_st.data_ptr(), d_it.data_ptr(), None, None)
+    else:
+        nmax, klo, khi = int(batch["n_points"].max()), int(keep.min()), int(keep.max())
+        rc = L.pqp_solve_batch_device(s._h, 0, B, total, nmax, klo, khi, d_n.data_ptr(), d_off.data_ptr(), d_ref.data_ptr(),
+                                      d_bnd.data_ptr(), d_x0.data_ptr(), d_end.data_ptr(), None, None, d_out.data_ptr(),
+                                      d_fr.data_ptr(), d_st.data_ptr(), d_it.data_ptr(), None, None)
+    assert rc == 0, _lib.last_error()
+    torch.cuda.synchronize()
+    return dict(status=d_st.cpu().numpy(), iters=d_it.cpu().numpy(), frenet=d_fr.cpu().numpy().reshape(-1, 3),
+                states=np.frombuffer(d_out.cpu().numpy().tobytes(), dtype=STATE_DTYPE))
+
+
+def test_config5_full_shard_sampled(oracle_params):
+    """4096 paths of U{50..400} stations (one GPU's share of config 5): host-buffer call sampled against the oracle in
+    every length bucket; the length-bucketed device entry point gives the same bits."""
+    batch = workloads.build(5)
+    B, total = len(batch["n_points"]), int(batch["offsets"][-1])
+    assert B == 4096 and batch["n_points"].min() >= 50 and batch["n_points"].max() <= 400
+    s = _solver(B, total)
+    res = s.solve(batch)
+    n = batch["n_points"]
+    idx = []
+    for lo, hi in [(50, 102), (103, 204), (205, 256), (257, 400)]:   # the four kernel classes of the range
+        cand = np.nonzero((n >= lo) & (n <= hi))[0]
+        idx += list(cand[:: max(1, len(cand) // (SAMPLE // 4))][: SAMPLE // 4])
+    idx = np.array(sorted(idx))
+    assert len(idx) >= SAMPLE - 4
+    _sample_vs_oracle(batch, res, oracle_params, idx)
+    dres = _device_call(s, batch, classes=True)
+    assert np.array_equal(dres["status"], res["status"]) and np.array_equal(dres["iters"], res["iters"])
+    assert np.array_equal(dres["frenet"], res["frenet"])
+    for f in "xyzks":
+        assert np.array_equal(dres["states"][f], res["states"][f])
+    s.close()
+
+
+@pytest.mark.parametrize("nmax,ds", [(128, 0.3), (150, 0.3), (150, 0.25), (256, 0.3), (400, 0.3)])
+def test_device_entry_with_loose_hints(oracle_params, nmax, ds):
+    """pqp_solve_batch_device picks ONE class from the caller's bounds: every path inside them must solve exactly as
+    pqp_solve_batch solves it (round 1 rejected in-range paths because neither fits() nor the shared-memory need is
+    monotone in the path length)."""
+    rng = np.random.default_rng(nmax)
+    n_points = rng.integers(2, nmax + 1, size=40)
+    n_points[:3] = [2, nmax, nmax - 1]
+    batch = synth.curvy_corridors(40, n_points=n_points)
+    if ds != 0.3:
+        o = batch["offsets"]
+        for b in range(40):
+            batch["ref"]["s"][o[b]:o[b + 1]] = np.arange(n_points[b]) * ds
+    total = int(batch["offsets"][-1])
+    s = _solver(40, total)
+    res = s.solve(batch)
+    dres = _device_call(s, batch, classes=False)
+    assert (dres["status"] != -100).all()
+    assert np.array_equal(dres["status"], res["status"]) and np.array_equal(dres["iters"], res["iters"])
+    np.testing.assert_allclose(dres["frenet"], res["frenet"], rtol=0, atol=TOL)
+    ref = oracle.solve_batch(oracle_params, 0, batch, threads=8)
+    assert np.array_equal(dres["status"], ref["status"]) and np.array_equal(dres["iters"], ref["iters"])
+    s.close()
