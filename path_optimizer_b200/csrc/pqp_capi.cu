@@ -26,19 +26,17 @@ namespace {
 #define g_err pqp_g_err
 
 // Shape classes, in order of preference (the records come from the kernels' own translation units, pqp_kernels.h).
-// keep_control_steps <= 4 (station spacing >= 0.24 m) maps onto one of the Kp3 / Kp2 instantiations; anything else
-// runs on the one-warp generic kernel (last).
+// keep_control_steps <= 4 (station spacing >= 0.24 m) and up to 408 stations map onto one of the thread-per-station
+// (Kp3) instantiations; anything else runs on the one-warp generic kernel (last).
 typedef PqpVariant Variant;
-constexpr int kNumVariants = 15;
+constexpr int kNumVariants = 10;
 struct VariantTable {
     Variant v[kNumVariants];
     VariantTable() {
         int k = 0;
         pqp_variant_k3_17_6_4_17(&v[k++]); pqp_variant_k3_23_7_4_17(&v[k++]); pqp_variant_k3_27_7_4_17(&v[k++]);
         pqp_variant_k3_17_6_8_34(&v[k++]); pqp_variant_k3_23_7_8_34(&v[k++]); pqp_variant_k3_27_7_8_34(&v[k++]);
-        pqp_variant_k3_37_7_8_17(&v[k++]); pqp_variant_k3_37_7_13_34(&v[k++]);
-        pqp_variant_k2_17_6(&v[k++]); pqp_variant_k2_10_7(&v[k++]); pqp_variant_k2_17_7(&v[k++]);
-        pqp_variant_k2_27_7(&v[k++]); pqp_variant_k2_37_7(&v[k++]); pqp_variant_k2_49_7(&v[k++]);
+        pqp_variant_k3_37_7_8_17(&v[k++]); pqp_variant_k3_37_7_12_34(&v[k++]); pqp_variant_k3_37_7_13_34(&v[k++]);
         pqp_variant_k1_generic(&v[k++]);
     }
 };
@@ -419,6 +417,10 @@ static int launch_variant(pqp_handle *h, int v, const pqp::BatchView &bv, int co
         set_err("path too long for one SM's shared memory");
         return PQP_ERR_UNSUPPORTED;
     }
+    // PQP_FORCE_SMEM=<bytes> (diagnostics only): launch with at least that much dynamic shared memory, e.g. to hold a
+    // two-CTA-per-SM class at one CTA per SM.  The kernel still lays out what the path needs.
+    static const size_t force = [] { const char *e = getenv("PQP_FORCE_SMEM"); return e ? (size_t)strtoul(e, nullptr, 0) : (size_t)0; }();
+    if (force > smem_bytes) smem_bytes = std::min(force, (size_t)h->smem_optin);
     int smem_doubles = (int)(smem_bytes / sizeof(double));
     void *args[] = {(void *)&h->dprm, (void *)&bv, (void *)&d_order, (void *)&smem_doubles};
     PQP_CUDA(cudaLaunchKernel(kVariants[v].fn, dim3(count), dim3(kVariants[v].threads), args, smem_bytes, st));

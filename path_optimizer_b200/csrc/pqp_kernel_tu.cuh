@@ -4,19 +4,6 @@
 #include "pqp_kernels.h"
 #include "pqp_kp_core3.cuh"
 
-// Chunked kernels: a CTA of kNW warps solves one path: all warps share the per-station phases, warp 0 runs the KKT solve.
-constexpr int kNW = 4;
-template <int IMAX, int BW>
-__global__ void __launch_bounds__(kNW * 32, 3)
-pqp_kp2_solve_kernel(const __grid_constant__ pqp::DevParams prm, const __grid_constant__ pqp::BatchView bv,
-                     const int32_t *__restrict__ order, int smem_doubles) {
-    extern __shared__ double pqp_smem[];
-    int prob = blockIdx.x;
-    if (order) prob = order[prob];
-    pqp::Cta c{pqp::Warp(), pqp::CtaSync(), (int)(threadIdx.x >> 5), kNW, pqp_smem};
-    pqp::Kp2<IMAX, BW>::solve_path(c, prm, bv, prob, pqp_smem + 128, (size_t)smem_doubles - 128);
-}
-
 #ifndef PQP_KP3_MINBLOCKS
 #define PQP_KP3_MINBLOCKS 2
 #endif
@@ -27,7 +14,7 @@ pqp_kp2_solve_kernel(const __grid_constant__ pqp::DevParams prm, const __grid_co
 template <int IMAX, int BW, int NW, int MMAX>
 __global__ void
 #if PQP_KP3_MAXNREG
-__maxnreg__(PQP_KP3_MAXNREG)   // (thirteen warps: 65536 / 416 = 157 -> 152; __launch_bounds__(416) settles on 128)
+__maxnreg__(PQP_KP3_MAXNREG)   // (diagnostics: registers are per SM sub-partition, 16 K for the warps that share one)
 #else
 __launch_bounds__(NW * 32, NW <= 4 ? PQP_KP3_MINBLOCKS : 1)
 #endif
@@ -49,14 +36,4 @@ pqp_kp3_solve_kernel(const __grid_constant__ pqp::DevParams prm, const __grid_co
     void pqp_variant_k3_##I##_##B##_##W##_##MM(PqpVariant *out) {                                                 \
         *out = PqpVariant{I, B, W * 32, (const void *)pqp_kp3_solve_kernel<I, B, W, MM>, tu_smem, tu_fits,        \
                           "pqp_kp3_solve_kernel<" #I "," #B "," #W "," #MM ">"};                                  \
-    }
-
-#define PQP_KP2_TU(I, B)                                                                                        \
-    static size_t tu_smem(int n, int keep) {                                                                    \
-        return (128 + pqp::Kp2<I, B>::smem_doubles(pqp::Kp2<I, B>::dims(n, keep))) * sizeof(double);            \
-    }                                                                                                           \
-    static bool tu_fits(int n, int keep) { return keep <= 10 && pqp::Kp2<I, B>::fits(pqp::kp2_dims(n, keep)); } \
-    void pqp_variant_k2_##I##_##B(PqpVariant *out) {                                                            \
-        *out = PqpVariant{I, B, kNW * 32, (const void *)pqp_kp2_solve_kernel<I, B>, tu_smem, tu_fits,           \
-                          "pqp_kp2_solve_kernel<" #I "," #B ">"};                                               \
     }

@@ -22,14 +22,8 @@ PQP_DECLARE_VARIANT(k3_17_6_8_34)
 PQP_DECLARE_VARIANT(k3_23_7_8_34)
 PQP_DECLARE_VARIANT(k3_27_7_8_34)
 PQP_DECLARE_VARIANT(k3_37_7_8_17)
+PQP_DECLARE_VARIANT(k3_37_7_12_34)
 PQP_DECLARE_VARIANT(k3_37_7_13_34)
-// chunked kernels Kp2<IMAX, BW>
-PQP_DECLARE_VARIANT(k2_17_6)
-PQP_DECLARE_VARIANT(k2_10_7)
-PQP_DECLARE_VARIANT(k2_17_7)
-PQP_DECLARE_VARIANT(k2_27_7)
-PQP_DECLARE_VARIANT(k2_37_7)
-PQP_DECLARE_VARIANT(k2_49_7)
 // one-warp generic KP kernel (any keep <= 10) and the generic banded-QP kernel of "K" / "KPC"
 PQP_DECLARE_VARIANT(k1_generic)
 const void *pqp_gen_kernel_fn();

@@ -19,7 +19,7 @@ struct LaneArgs {
     int prob;
     double *smem;
     size_t smem_doubles;
-    int variant;  // 0: generic v1 core; 1: v2 <17,6>; 2: v2 <10,7>; 3: v2 <27,7>; 4: v2 <49,7>
+    int variant;  // 0: one-warp generic core; 5..11: thread-per-station classes (tests/emu/emu.py)
 };
 void *lane_main(void *p) {
     LaneArgs *a = (LaneArgs *)p;
@@ -29,16 +29,13 @@ void *lane_main(void *p) {
     double *sm = a->smem + res;
     const size_t cap = a->smem_doubles - res;
     switch (a->variant) {
-    case 1: pqp::Kp2<17, 6>::solve_path(c, *a->prm, *a->bv, a->prob, sm, cap); break;
-    case 2: pqp::Kp2<10, 7>::solve_path(c, *a->prm, *a->bv, a->prob, sm, cap); break;
-    case 3: pqp::Kp2<27, 7>::solve_path(c, *a->prm, *a->bv, a->prob, sm, cap); break;
-    case 4: pqp::Kp2<49, 7>::solve_path(c, *a->prm, *a->bv, a->prob, sm, cap); break;
     case 5: pqp::Kp3<17, 6, 4>::solve_path(c, *a->prm, *a->bv, a->prob, sm, cap); break;
     case 6: pqp::Kp3<23, 7, 4>::solve_path(c, *a->prm, *a->bv, a->prob, sm, cap); break;
     case 7: pqp::Kp3<27, 7, 8>::solve_path(c, *a->prm, *a->bv, a->prob, sm, cap); break;
     case 8: pqp::Kp3<17, 6, 8, 34>::solve_path(c, *a->prm, *a->bv, a->prob, sm, cap); break;
     case 9: pqp::Kp3<23, 7, 8, 34>::solve_path(c, *a->prm, *a->bv, a->prob, sm, cap); break;
     case 10: pqp::Kp3<37, 7, 13, 34>::solve_path(c, *a->prm, *a->bv, a->prob, sm, cap); break;
+    case 11: pqp::Kp3<37, 7, 12, 34>::solve_path(c, *a->prm, *a->bv, a->prob, sm, cap); break;
     default: pqp::kp_solve_path(w, *a->prm, *a->bv, a->prob, sm, cap);   // generic core: one warp
     }
     return nullptr;
@@ -54,6 +51,7 @@ extern "C" int kp_emu_solve_batch(const pqp_params *params, int batch, const int
     if (variant == 5 || variant == 6) nwarps = 4;
     if (variant >= 7) nwarps = 8;
     if (variant == 10) nwarps = 13;
+    if (variant == 11) nwarps = 12;
     pqp::DevParams prm = pqp::dev_params_from(*params);
     pqp::BatchView bv;
     bv.batch = batch; bv.n_points = n_points; bv.offsets = offsets; bv.ref = ref; bv.bounds = bounds;

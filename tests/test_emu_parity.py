@@ -13,19 +13,20 @@ TOL = 1e-9  # same recurrence in fp64: agreement is ~1e-13 in practice
 
 
 def _variant_for(batch):
-    """Pick the kernel shape class the library would pick (mirrors pick_variant in pqp_capi.cu)."""
+    """One emulator variant for the whole batch: the class the library would pick (pick_variant in pqp_capi.cu) when
+    every path maps onto the same one, else a class wide enough for all of them."""
     keeps = [oracle.keep_control_steps(0, batch["ref"][batch["offsets"][b]:batch["offsets"][b + 1]])
              for b in range(len(batch["n_points"]))]
     nmax, kmax = int(batch["n_points"].max()), max(keeps)
     if kmax > 4:
-        return 0
+        return 0          # one-warp generic kernel
     if kmax <= 3 and nmax <= 102:
         return 5          # Kp3<17,6,4>  (thread-per-station production kernel)
-    if kmax <= 3 and nmax <= 187:
-        return 1          # Kp2<17,6>
-    if kmax == 4 and nmax <= 125 and min(keeps) == 4:
-        return 2          # Kp2<10,7>
-    return 4              # Kp2<49,7>
+    if nmax <= 128 and min(keeps) == 4:
+        return 6          # Kp3<23,7,4>
+    if nmax <= 153:
+        return 7          # Kp3<27,7,8> (17 separators): keep 1..4
+    return 0
 
 
 def _check(batch, params, variant=None):
@@ -61,7 +62,7 @@ def test_emu_invalid_and_unconstrained_end(oracle_params):
     b["bounds"]["c2_lb"][5] = 1.0
     b["bounds"]["c2_ub"][5] = -1.0      # path 0 invalid (l > u)
     b["end_heading"][1] = 2.0           # path 1: end_psi > 70 deg -> end heading row is free
-    e = emu.solve_batch(oracle_params, b, variant=1)
+    e = emu.solve_batch(oracle_params, b, variant=5)
     o = oracle.solve_batch(oracle_params, 0, b)
     assert e["status"][0] == o["status"][0] == -100
     assert np.all(np.isnan(e["frenet"][:20]))
@@ -73,7 +74,7 @@ def test_emu_max_iter_status(oracle_params):
     p = oracle_params.copy()
     p.max_iter = 50
     b = synth.straight_corridors(1, 30)
-    e = emu.solve_batch(p, b, variant=1)
+    e = emu.solve_batch(p, b, variant=5)
     o = oracle.solve_batch(p, 0, b)
     assert e["status"][0] == o["status"][0]
     assert e["iters"][0] == o["iters"][0] == 50
@@ -85,10 +86,9 @@ def test_emu_generic_core_still_matches(oracle_params):
     _check(synth.curvy_corridors(2, n_points=[33, 70]), oracle_params, variant=0)
 
 
-@pytest.mark.parametrize("variant,n,ds", [(1, 187, 0.3), (2, 125, 0.25), (3, 200, 0.3), (4, 300, 0.3),
-                                           (5, 102, 0.3), (6, 128, 0.25), (6, 77, 0.5), (7, 128, 0.3), (7, 150, 0.3),
+@pytest.mark.parametrize("variant,n,ds", [(8, 187, 0.3), (6, 125, 0.25), (5, 102, 0.3), (6, 128, 0.25), (6, 77, 0.5), (7, 128, 0.3), (7, 150, 0.3),
                                            (8, 200, 0.3), (8, 131, 0.3), (9, 200, 0.25),
-                                           (10, 400, 0.3), (10, 257, 0.3), (10, 408, 0.25),   # thirteen-warp long-path class
+                                           (10, 400, 0.3), (10, 257, 0.3), (10, 408, 0.25), (11, 384, 0.3),   # thirteen- / twelve-warp long-path classes
                                            (0, 400, 0.3)])   # one-warp kernel with its scalings in the global workspace
 def test_emu_shape_classes(oracle_params, variant, n, ds):
     b = synth.curvy_corridors(1, n)
@@ -123,7 +123,7 @@ def test_emu_generic_kernel_k_and_kpc(oracle_params, form):
         np.testing.assert_allclose(e["states"][f], o["states"][f], rtol=0, atol=TOL)
 
 
-@pytest.mark.parametrize("variant", [0, 1, 7])
+@pytest.mark.parametrize("variant", [0, 5, 7])
 def test_emu_primal_infeasible(oracle_params, variant):
     """Corridors with no feasible path: OSQP's primal-infeasibility certificate fires (status -3) at the
     same check iteration as in the oracle, the output is NaN, feasible neighbours are untouched."""
