@@ -248,7 +248,7 @@ def run_reference(args, rank, world):
 class GpuWorkload:
     """One config's shard resident on one GPU + the two timed calls (device-resident, host-buffer)."""
 
-    def __init__(self, config, rank, world, local_rank, torch):
+    def __init__(self, config, rank, world, local_rank, torch, join_comm=True):
         from path_optimizer_b200 import _lib, planner
         self.torch = torch
         self.config, self.rank, self.world = config, rank, world
@@ -297,6 +297,19 @@ class GpuWorkload:
             self.gather_rows = int(t.item())
         self.d_frenet = torch.zeros(self.gather_rows * 3, dtype=torch.float64, device=self.dev)
         self.gathered = torch.zeros(world * self.gather_rows * 3, dtype=torch.float64, device=self.dev) if world > 1 else None
+        self.comm = False
+        if world > 1 and join_comm:
+            # the data-path collective is the library's own (pqp_allgather: NCCL inside libpqp.so); torch.distributed only
+            # carries the 128-byte communicator id and the timing reductions
+            import torch.distributed as dist
+            uid = (C.c_char * 128)()
+            if rank == 0:
+                assert self.L.pqp_nccl_unique_id(uid) == 0, self._lib.last_error()
+            t = torch.tensor(list(bytes(uid)), dtype=torch.uint8, device=self.dev)
+            dist.broadcast(t, 0)
+            uid = (C.c_char * 128).from_buffer_copy(bytes(t.cpu().numpy().tobytes()))
+            assert self.L.pqp_comm_init_rank(self.solver._h, world, rank, uid) == 0, self._lib.last_error()
+            self.comm = True
         self.h_n = np.ascontiguousarray(b["n_points"], dtype=np.int32)
         self._pinned = None
 
@@ -320,10 +333,16 @@ class GpuWorkload:
                                                        self.d_iters.data_ptr(), sp, st)
         assert rc == 0, self._lib.last_error()
 
-    def gather(self):
+    def gather(self, stream=None):
         if self.world > 1:
-            import torch.distributed as dist
-            dist.all_gather_into_tensor(self.gathered, self.d_frenet)
+            if self.comm:
+                sp = C.c_void_p(stream.cuda_stream) if stream is not None else None
+                rc = self.L.pqp_allgather(self.solver._h, self.d_frenet.data_ptr(), self.gathered.data_ptr(),
+                                          self.gather_rows * 3, sp)
+                assert rc == 0, self._lib.last_error()
+            else:
+                import torch.distributed as dist
+                dist.all_gather_into_tensor(self.gathered, self.d_frenet)
 
     # ---- host-buffer call (synchronous)
     def _pin(self):
@@ -344,6 +363,14 @@ class GpuWorkload:
                                     p["x0"].data_ptr(), p["end"].data_ptr(), None, None, p["out"].data_ptr(),
                                     p["frenet"].data_ptr(), p["status"].data_ptr(), p["iters"].data_ptr(), C.byref(stats))
         assert rc == 0, self._lib.last_error()
+
+    def gather_from(self, other):
+        """A gather() for `other` (a workload without a communicator of its own) through this workload's communicator."""
+        def g(stream=None):
+            sp = C.c_void_p(stream.cuda_stream) if stream is not None else None
+            rc = self.L.pqp_allgather(self.solver._h, other.d_frenet.data_ptr(), self.gathered.data_ptr(), self.gather_rows * 3, sp)
+            assert rc == 0, self._lib.last_error()
+        return g
 
     def class_mix(self):
         """{kernel name: paths} as the library selects classes for this shard."""
@@ -369,7 +396,7 @@ def time_workload(w, torch, steps, warmup, flush, stream, barrier, with_e2e=True
     launches = int(st.kernel_launches)
     for _ in range(max(0, warmup - 1)):
         w.solve_device(stream)
-        w.gather()
+        w.gather(stream)
     barrier()
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(steps)]
     barrier()
@@ -379,7 +406,7 @@ def time_workload(w, torch, steps, warmup, flush, stream, barrier, with_e2e=True
         ev[k][0].record(stream)
         w.solve_device(stream)
         ev[k][1].record(stream)
-        w.gather()
+        w.gather(stream)
         ev[k][2].record(stream)
     barrier()
     wall = time.perf_counter() - t0
@@ -462,6 +489,7 @@ def run_ours(args, rank, world, local_rank):
         w0 = GpuWorkload(args.config, 0, 1, local_rank, torch)
         w0.world, w0.gathered, w0.gather_rows = world, w.gathered, w.gather_rows
         w0.d_frenet = w.d_frenet
+        w0.gather = w.gather_from(w0)   # the collective goes through the main workload's communicator
         rc_ = time_workload(w0, torch, max(3, args.steps // 4), 2, flush, stream, barrier, with_e2e=False)
         tc = torch.tensor([rc_["dev_ms"] / max(3, args.steps // 4)], dtype=torch.float64, device=dev)
         dist.all_reduce(tc, op=dist.ReduceOp.MAX)

@@ -55,6 +55,18 @@ int pqp_set_map(pqp_handle *h, const pqp_distance_map *map);
  * the grid, 0 outside the map; result rounded to float like grid_map's atPosition. */
 int pqp_map_distance(pqp_handle *h, int n, const double *xy, double *out);
 
+/* Curvature and curvature-rate limits of the "KPC" formulation from the speed profile carried by the reference
+ * states (v, a fields): friction circle  max_k = sqrt((mu g)^2 - a^2) / v^2  and rate limit
+ * max_kp = max_curvature_rate / v, both DBL_MAX where v <= 1e-4; when the reference states were rebuilt from splines
+ * (`from_spline` != 0: no speed information) max_k = tan(max_steering_angle) / wheel_base and max_kp = DBL_MAX.
+ * g = 9.8 as in the reference.  Host arrays, n entries each (what pqp_solve_batch takes as max_k / max_kp).
+ * pqp_update_limits_device does the same on device arrays of the handle's device, asynchronously on `stream`
+ * (NULL: the handle's stream).  Replaces: ReferencePathImpl::updateLimits (reference_path_impl.cpp:203-235). */
+int pqp_update_limits(const pqp_params *params, int from_spline, int n, const pqp_state *ref,
+                      double *max_k, double *max_kp);
+int pqp_update_limits_device(pqp_handle *h, int from_spline, int n, const pqp_state *d_ref,
+                             double *d_max_k, double *d_max_kp, void *stream);
+
 /* Natural cubic spline through (t_i, y_i), i < n (n >= 3, t strictly increasing), in the
  * piecewise form tk::spline keeps (src/tools/spline.cpp:161-249, default boundary = zero second
  * derivative, quadratic extrapolation):  f(t) = ((a_i h + b_i) h + c_i) h + y_i,  h = t - t_i.

@@ -83,6 +83,8 @@ def lib():
         L.oracle_clearance_strict.restype = None
         L.oracle_update_bounds.argtypes = [pp, dm, C.c_int, C.c_int, vp, C.c_int, vp, vp, vp, vp]
         L.oracle_car_circles.argtypes = [pp, vp]
+        L.oracle_update_limits.argtypes = [pp, C.c_int, C.c_int, vp, vp, vp]
+        L.oracle_update_limits.restype = None
         L.oracle_car_circles.restype = None
         L.oracle_state_collision_free.argtypes = [pp, dm, vp]
         L.oracle_finish_raw.argtypes = [pp, dm, C.c_int, vp, C.c_int, C.POINTER(C.c_int)]
@@ -224,6 +226,14 @@ def update_bounds(params, m, batch, mode=1, splines=None):
                                                 ptr(xc), ptr(yc), ptr(o))
         bounds[off[b]:off[b + 1]] = o
     return dict(bounds=bounds, n_valid=n_valid)
+
+
+def update_limits(params, ref, from_spline=False):
+    """ReferencePathImpl::updateLimits -> (max_k, max_kp)."""
+    ref = np.ascontiguousarray(ref, dtype=STATE_DTYPE)
+    mk, mkp = np.zeros(len(ref)), np.zeros(len(ref))
+    lib().oracle_update_limits(C.byref(params), int(bool(from_spline)), len(ref), ptr(ref), ptr(mk), ptr(mkp))
+    return mk, mkp
 
 
 def car_circles(params):

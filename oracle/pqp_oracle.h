@@ -120,6 +120,8 @@ int oracle_update_bounds(const pqp_params *prm, const pqp_distance_map *map, int
 
 /* CarGeometry circles + CollisionChecker, car_geometry.cpp:38-57, collision_checker.cpp:17-59. */
 void oracle_car_circles(const pqp_params *prm, double c[7][3]);
+/* ReferencePathImpl::updateLimits (reference_path_impl.cpp:203-235) */
+void oracle_update_limits(const pqp_params *prm, int from_spline, int n, const pqp_state *ref, double *max_k, double *max_kp);
 int oracle_state_collision_free(const pqp_params *prm, const pqp_distance_map *map,
                                 const pqp_state *s);
 

@@ -427,3 +427,24 @@ int oracle_plan_path(const pqp_params *prm, const pqp_distance_map *map, int for
     free(bounds);
     return ok;
 }
+
+/* ReferencePathImpl::updateLimits, reference_path_impl.cpp:203-235: curvature and curvature-rate limits of the KPC
+ * formulation from the speed profile (v, a) of the reference states; from_spline = the use_spline_ branch (:214-221). */
+void oracle_update_limits(const pqp_params *prm, int from_spline, int n, const pqp_state *ref, double *max_k, double *max_kp) {
+    for (int i = 0; i < n; ++i) {
+        if (from_spline) {
+            max_k[i] = tan(prm->max_steering_angle) / prm->wheel_base;
+            max_kp[i] = 1.7976931348623157e308; /* DBL_MAX */
+            continue;
+        }
+        /* Friction circle limit. */
+        double ref_v = ref[i].v;
+        double ref_ax = ref[i].a;
+        double ay_allowed = sqrt(pow(prm->mu * 9.8, 2) - pow(ref_ax, 2));
+        if (ref_v > 0.0001) max_k[i] = ay_allowed / pow(ref_v, 2);
+        else max_k[i] = 1.7976931348623157e308;
+        /* Control rate limit. */
+        if (ref_v > 0.0001) max_kp[i] = prm->max_curvature_rate / ref_v;
+        else max_kp[i] = 1.7976931348623157e308;
+    }
+}

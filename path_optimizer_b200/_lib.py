@@ -14,9 +14,13 @@ SYMBOLS = ["pqp_params_default", "pqp_params_update_config", "pqp_keep_control_s
            "pqp_solve_batch_device_classes", "pqp_last_error", "pqp_version", "pqp_max_points", "pqp_max_points_keep",
            "pqp_class_info", "pqp_class_name", "pqp_device_class_info"]
 # ... and include/pqp_env.h
-ENV_SYMBOLS = ["pqp_set_map", "pqp_map_distance", "pqp_spline_fit", "pqp_spline_eval", "pqp_update_bounds_batch",
+ENV_SYMBOLS = ["pqp_update_limits", "pqp_update_limits_device", "pqp_set_map", "pqp_map_distance", "pqp_spline_fit", "pqp_spline_eval", "pqp_update_bounds_batch",
                "pqp_check_states", "pqp_finish_raw_batch", "pqp_densify_batch", "pqp_plan_batch"]
-SYMBOLS = SYMBOLS + ENV_SYMBOLS
+# ... and include/pqp_multi.h
+MULTI_SYMBOLS = ["pqp_nccl_unique_id", "pqp_comm_init_rank", "pqp_allgather", "pqp_comm_destroy", "pqp_multi_create",
+                 "pqp_multi_destroy", "pqp_multi_devices", "pqp_multi_solve_batch", "pqp_multi_gathered",
+                 "pqp_multi_gather_rows", "pqp_multi_shard"]
+SYMBOLS = SYMBOLS + ENV_SYMBOLS + MULTI_SYMBOLS
 
 _lib = None
 
@@ -51,6 +55,8 @@ def load():
     L.pqp_device_class_info.argtypes = [C.c_int] * 4 + [C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int64)]
     L.pqp_solve_batch_device_classes.argtypes = [vp] + [C.c_int] * 3 + [vp] * 15 + [C.POINTER(Stats)]
     # include/pqp_env.h
+    L.pqp_update_limits.argtypes = [C.POINTER(Params), C.c_int, C.c_int, vp, vp, vp]
+    L.pqp_update_limits_device.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, vp]
     L.pqp_set_map.argtypes = [vp, C.POINTER(DistanceMap)]
     L.pqp_map_distance.argtypes = [vp, C.c_int, vp, vp]
     L.pqp_spline_fit.argtypes = [C.c_int, vp, vp, vp]
@@ -62,6 +68,21 @@ def load():
     L.pqp_densify_batch.argtypes = [vp, C.c_int, vp, vp, C.c_double, C.c_int, C.c_int, vp, vp, vp, C.POINTER(Stats)]
     L.pqp_plan_batch.argtypes = ([vp, C.c_int, C.c_int, C.c_int, C.c_int] + [vp] * 8 +
                                  [C.c_double, C.c_int, C.c_int] + [vp] * 6 + [C.POINTER(Stats)])
+    # include/pqp_multi.h
+    L.pqp_nccl_unique_id.argtypes = [vp]
+    L.pqp_comm_init_rank.argtypes = [vp, C.c_int, C.c_int, vp]
+    L.pqp_allgather.argtypes = [vp, vp, vp, C.c_int64, vp]
+    L.pqp_comm_destroy.argtypes = [vp]
+    L.pqp_multi_create.argtypes = [C.POINTER(vp), C.POINTER(Params), C.c_int, vp, C.c_int, C.c_int]
+    L.pqp_multi_destroy.argtypes = [vp]
+    L.pqp_multi_destroy.restype = None
+    L.pqp_multi_devices.argtypes = [vp]
+    L.pqp_multi_solve_batch.argtypes = [vp, C.c_int, C.c_int] + [vp] * 9 + [C.c_int, C.POINTER(Stats)]
+    L.pqp_multi_gathered.argtypes = [vp, C.c_int]
+    L.pqp_multi_gathered.restype = vp
+    L.pqp_multi_gather_rows.argtypes = [vp]
+    L.pqp_multi_gather_rows.restype = C.c_int64
+    L.pqp_multi_shard.argtypes = [vp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int64)]
     _lib = L
     return L
 

@@ -53,7 +53,7 @@ def build(force=False, verbose=False, jobs=None):
         for _, log in results:
             print(log, end="")
     objs = [o for o, _ in results]
-    subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB_PATH] + objs, check=True)
+    subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB_PATH] + objs + ["-ldl"], check=True)
     return LIB_PATH
 
 

@@ -29,14 +29,14 @@ namespace {
 // keep_control_steps <= 4 (station spacing >= 0.24 m) and up to 408 stations map onto one of the thread-per-station
 // (Kp3) instantiations; anything else runs on the one-warp generic kernel (last).
 typedef PqpVariant Variant;
-constexpr int kNumVariants = 10;
+constexpr int kNumVariants = 9;
 struct VariantTable {
     Variant v[kNumVariants];
     VariantTable() {
         int k = 0;
-        pqp_variant_k3_17_6_4_17(&v[k++]); pqp_variant_k3_23_7_4_17(&v[k++]); pqp_variant_k3_27_7_4_17(&v[k++]);
+        pqp_variant_k3_17_6_4_17(&v[k++]); pqp_variant_k3_23_7_4_17(&v[k++]);
         pqp_variant_k3_17_6_8_34(&v[k++]); pqp_variant_k3_23_7_8_34(&v[k++]); pqp_variant_k3_27_7_8_34(&v[k++]);
-        pqp_variant_k3_37_7_8_17(&v[k++]); pqp_variant_k3_37_7_12_34(&v[k++]); pqp_variant_k3_37_7_13_34(&v[k++]);
+        pqp_variant_k3_27_7_10_34(&v[k++]); pqp_variant_k3_37_7_12_34(&v[k++]); pqp_variant_k3_37_7_13_34(&v[k++]);
         pqp_variant_k1_generic(&v[k++]);
     }
 };
@@ -265,9 +265,12 @@ int pqp_problem_size(int formulation, int n, int keep, int *n_var, int *n_con) {
     }
 }
 
+extern "C" int pqp_comm_destroy(pqp_handle *h);   // pqp_multi.cu
+
 void pqp_destroy(pqp_handle *h) {
     if (!h) return;
     cudaSetDevice(h->device);
+    if (h->nccl_comm) pqp_comm_destroy(h);
     cudaFree(h->d_n); cudaFree(h->d_off); cudaFree(h->d_order); cudaFree(h->d_status); cudaFree(h->d_iters);
     cudaFree(h->d_ref); cudaFree(h->d_out); cudaFree(h->d_bounds);
     cudaFree(h->d_x0); cudaFree(h->d_end); cudaFree(h->d_frenet); cudaFree(h->d_ws);
@@ -346,6 +349,7 @@ int pqp_create(pqp_handle **out, const pqp_params *params, int device, int max_b
     PQP_TRY(cudaMalloc(&h->d_x0, B * 3 * sizeof(double)));
     PQP_TRY(cudaMalloc(&h->d_end, B * sizeof(double)));
     PQP_TRY(cudaMalloc(&h->d_frenet, T * 3 * sizeof(double)));
+    PQP_TRY(cudaMemset(h->d_frenet, 0, T * 3 * sizeof(double)));   // (padded rows of a multi-GPU gather read as zeros)
     PQP_TRY(cudaMalloc(&h->d_ws, pqp::kp2_ws_doubles(T, B) * sizeof(double)));
     PQP_TRY(cudaMallocHost(&h->h_off, (B + 1) * sizeof(int32_t)));
     PQP_TRY(cudaMallocHost(&h->h_order, B * sizeof(int32_t)));
@@ -734,7 +738,7 @@ int pqp_solve_batch(pqp_handle *h, int formulation, int batch, const int32_t *n_
     pqp::BatchView bv;
     bv.batch = batch; bv.n_points = h->d_n; bv.offsets = h->d_off; bv.ref = h->d_ref; bv.bounds = h->d_bounds;
     bv.x0 = h->d_x0; bv.end_heading = h->d_end; bv.out_states = h->d_out;
-    bv.out_frenet = out_frenet ? h->d_frenet : nullptr;
+    bv.out_frenet = (out_frenet || h->force_frenet) ? h->d_frenet : nullptr;
     bv.status = h->d_status; bv.iters = h->d_iters;
     bv.workspace = h->d_ws;
     bv.debug = nullptr;
@@ -753,7 +757,10 @@ int pqp_solve_batch(pqp_handle *h, int formulation, int batch, const int32_t *n_
     bool ev1_done = false;
     // Once copies into the caller's buffers are in flight, no error return may leave them running: both lanes are
     // drained first (PQP_CUDA_DRAIN = PQP_CUDA with that drain).
-    auto drain = [&]() { cudaStreamSynchronize(sts[0]); cudaStreamSynchronize(sts[1]); };
+    auto drain = [&]() {
+        cudaStreamSynchronize(sts[0]); cudaStreamSynchronize(sts[1]);
+        for (auto &q : h->cls_stream) cudaStreamSynchronize(q);
+    };
 #define PQP_CUDA_DRAIN(call)                                                 \
     do {                                                                     \
         cudaError_t e_ = (call);                                             \
@@ -782,11 +789,28 @@ int pqp_solve_batch(pqp_handle *h, int formulation, int batch, const int32_t *n_
         PQP_CUDA_DRAIN(cudaMemcpyAsync(h->d_x0 + 3 * (size_t)pb, x0 + 3 * (size_t)pb, nB * 3 * sizeof(double), cudaMemcpyHostToDevice, st));
         PQP_CUDA_DRAIN(cudaMemcpyAsync(h->d_end + pb, end_heading + pb, nB * sizeof(double), cudaMemcpyHostToDevice, st));
         if (!ev1_done) { PQP_CUDA_DRAIN(cudaEventRecord(h->ev[1], st)); ev1_done = true; }
-        for (int v = 0; v < kNumVariants; ++v) {
+        // One launch per class of the chunk; a mixed-length chunk has several: they go out on the class lanes (forked
+        // after the chunk's upload, joined before its download), longest class first, so that they overlap instead of
+        // each waiting for the tail of the one before.
+        int n_cls = 0;
+        for (int v = 0; v < kNumVariants; ++v) n_cls += count_cv[k][v] > 0;
+        if (n_cls > 1) PQP_CUDA_DRAIN(cudaEventRecord(h->ev_fork, st));
+        int lane = 0;
+        for (int v = kNumVariants - 1; v >= 0; --v) {
             if (!count_cv[k][v]) continue;
-            int rc = launch_variant(h, v, bv, count_cv[k][v], h->d_order + start_cv[k][v], smem_cv[k][v], st);
+            cudaStream_t cs = st;
+            if (n_cls > 1) {
+                cs = h->cls_stream[lane % PQP_CLASS_LANES];
+                PQP_CUDA_DRAIN(cudaStreamWaitEvent(cs, h->ev_fork, 0));
+                ++lane;
+            }
+            int rc = launch_variant(h, v, bv, count_cv[k][v], h->d_order + start_cv[k][v], smem_cv[k][v], cs);
             if (rc != PQP_OK) { drain(); return rc; }
             ++launches;
+        }
+        for (int j = 0; j < std::min(lane, PQP_CLASS_LANES); ++j) {
+            PQP_CUDA_DRAIN(cudaEventRecord(h->ev_cls[j], h->cls_stream[j]));
+            PQP_CUDA_DRAIN(cudaStreamWaitEvent(st, h->ev_cls[j], 0));
         }
         PQP_CUDA_DRAIN(cudaEventRecord(h->ev_chunk[1 + k], st));   // this chunk's kernels done
         PQP_CUDA_DRAIN(cudaMemcpyAsync(out_states + o0, h->d_out + o0, nT * sizeof(pqp_state), cudaMemcpyDeviceToHost, st));
@@ -803,6 +827,10 @@ int pqp_solve_batch(pqp_handle *h, int formulation, int batch, const int32_t *n_
     PQP_CUDA_DRAIN(cudaEventRecord(h->ev_chunk[kMaxChunks + 1], sts[1]));
     PQP_CUDA_DRAIN(cudaStreamWaitEvent(sts[0], h->ev_chunk[kMaxChunks + 1], 0));
     PQP_CUDA_DRAIN(cudaEventRecord(h->ev[3], sts[0]));
+    if (h->defer_sync) {   // pqp_multi_solve_batch: every device is enqueued first, the caller synchronises (and has passed `iters`)
+        h->deferred_launches = launches;
+        return PQP_OK;
+    }
     PQP_CUDA(cudaStreamSynchronize(sts[0]));
 #undef PQP_CUDA_DRAIN
 #ifdef PQP_PHASE_TIMING

@@ -449,6 +449,54 @@ int pqp_update_bounds_batch(pqp_handle *h, int mode, int batch, const int32_t *n
     return PQP_OK;
 }
 
+// ReferencePathImpl::updateLimits, reference_path_impl.cpp:221-233.  Products and differences are rounded one by one
+// (no contraction into fused multiply-adds) so that host, device and the reference's own sequence agree bit for bit.
+static __host__ __device__ inline void limits_of(double mu, double rate, double v, double a, double *mk, double *mkp) {
+#ifdef __CUDA_ARCH__
+    const double ay2 = __dsub_rn(__dmul_rn(mu * 9.8, mu * 9.8), __dmul_rn(a, a));
+    const double v2 = __dmul_rn(v, v);
+#else
+    volatile double t1 = (mu * 9.8) * (mu * 9.8), t2 = a * a;
+    const double ay2 = t1 - t2;
+    volatile double v2v = v * v;
+    const double v2 = v2v;
+#endif
+    const double ay = sqrt(ay2);
+    *mk = (v > 0.0001) ? ay / v2 : 1.7976931348623157e308;
+    *mkp = (v > 0.0001) ? rate / v : 1.7976931348623157e308;
+}
+
+__global__ void pqp_limits_kernel(double mu, double rate, double kmax, int from_spline, int n, const pqp_state *ref,
+                                  double *max_k, double *max_kp) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (from_spline) { max_k[i] = kmax; max_kp[i] = 1.7976931348623157e308; return; }
+    limits_of(mu, rate, ref[i].v, ref[i].a, max_k + i, max_kp + i);
+}
+
+int pqp_update_limits(const pqp_params *params, int from_spline, int n, const pqp_state *ref, double *max_k, double *max_kp) {
+    if (!params || n < 0 || (n > 0 && (!ref || !max_k || !max_kp))) { pqp_set_err("pqp_update_limits: bad argument"); return PQP_ERR_ARG; }
+    const double kmax = tan(params->max_steering_angle) / params->wheel_base;
+    for (int i = 0; i < n; ++i) {
+        if (from_spline) { max_k[i] = kmax; max_kp[i] = 1.7976931348623157e308; }
+        else limits_of(params->mu, params->max_curvature_rate, ref[i].v, ref[i].a, max_k + i, max_kp + i);
+    }
+    return PQP_OK;
+}
+
+int pqp_update_limits_device(pqp_handle *h, int from_spline, int n, const pqp_state *d_ref, double *d_max_k, double *d_max_kp,
+                             void *stream) {
+    if (!h || n < 0 || (n > 0 && (!d_ref || !d_max_k || !d_max_kp))) { pqp_set_err("pqp_update_limits_device: bad argument"); return PQP_ERR_ARG; }
+    if (n == 0) return PQP_OK;
+    PQP_CUDA(cudaSetDevice(h->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    const double kmax = tan(h->params.max_steering_angle) / h->params.wheel_base;
+    pqp_limits_kernel<<<(n + 255) / 256, 256, 0, st>>>(h->params.mu, h->params.max_curvature_rate, kmax, from_spline, n, d_ref,
+                                                       d_max_k, d_max_kp);
+    PQP_CUDA(cudaGetLastError());
+    return PQP_OK;
+}
+
 int pqp_check_states(pqp_handle *h, int n, const pqp_state *states, int32_t *ok) {
     if (!h || n < 0 || (n > 0 && (!states || !ok))) { pqp_set_err("pqp_check_states: bad argument"); return PQP_ERR_ARG; }
     EnvState *e;

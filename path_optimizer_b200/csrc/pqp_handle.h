@@ -28,6 +28,12 @@ struct pqp_handle {
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaStream_t cls_stream[PQP_CLASS_LANES] = {};  // lanes for the per-class launches of a mixed-length batch
     cudaEvent_t ev_fork = nullptr, ev_cls[PQP_CLASS_LANES] = {};
+    // pqp_multi_solve_batch enqueues the host-buffer call on every device before synchronising any
+    bool defer_sync = false;
+    bool force_frenet = false;       // keep the Frenet states on the device even when the caller passes no host buffer
+    int deferred_launches = 0;
+    // NCCL communicator bound to this handle's device (pqp_multi.cu; void*: nccl.h stays out of this header)
+    void *nccl_comm = nullptr;
     // cached choice of pqp_solve_batch_device for (max_n_points, min_keep, max_keep)
     int dc_nmax = -1, dc_klo = -1, dc_khi = -1, dc_skip = -1, dc_v = -1;
     size_t dc_smem = 0;

@@ -17,11 +17,10 @@ struct PqpVariant {
 // thread-per-station kernels Kp3<IMAX, BW, NW, MMAX>
 PQP_DECLARE_VARIANT(k3_17_6_4_17)
 PQP_DECLARE_VARIANT(k3_23_7_4_17)
-PQP_DECLARE_VARIANT(k3_27_7_4_17)
 PQP_DECLARE_VARIANT(k3_17_6_8_34)
 PQP_DECLARE_VARIANT(k3_23_7_8_34)
 PQP_DECLARE_VARIANT(k3_27_7_8_34)
-PQP_DECLARE_VARIANT(k3_37_7_8_17)
+PQP_DECLARE_VARIANT(k3_27_7_10_34)
 PQP_DECLARE_VARIANT(k3_37_7_12_34)
 PQP_DECLARE_VARIANT(k3_37_7_13_34)
 // one-warp generic KP kernel (any keep <= 10) and the generic banded-QP kernel of "K" / "KPC"

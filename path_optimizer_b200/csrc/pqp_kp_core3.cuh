@@ -66,8 +66,7 @@ struct Kp3 {
     // Long-path classes (more than eight warps: up to 416 stations, 37-unknown interiors) need every byte of the
     // 227 KB a CTA can opt into: their refactorisation scratch is overlaid on the rhs / y vectors (free while a
     // refactorisation runs; both are zeroed again at its end so that the padded entries stay finite).
-    static constexpr bool kScratchOnVec = !kDense && (NW > 8);
-    static_assert(!kScratchOnVec || (kTwoLevel && 2 * ((IMAX + 3) | 1) >= kRed2 + 27 + 12), "scratch must fit in the two solve vectors");
+    static constexpr bool kScratchOnVec = !kDense && (NW > 8) && kTwoLevel && (2 * ((IMAX + 3) | 1) >= kRed2 + 27 + 12);
     // exchange rows of kT doubles: 0..5, ds, separator rhs; the long-path classes park the separator rhs in row 5
     // (only the Ruiz sweeps and diagnostic builds use that row otherwise)
     static constexpr int kExRows = kScratchOnVec ? 7 : 8;

@@ -23,6 +23,17 @@ BOUNDS_IMPROVED, BOUNDS_SIMPLE = 0, 1
 OUTPUT_RAW, OUTPUT_DENSIFY = 0, 1
 
 
+def update_limits(params, ref, from_spline=False):
+    """ReferencePathImpl::updateLimits (reference_path_impl.cpp:203-235): (max_k, max_kp) of the KPC formulation from the
+    v, a fields of the reference states.  Host helper of libpqp.so."""
+    ref = np.ascontiguousarray(ref, dtype=STATE_DTYPE)
+    mk, mkp = np.zeros(len(ref)), np.zeros(len(ref))
+    rc = _lib.load().pqp_update_limits(C.byref(params), int(bool(from_spline)), len(ref), ptr(ref), ptr(mk), ptr(mkp))
+    if rc != OK:
+        raise PqpError(f"pqp_update_limits failed (rc={rc}): {_lib.last_error()}")
+    return mk, mkp
+
+
 def spline_fit(t, y):
     """Natural cubic spline coefficients [n, 4] = (a, b, c, y) per knot (tk::spline layout)."""
     t = np.ascontiguousarray(t, dtype=np.float64)

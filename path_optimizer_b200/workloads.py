@@ -44,7 +44,7 @@ def describe(config, world=1):
         "n_gpus": world,
         "seed": synth.BASE_SEED,
         "l2": "GPU arm: L2 flushed between timed steps (256 MiB fill); CPU arm: not applicable",
-        "multi_gpu": "independent shards, one NCCL all-gather of the Frenet states per step" if world > 1 else "single GPU",
+        "multi_gpu": "independent shards, one NCCL all-gather of the Frenet states per step (pqp_allgather: NCCL inside libpqp.so)" if world > 1 else "single GPU",
     }
 
 

@@ -47,7 +47,7 @@ def lib():
 
 def solve_batch(params, batch, smem_bytes=227 * 1024, variant=0, nwarps=4):
     """variant 0 = one-warp generic core (pqp_kp_core.cuh); 5..7 = Kp3<17,6,4>, <23,7,4>, <27,7,8>; 8, 9 = the 34-separator eight-warp classes Kp3<17,6,8,34>, <23,7,8,34>;
-    10, 11 = the long-path classes Kp3<37,7,13,34>, <37,7,12,34>."""
+    10, 11, 12 = the long-path classes Kp3<37,7,13,34>, <37,7,12,34>, <27,7,10,34>."""
     B = len(batch["n_points"])
     total = int(batch["offsets"][-1])
     ref = np.ascontiguousarray(batch["ref"], dtype=STATE_DTYPE)

@@ -36,6 +36,7 @@ void *lane_main(void *p) {
     case 9: pqp::Kp3<23, 7, 8, 34>::solve_path(c, *a->prm, *a->bv, a->prob, sm, cap); break;
     case 10: pqp::Kp3<37, 7, 13, 34>::solve_path(c, *a->prm, *a->bv, a->prob, sm, cap); break;
     case 11: pqp::Kp3<37, 7, 12, 34>::solve_path(c, *a->prm, *a->bv, a->prob, sm, cap); break;
+    case 12: pqp::Kp3<27, 7, 10, 34>::solve_path(c, *a->prm, *a->bv, a->prob, sm, cap); break;
     default: pqp::kp_solve_path(w, *a->prm, *a->bv, a->prob, sm, cap);   // generic core: one warp
     }
     return nullptr;
@@ -52,6 +53,7 @@ extern "C" int kp_emu_solve_batch(const pqp_params *params, int batch, const int
     if (variant >= 7) nwarps = 8;
     if (variant == 10) nwarps = 13;
     if (variant == 11) nwarps = 12;
+    if (variant == 12) nwarps = 10;
     pqp::DevParams prm = pqp::dev_params_from(*params);
     pqp::BatchView bv;
     bv.batch = batch; bv.n_points = n_points; bv.offsets = offsets; bv.ref = ref; bv.bounds = bounds;

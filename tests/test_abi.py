@@ -22,7 +22,7 @@ def L():
 
 
 def test_exports_every_declared_symbol(L):
-    header = open(os.path.join(ROOT, "include", "pqp.h")).read() + open(os.path.join(ROOT, "include", "pqp_env.h")).read()
+    header = "".join(open(os.path.join(ROOT, "include", f)).read() for f in ("pqp.h", "pqp_env.h", "pqp_multi.h"))
     declared = set(re.findall(r"\b(pqp_[a-z_]+)\s*\(", header))
     assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
     for sym in declared:

@@ -25,7 +25,8 @@ def test_every_baseline_length_runs_thread_per_station():
             assert threads >= n and smem <= 232448
     assert _class(100, 3)[1] == "pqp_kp3_solve_kernel<17,6,4,17>"
     assert _class(200, 3)[1] == "pqp_kp3_solve_kernel<17,6,8,34>"
-    assert _class(300, 3)[1] == "pqp_kp3_solve_kernel<37,7,12,34>"
+    assert _class(300, 3)[1] == "pqp_kp3_solve_kernel<27,7,10,34>"
+    assert _class(350, 3)[1] == "pqp_kp3_solve_kernel<37,7,12,34>"
     assert _class(400, 3)[1] == "pqp_kp3_solve_kernel<37,7,13,34>"
 
 

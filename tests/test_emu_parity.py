@@ -88,7 +88,7 @@ def test_emu_generic_core_still_matches(oracle_params):
 
 @pytest.mark.parametrize("variant,n,ds", [(8, 187, 0.3), (6, 125, 0.25), (5, 102, 0.3), (6, 128, 0.25), (6, 77, 0.5), (7, 128, 0.3), (7, 150, 0.3),
                                            (8, 200, 0.3), (8, 131, 0.3), (9, 200, 0.25),
-                                           (10, 400, 0.3), (10, 257, 0.3), (10, 408, 0.25), (11, 384, 0.3),   # thirteen- / twelve-warp long-path classes
+                                           (10, 400, 0.3), (10, 257, 0.3), (10, 408, 0.25), (11, 384, 0.3), (12, 300, 0.3),   # thirteen- / twelve- / ten-warp long-path classes
                                            (0, 400, 0.3)])   # one-warp kernel with its scalings in the global workspace
 def test_emu_shape_classes(oracle_params, variant, n, ds):
     b = synth.curvy_corridors(1, n)

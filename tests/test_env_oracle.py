@@ -321,3 +321,28 @@ def test_config1_reference_benchmark_case():
     assert np.abs(k["states"]["x"] - g["plan_improved_states"]["x"]).max() <= 1e-9
     # the optimized path stays clear of the obstacles and inside the corridor it was given
     assert oracle.check_states(p, field, pl["states"]).all()
+
+
+def test_update_limits_host_matches_oracle_bit_for_bit(oracle_params):
+    """ReferencePathImpl::updateLimits (reference_path_impl.cpp:203-235): friction circle and rate limit from (v, a),
+    DBL_MAX at standstill, the use_spline_ branch, and a hand-computed value.  The library's host helper needs no GPU."""
+    from path_optimizer_b200 import planner
+    from path_optimizer_b200.abi import STATE_DTYPE
+    rng = np.random.default_rng(5)
+    ref = np.zeros(400, dtype=STATE_DTYPE)
+    ref["v"] = rng.uniform(0.0, 12.0, 400)
+    ref["a"] = rng.uniform(-3.0, 3.0, 400)
+    ref["v"][:4] = [0.0, 1e-4, 1.0000001e-4, 5.0]
+    ref["a"][3] = 1.0
+    ref["a"][10] = 4.5      # beyond mu g = 3.92: sqrt of a negative number, NaN like the reference
+    mk, mkp = planner.update_limits(oracle_params, ref)
+    omk, omkp = oracle.update_limits(oracle_params, ref)
+    assert np.array_equal(mk, omk, equal_nan=True) and np.array_equal(mkp, omkp)
+    assert mk[0] == mk[1] == np.finfo(np.float64).max and mkp[0] == np.finfo(np.float64).max
+    assert np.isnan(mk[10]) and np.isfinite(mk[2])
+    assert mk[3] == np.sqrt((0.4 * 9.8) ** 2 - 1.0) / 25.0 and mkp[3] == 0.1 / 5.0
+    smk, smkp = planner.update_limits(oracle_params, ref, from_spline=True)
+    osk, oskp = oracle.update_limits(oracle_params, ref, from_spline=True)
+    assert np.array_equal(smk, osk) and np.array_equal(smkp, oskp)
+    assert (smk == np.tan(oracle_params.max_steering_angle) / oracle_params.wheel_base).all()
+    assert (smkp == np.finfo(np.float64).max).all()

@@ -189,10 +189,26 @@ def test_k_and_kpc_formulations(solver, oracle_params, form, name):
     total = int(n_points.sum())
     mk = mkp = None
     if form == 2:
-        v = 4.0 + 3.0 * np.sin(np.arange(total) * 0.05)
-        a = 0.5 * np.cos(np.arange(total) * 0.05)
-        mk = np.sqrt((0.4 * 9.8) ** 2 - a ** 2) / v ** 2      # reference_path_impl.cpp:224-231
-        mkp = 0.1 / v
+        # KPC limits from a speed profile on the reference states, derived on the DEVICE by the library's restatement of
+        # ReferencePathImpl::updateLimits (reference_path_impl.cpp:203-235) and checked against the oracle's bit for bit
+        import ctypes as C
+        import torch
+        from path_optimizer_b200 import _lib
+        from path_optimizer_b200.abi import STATE_DTYPE
+        b["ref"]["v"] = 4.0 + 3.0 * np.sin(np.arange(total) * 0.05)
+        b["ref"]["a"] = 0.5 * np.cos(np.arange(total) * 0.05)
+        b["ref"]["v"][7] = 0.0     # standstill: DBL_MAX limits (rows free on that side)
+        d_ref = torch.from_numpy(np.frombuffer(np.ascontiguousarray(b["ref"], dtype=STATE_DTYPE).tobytes(), dtype=np.uint8).copy()).cuda()
+        d_mk = torch.zeros(total, dtype=torch.float64, device="cuda")
+        d_mkp = torch.zeros(total, dtype=torch.float64, device="cuda")
+        torch.cuda.synchronize()
+        rc = _lib.load().pqp_update_limits_device(solver._h, 0, total, d_ref.data_ptr(), d_mk.data_ptr(), d_mkp.data_ptr(), None)
+        assert rc == 0, _lib.last_error()
+        torch.cuda.synchronize()
+        mk, mkp = d_mk.cpu().numpy(), d_mkp.cpu().numpy()
+        omk, omkp = oracle.update_limits(oracle_params, b["ref"])
+        assert np.array_equal(mk, omk) and np.array_equal(mkp, omkp)
+        assert mk[7] == np.finfo(np.float64).max
     res = solver.solve(b, formulation=name, max_k=mk, max_kp=mkp)
     ref = oracle.solve_batch(oracle_params, form, b, threads=8, max_k=mk, max_kp=mkp)
     _compare(res, ref)
