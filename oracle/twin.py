@@ -115,6 +115,152 @@ def assemble_kp(prm, ref, bounds, x0, end_heading):
     return H, np.zeros(n), cons, lo, up
 
 
+def assemble_k(prm, ref, bounds, x0, end_heading):
+    """solver_k_as_input.cpp:14-207 in dense-block style (its own Eigen block fills, one numpy statement each).
+    Variables [(e_phi, e_y)_i ; delta_i ; slack_i]; returns (P, q, A, l, u) dense."""
+    N = len(ref)
+    state, control, slack = 2 * N, N - 1, N
+    n, m = 4 * N - 1, 11 * N - 1
+    w_c, w_cr, w_pq, w_e = prm.K_curvature_weight, prm.K_curvature_rate_weight, prm.K_deviation_weight, prm.KP_slack_weight
+    H = np.zeros((n, n))
+    Q = np.array([[0.0, 0.0], [0.0, w_pq]])
+    R = np.zeros((control, control))
+    for i in range(control):            # :60-72
+        for j in range(control):
+            if i == j:
+                R[i, j] = (w_c + w_cr) if (i == 0 or i == control - 1) else (w_cr * 2 + w_c)
+            elif i == j - 1 or i == j + 1:
+                R[i, j] = -w_cr
+    for i in range(N):
+        H[2 * i:2 * i + 2, 2 * i:2 * i + 2] = Q
+    H[2 * N:2 * N + control, 2 * N:2 * N + control] = R
+    H[3 * N - 1:3 * N - 1 + slack, 3 * N - 1:3 * N - 1 + slack] = np.eye(slack) * w_e
+    cons = np.zeros((m, n))
+    cons[np.arange(2 * N), np.arange(2 * N)] = -1                      # :112-114
+    lo = np.zeros(m); up = np.zeros(m)
+    for i in range(N - 1):                                              # setDynamicMatrix :89-103
+        ref_k = float(ref["k"][i])
+        ref_s = float(ref["s"][i + 1]) - float(ref["s"][i])
+        ref_delta = np.arctan(ref_k * prm.wheel_base)
+        a = np.array([[1.0, -ref_s * ref_k ** 2], [ref_s, 1.0]])
+        b = np.array([ref_s / prm.wheel_base / np.cos(ref_delta) ** 2, 0.0])
+        cons[2 * (i + 1):2 * (i + 1) + 2, 2 * i:2 * i + 2] = a
+        cons[2 * (i + 1):2 * (i + 1) + 2, 2 * N + i] = b
+    cons[2 * N + np.arange(n), np.arange(n)] = 1                         # :124-126
+    coll = np.array([[prm.d1, 1.0], [prm.d3, 1.0], [prm.d4, 1.0]])       # :129-136
+    for i in range(N):
+        cons[6 * N - 1 + 3 * i:6 * N - 1 + 3 * i + 3, 2 * i:2 * i + 2] = coll
+        cons[9 * N - 1 + i, 2 * i:2 * i + 2] = [prm.d2, 1.0]
+        cons[10 * N - 1 + i, 2 * i:2 * i + 2] = [prm.d2, 1.0]
+    cons[9 * N - 1:10 * N - 1, 3 * N - 1:4 * N - 1] = -np.eye(N)
+    cons[10 * N - 1:11 * N - 1, 3 * N - 1:4 * N - 1] = np.eye(N)
+    # bounds :151-206
+    lo[0:2] = [-x0[1], -x0[0]]; up[0:2] = lo[0:2]
+    for i in range(N - 1):
+        ds = float(ref["s"][i + 1]) - float(ref["s"][i])
+        steer = np.arctan(float(ref["k"][i]) * prm.wheel_base)
+        c = ds * steer / prm.wheel_base / np.cos(steer) ** 2
+        lo[2 + 2 * i], up[2 + 2 * i] = c, c
+    lo[2 * N:4 * N] = -INFTY; up[2 * N:4 * N] = INFTY
+    if prm.constraint_end_heading:
+        end_psi = constraint_angle(end_heading - float(ref["z"][-1]))
+        if end_psi < 70 * np.pi / 180:
+            lo[2 * N + 2 * N - 2] = end_psi - 5 * np.pi / 180
+            up[2 * N + 2 * N - 2] = end_psi + 5 * np.pi / 180
+    lo[4 * N:5 * N - 1] = -prm.max_steering_angle; up[4 * N:5 * N - 1] = prm.max_steering_angle
+    lo[5 * N - 1:6 * N - 1] = 0; up[5 * N - 1:6 * N - 1] = prm.expected_safety_margin
+    for i in range(N):
+        bd = bounds[i]
+        up[6 * N - 1 + 3 * i:6 * N - 1 + 3 * i + 3] = [bd["c0_ub"], bd["c2_ub"], bd["c3_ub"]]
+        lo[6 * N - 1 + 3 * i:6 * N - 1 + 3 * i + 3] = [bd["c0_lb"], bd["c2_lb"], bd["c3_lb"]]
+        up[9 * N - 1 + i] = bd["c1_ub"] - prm.expected_safety_margin
+        lo[10 * N - 1 + i] = bd["c1_lb"] + prm.expected_safety_margin
+    up[10 * N - 1:11 * N - 1] = INFTY
+    lo[9 * N - 1:10 * N - 1] = -INFTY
+    return H, np.zeros(n), cons, lo, up
+
+
+def assemble_kpc(prm, ref, bounds, x0, end_heading, max_k, max_kp):
+    """solver_kp_as_input_constrained.cpp:13-221 in dense-block style.  keep_control_steps_ = 4 (:17).
+    Returns (P, q, A, l, u) dense."""
+    N = len(ref)
+    keep = 4
+    ch = (N + keep - 2) // keep
+    ns, nc, nsl = 3 * N, ch, 3 * N
+    n, m = ns + nc + nsl, 12 * N + 3 * ch + 2
+    H = np.zeros((n, n))
+    w_k_slack, w_kp_slack = 500.0, 25000.0
+    for i in range(N):                                                   # :54-59
+        H[3 * i, 3 * i] += prm.KP_deviation_weight
+        H[3 * i + 2, 3 * i + 2] += prm.KP_curvature_weight
+        H[ns + nc + i, ns + nc + i] += prm.KP_slack_weight
+        H[ns + nc + N + i, ns + nc + N + i] += w_k_slack
+    for j in range(ch):                                                  # :60-64
+        H[ns + j, ns + j] += keep * prm.KP_curvature_rate_weight
+        H[ns + nc + 2 * N + j, ns + nc + 2 * N + j] += w_kp_slack * keep
+    kl_b = 3 * N; ku_b = kl_b + N; kpl_b = ku_b + N; kpu_b = kpl_b + ch
+    slack_b = kpu_b + ch; coll_b = slack_b + 2 * N + ch; end_b = coll_b + 5 * N
+    cons = np.zeros((m, n))
+    cons[np.arange(ns), np.arange(ns)] = -1
+    a = np.zeros((3, 3)); a[0, 1] = 1; a[1, 2] = 1
+    bvec = np.array([0.0, 0.0, 1.0])
+    lo = np.zeros(m); up = np.zeros(m)
+    for i in range(N - 1):                                               # :86-102
+        ref_k = float(ref["k"][i])
+        ds = float(ref["s"][i + 1]) - float(ref["s"][i])
+        ref_kp = (float(ref["k"][i + 1]) - ref_k) / ds
+        a[1, 0] = -ref_k ** 2
+        cons[3 * (i + 1):3 * (i + 1) + 3, 3 * i:3 * i + 3] = a * ds + np.eye(3)
+        cons[3 * (i + 1):3 * (i + 1) + 3, ns + i // keep] = bvec * ds
+        c = np.array([0.0, 0.0, ref_kp]); ref_state = np.array([0.0, 0.0, ref_k])
+        c_i = ds * (c - a @ ref_state - bvec * ref_kp)
+        lo[3 * (i + 1):3 * (i + 1) + 3] = -c_i
+        up[3 * (i + 1):3 * (i + 1) + 3] = -c_i
+    for i in range(N):                                                   # :106-113
+        cons[kl_b + i, 3 * i + 2] = 1
+        cons[kl_b + i, ns + nc + N + i] = 1
+        cons[ku_b + i, 3 * i + 2] = 1
+        cons[ku_b + i, ns + nc + N + i] = -1
+        cons[slack_b + i, ns + nc + i] = 1
+        cons[slack_b + N + i, ns + nc + N + i] = 1
+    for j in range(ch):                                                  # :115-121
+        cons[kpl_b + j, ns + j] = 1
+        cons[kpl_b + j, ns + nc + 2 * N + j] = 1
+        cons[kpu_b + j, ns + j] = 1
+        cons[kpu_b + j, ns + nc + 2 * N + j] = -1
+        cons[slack_b + 2 * N + j, ns + nc + 2 * N + j] = 1
+    coll = np.array([[1.0, prm.d1], [1.0, prm.d2], [1.0, prm.d4]])       # :124-131
+    for i in range(N):
+        cons[coll_b + 3 * i:coll_b + 3 * i + 3, 3 * i:3 * i + 2] = coll
+        cons[coll_b + 3 * N + i, 3 * i:3 * i + 2] = [1.0, prm.d3]
+        cons[coll_b + 3 * N + i, ns + nc + i] = -1
+        cons[coll_b + 4 * N + i, 3 * i:3 * i + 2] = [1.0, prm.d3]
+        cons[coll_b + 4 * N + i, ns + nc + i] = 1
+    cons[end_b, ns - 3] = 1
+    cons[end_b + 1, ns - 2] = 1
+    lo[0:3] = -np.asarray(x0); up[0:3] = -np.asarray(x0)
+    kmax = np.tan(prm.max_steering_angle) / prm.wheel_base
+    mg = prm.expected_safety_margin
+    for i in range(N):                                                   # :160-172
+        lo[kl_b + i], up[kl_b + i] = -max_k[i], INFTY
+        lo[ku_b + i], up[ku_b + i] = -INFTY, max_k[i]
+        lo[slack_b + i], up[slack_b + i] = 0, mg
+        lo[slack_b + N + i], up[slack_b + N + i] = 0, max(kmax - max_k[i], 0.0)
+    for j in range(ch):                                                  # :173-182
+        lo[kpl_b + j], up[kpl_b + j] = -max_kp[j], INFTY
+        lo[kpu_b + j], up[kpu_b + j] = -INFTY, max_kp[j]
+        lo[slack_b + 2 * N + j], up[slack_b + 2 * N + j] = 0, INFTY
+    for i in range(N):                                                   # :185-200
+        bd = bounds[i]
+        up[coll_b + 3 * i:coll_b + 3 * i + 3] = [bd["c0_ub"], bd["c1_ub"], bd["c3_ub"]]
+        lo[coll_b + 3 * i:coll_b + 3 * i + 3] = [bd["c0_lb"], bd["c1_lb"], bd["c3_lb"]]
+        up[coll_b + 3 * N + i] = bd["c2_ub"] - mg; lo[coll_b + 3 * N + i] = -INFTY
+        lo[coll_b + 4 * N + i] = bd["c2_lb"] + mg; up[coll_b + 4 * N + i] = INFTY
+    lo[end_b], up[end_b] = -INFTY, INFTY                                 # :204-205: end e_y is not constrained
+    lo[end_b + 1], up[end_b + 1] = _end_window(prm, end_heading, ref)
+    return H, np.zeros(n), cons, lo, up
+
+
 def _limit(v):
     v = np.where(v < MIN_SCALING, 1.0, v)
     return np.where(v > MAX_SCALING, MAX_SCALING, v)

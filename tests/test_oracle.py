@@ -39,6 +39,60 @@ def test_kp_assembly_matches_dense_block_twin(oracle_params, gen, n):
         assert np.all(qp["q"] == 0)  # solver.cpp:54
 
 
+@pytest.mark.parametrize("form", [1, 2])
+@pytest.mark.parametrize("gen,n", [(synth.straight_corridors, 9), (synth.curvy_corridors, 38)])
+def test_k_and_kpc_assembly_match_dense_block_twins(oracle_params, form, gen, n):
+    """SolverKAsInput / SolverKpAsInputConstrained: the oracle's sparse triplets against an independent numpy restatement
+    written in the reference's own dense-block style (sparseView drops the exact zeros of the dense matrix)."""
+    b = gen(2, n)
+    total = 2 * n
+    v = 3.0 + 2.0 * np.sin(np.arange(total) * 0.07)
+    a = 0.8 * np.cos(np.arange(total) * 0.05)
+    v[3] = 0.0                                   # standstill: DBL_MAX limits
+    ref_all = b["ref"].copy()
+    ref_all["v"], ref_all["a"] = v, a
+    mk_all, mkp_all = oracle.update_limits(oracle_params, ref_all)
+    for k in range(2):
+        o0, o1 = b["offsets"][k], b["offsets"][k + 1]
+        args = (b["ref"][o0:o1], b["bounds"][o0:o1], b["x0"][k], b["end_heading"][k])
+        if form == 1:
+            qp = oracle.assemble(oracle_params, 1, *args)
+            H, q, A, l, u = twin.assemble_k(oracle_params, *args)
+            assert qp["n"] == 4 * n - 1 and qp["m"] == 11 * n - 1           # solver_k_as_input.cpp:18-19
+        else:
+            mk, mkp = np.ascontiguousarray(mk_all[o0:o1]), np.ascontiguousarray(mkp_all[o0:o1])
+            qp = oracle.assemble(oracle_params, 2, *args, max_k=mk, max_kp=mkp)
+            H, q, A, l, u = twin.assemble_kpc(oracle_params, *args, mk, mkp)
+            ch = (n + 2) // 4
+            assert qp["n"] == 6 * n + ch and qp["m"] == 12 * n + 3 * ch + 2  # solver_kp_as_input_constrained.cpp:18-24
+        P, Ac = _dense(qp)
+        assert np.array_equal(np.triu(H), P)
+        assert np.array_equal(A, Ac)
+        # bounds: OSQP clips nothing at assembly, DBL_MAX limits pass through as they are
+        assert np.array_equal(l, qp["l"]) and np.array_equal(u, qp["u"])
+        assert np.all(qp["q"] == 0)
+
+
+@pytest.mark.parametrize("form", [1, 2])
+def test_k_and_kpc_oracle_vs_twin_solve(oracle_params, form):
+    """Same iteration counts and iterates from the C oracle and the scipy twin on the K / KPC problems."""
+    b = synth.curvy_corridors(1, 30)
+    args = (b["ref"], b["bounds"], b["x0"][0], b["end_heading"][0])
+    if form == 1:
+        r = oracle.solve_qp(oracle_params, 1, *args)
+        H, q, A, l, u = twin.assemble_k(oracle_params, *args)
+    else:
+        ref = b["ref"].copy()
+        ref["v"] = 5.0
+        mk, mkp = oracle.update_limits(oracle_params, ref)
+        r = oracle.solve_qp(oracle_params, 2, *args, max_k=mk, max_kp=mkp)
+        H, q, A, l, u = twin.assemble_kpc(oracle_params, *args, mk, mkp)
+    t = twin.osqp_twin(oracle_params, H, q, A, l, u)
+    assert r["info"].status == t["status"] and r["info"].iters == t["iters"]
+    assert r["info"].rho_updates == t["rho_updates"]
+    np.testing.assert_allclose(r["x"], t["x"], rtol=0, atol=1e-9)
+
+
 def test_keep_control_steps_is_3_for_accumulated_03(oracle_params):
     # SURVEY.md section 7: stations accumulated by += 0.3 give int(1.2 / 0.30000000000000004) = 3
     b = synth.straight_corridors(1, 30)
