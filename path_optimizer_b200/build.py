@@ -8,8 +8,8 @@ from concurrent.futures import ThreadPoolExecutor
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
-OBJ = os.path.join(_HERE, "_obj")
-LIB_PATH = os.path.join(_HERE, "libpqp.so")
+LIB_PATH = os.environ.get("PQP_LIB_OUT") or os.path.join(_HERE, "libpqp.so")   # PQP_LIB_OUT / PQP_NVCC_EXTRA: A/B builds (diagnostics)
+OBJ = os.path.join(_HERE, "_obj" + os.environ.get("PQP_OBJ_SUFFIX", ""))
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-diag-suppress", "550"]
 
@@ -35,7 +35,7 @@ def build(force=False, verbose=False, jobs=None):
         return LIB_PATH
     nvcc = os.environ.get("NVCC", "nvcc")
     os.makedirs(OBJ, exist_ok=True)
-    extra = ["-Xptxas", "-v"] if verbose else []
+    extra = (["-Xptxas", "-v"] if verbose else []) + os.environ.get("PQP_NVCC_EXTRA", "").split()
     newest_header = max(os.path.getmtime(d) for d in _deps() if not d.endswith(".cu"))
 
     def compile_one(src):
