@@ -70,9 +70,6 @@ struct Kp3 {
     // exchange rows of kT doubles: 0..5, ds, separator rhs; the long-path classes park the separator rhs in row 5
     // (only the Ruiz sweeps and diagnostic builds use that row otherwise)
     static constexpr int kExRows = kScratchOnVec ? 7 : 8;
-#ifndef PQP_EXP_SHARE
-#define PQP_EXP_SHARE 0
-#endif
     static constexpr int kCtaScratch = (NW <= 8) ? 128 : 256;   // doubles reserved ahead of the layout for the CTA reductions (16 per warp)
 
     PQP_HD static Kp3Dims dims(int N, int keep) {
@@ -815,7 +812,8 @@ struct Kp3 {
             // slots of the other, so what counts is the instruction total, not the balance inside one CTA.)
             auto dense_rows = [&](int qfirst, int q1, int stride) {
                 if constexpr (kDense) {
-                    for (int q = qfirst; q < q1; q += stride) {
+                    int q = qfirst;
+                    for (; q < q1; q += stride) {
                         const int p = q / IMAX, k = q - p * IMAX;
                         const double *kv = s.fac() + (size_t)q * kRow;
                         const double *rI = s.tr() + p * d.CS + 3;
@@ -831,13 +829,11 @@ struct Kp3 {
             };
             const int yQ = IMAX * M;
             // Phase (b2) of the dense form.  The separator product x_S = Sinv g runs on the first nSr threads, the row tasks
-            // of y = K_I^-1 r_I on the WARPS after them (a warp that held both kinds of thread would run the two pieces of
-            // work one after the other and become the slowest of the phase: 4.40 -> 4.12 ms per 1024 x 100).  When the
-            // row tasks do not fill their last round, the threads of the product warps take that round's tasks after
-            // their own row, provided this shortens the longest warp (N = 100: 68 instead of 85 dependent steps).
+            // of y = K_I^-1 r_I on the WARPS after them: a warp that held both kinds of thread would run the two pieces of
+            // work one after the other and become the slowest of the phase (4.40 -> 4.10 ms per 1024 x 100).  (Handing the
+            // last, partly filled round of row tasks to the product warps, or two row tasks per loop trip, measured
+            // 1-4 % slower: profiles/r02_experiments.md.)
             const int yT0 = (nSr + 31) & ~31, yNw = kT - yT0;
-            const int yFull = (yQ / yNw) * yNw, yRest = yQ - yFull;
-            const bool yShare = kDense && (PQP_EXP_SHARE != 0) && yRest > 0 && yRest <= yT0 && (yFull / yNw) * IMAX > nSr;
 #ifdef PQP_PHASE_TIMING
             static_assert(!kScratchOnVec, "phase timing uses exchange row 5, which the long-path classes give to the separator rhs");
             // clock64() at the phase boundaries, accumulated per warp-0 / warp-1 lead thread in shared scratch
@@ -961,8 +957,7 @@ struct Kp3 {
                         const int xo = kTwoLevel ? 6 * (tid / 3) + (tid % 3) : tid;   // even separator 2*(t/3) in full numbering
                         s.ex(3)[xo] = (a0 + a1) + a2;
                     }
-                    if (tid >= yT0) dense_rows(tid - yT0, yShare ? yFull : yQ, yNw);
-                    else if (yShare) dense_rows(yFull + tid, yQ, yT0);
+                    if (tid >= yT0) dense_rows(tid - yT0, yQ, yNw);
                 } else if (tid < kSolveT) {
                     if (solver) K2::local_solve2(s.tr() + lo, s.yv() + lo, s.fac() + sid, Mst);
                 } else {
