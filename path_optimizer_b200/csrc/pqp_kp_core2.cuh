@@ -65,43 +65,6 @@ struct Kp2 {
         return ok;
     }
 
-    // x = K_I^-1 y.  The vector is read from / written back to shared memory (element k at
-    // vec[k * vst]) and lives in registers in between.  Out of line on purpose (register allocation).
-    PQP_NOINLINE static void local_solve(double *vec, int vst, const double *fcol, int Mst) {
-        double y[IMAX];
-#pragma unroll
-        for (int k = 0; k < IMAX; ++k) y[k] = vec[k * vst];
-        // forward: y[k] -= sum_d L[k][k-d] y[k-d].  Only the d = 1 term depends on the pivot just
-        // computed, so the other terms are accumulated in two independent partial sums first and the
-        // serial chain is ONE DFMA per pivot (instead of BW).
-#pragma unroll
-        for (int k = 1; k < IMAX; ++k) {
-            double p0 = y[k], p1 = 0.0;
-#pragma unroll
-            for (int dd = BW; dd >= 2; --dd)
-                if (k - dd >= 0) {
-                    if (dd & 1) p1 -= PQP_F(k, dd) * y[k - dd];
-                    else p0 -= PQP_F(k, dd) * y[k - dd];
-                }
-            y[k] = (p0 + p1) - PQP_F(k, 1) * y[k - 1];
-        }
-#pragma unroll
-        for (int k = IMAX - 1; k >= 0; --k) {
-            double p0 = y[k] * PQP_F(k, 0), p1 = 0.0;
-#pragma unroll
-            for (int dd = BW; dd >= 2; --dd)
-                if (k + dd < IMAX) {
-                    if (dd & 1) p1 -= PQP_F(k + dd, dd) * y[k + dd];
-                    else p0 -= PQP_F(k + dd, dd) * y[k + dd];
-                }
-            double r = p0 + p1;
-            if (k + 1 < IMAX) r -= PQP_F(k + 1, 1) * y[k + 1];
-            y[k] = r;
-        }
-#pragma unroll
-        for (int k = 0; k < IMAX; ++k) vec[k * vst] = y[k];
-    }
-
     // y = K_I^-1 r with separate input / output vectors (unit stride).
     PQP_NOINLINE static void local_solve2(const double *in, double *outv, const double *fcol, int Mst) {
         double y[IMAX];
@@ -170,6 +133,43 @@ struct Kp2 {
         }
 #pragma unroll
         for (int k = 0; k < IMAX; ++k) x[k] = y[k];
+    }
+
+    // The same two solves IN PLACE in shared memory (vector at v[0..IMAX), unit stride), for the refactorisation: the
+    // vector never sits in registers, so these out-of-line calls need a handful of registers and the call does not push
+    // the caller's (255 live registers) onto the local-memory stack.  (With the register forms above, 80 % of the
+    // kernel's local-memory stores -- and through L2 write-back most of its DRAM writes -- came from exactly these calls.)
+    PQP_NOINLINE static void local_solve_mem(double *v, const double *fcol, int Mst) {
+        // (same association order as local_solve: even / odd partial sums over d >= 2, the d = 1 term last)
+#pragma unroll
+        for (int k = 1; k < IMAX; ++k) {
+            double p0 = v[k], p1 = 0.0;
+#pragma unroll
+            for (int dd = BW; dd >= 2; --dd)
+                if (k - dd >= 0) {
+                    if (dd & 1) p1 -= PQP_F(k, dd) * v[k - dd];
+                    else p0 -= PQP_F(k, dd) * v[k - dd];
+                }
+            v[k] = (p0 + p1) - PQP_F(k, 1) * v[k - 1];
+        }
+#pragma unroll
+        for (int k = IMAX - 1; k >= 0; --k) {
+            double p0 = v[k] * PQP_F(k, 0), p1 = 0.0;
+#pragma unroll
+            for (int dd = BW; dd >= 2; --dd)
+                if (k + dd < IMAX) {
+                    if (dd & 1) p1 -= PQP_F(k + dd, dd) * v[k + dd];
+                    else p0 -= PQP_F(k + dd, dd) * v[k + dd];
+                }
+            double r = p0 + p1;
+            if (k + 1 < IMAX) r -= PQP_F(k + 1, 1) * v[k + 1];
+            v[k] = r;
+        }
+    }
+    PQP_NOINLINE static void local_solve_unit_mem(int j, double *v, const double *fcol, int Mst) {
+#pragma unroll
+        for (int k = 0; k < IMAX; ++k) v[k] = (k == j) ? 1.0 : 0.0;
+        local_solve_mem(v, fcol, Mst);
     }
 
     // ---- row weights for the current rho, from the workspace E ----------------------------------

@@ -81,6 +81,7 @@ struct Kp3 {
     PQP_HD static bool fits(int N, int keep) {
         if (N < 2 || N > kT || keep < 1 || keep > 10) return false;
         const Kp3Dims d = kp3_dims_raw(N, keep, MMAX);
+        if (kScratchOnVec && 2 * ((d.ch + 1) & ~1) > kT - 64) return false;   // (held-control state in the row tails, see Smem)
         return d.I <= IMAX && d.bw <= BW && d.M <= MMAX && 6 * d.M <= kT && kSolveT + 3 * d.M <= kT;
     }
 
@@ -93,7 +94,18 @@ struct Kp3 {
         PQP_DEV double *ex(int k) const { return base + 2 * nv + k * kT; }  // 6 exchange rows of kT
         PQP_DEV double *dsS() const { return ex(6); }                     // ds per station     [kT]
         PQP_DEV double *gS() const { return ex(kScratchOnVec ? 5 : 7); }     // separator rhs      [nS <= kT]
-        PQP_DEV double *fac() const { return ex(kExRows); }               // [IMAX*(BW+1)*M]; kDense: then K_I^-1 [M][IMAX][kRow]
+        // State only a few threads touch lives in shared memory instead of in (everybody's) registers: the two end rows of
+        // the last station (v, W, window: 6 doubles) and the held controls' (v, W, x, sigma), ch each.  It has a region of
+        // its own after the exchange rows -- except in the long-path classes, which have no byte to spare: there it sits
+        // in the unused tails of the separator rows 3 (x_S: 3M <= 102 entries used), 4 (<= 51 used) and 5 (<= 102 used).
+        PQP_DEV int chp() const { return (ch + 1) & ~1; }
+        PQP_DEV double *endr() const { return kScratchOnVec ? ex(4) + 56 : ex(kExRows); }   // vEY vEH WEY WEH lEH uEH . .
+        PQP_DEV double *ubs(int f) const {                                                 // f: 0 v, 1 W, 2 x, 3 sigma
+            if (!kScratchOnVec) return ex(kExRows) + 8 + f * chp();
+            return f == 0 ? ex(4) + 64 : f == 3 ? ex(4) + 64 + chp() : f == 1 ? ex(3) + 104 : ex(5) + 104;
+        }
+        PQP_HD static int aux_doubles(int ch_) { return kScratchOnVec ? 0 : 8 + 4 * ((ch_ + 1) & ~1); }
+        PQP_DEV double *fac() const { return ex(kExRows) + aux_doubles(ch); }   // [IMAX*(BW+1)*M]; kDense: then K_I^-1 [M][IMAX][kRow]
         PQP_DEV double *T() const { return fac() + kFacSlots * M; }       // spikes T[c][pos], c < 6: [6*nv]
         PQP_DEV int nSd() const { return kTwoLevel ? 3 * ((M + 1) / 2) : nS; }   // order of the dense separator inverse
         PQP_DEV double *Sinv() const { return T() + 6 * nv; }             // [nSd*nSd]
@@ -108,7 +120,7 @@ struct Kp3 {
         PQP_DEV double *red2() const { return lv() + 36 * M; }
     };
     PQP_HD static size_t smem_doubles(const Kp3Dims &d) {
-        return 2 * (size_t)d.nv + (size_t)kExRows * kT + (size_t)kFacSlots * d.M + 6 * (size_t)d.nv +
+        return 2 * (size_t)d.nv + (size_t)kExRows * kT + (size_t)Smem::aux_doubles(d.ch) + (size_t)kFacSlots * d.M + 6 * (size_t)d.nv +
                (kTwoLevel ? (size_t)9 * ((d.M + 1) / 2) * ((d.M + 1) / 2) : (size_t)d.nS * d.nS) +
                ((kDense || kScratchOnVec) ? 0 : (size_t)(kRed2 + 27 + 12) * d.M) +
                (kTwoLevel ? (size_t)36 * d.M + (size_t)kRed2 * ((d.M + 1) / 2) : 0);
@@ -131,8 +143,7 @@ struct Kp3 {
         bool live, first, last, sep;
     };
     struct Ub {                     // held control j (thread j < ch)
-        double v, W, x, sg;
-        int pos, t0, t1;            // padded index, first / last transition of the block
+        int pos, t0, t1;            // padded index, first / last transition of the block (v, W, x, sigma: shared memory)
         bool live;
     };
 
@@ -232,13 +243,13 @@ struct Kp3 {
             cnt = g1 - g0 - 3;
         }
         // end-heading window, solver_kp_as_input.cpp:193-201
-        double lEH = -kOsqpInfty, uEH = kOsqpInfty;
+        double lEH0 = -kOsqpInfty, uEH0 = kOsqpInfty;
         if (pm.constraint_end_heading) {
             const double pi = 3.14159265358979323846;
             const double end_psi = constraint_angle(bv.end_heading[prob] - ref[N - 1].z);
             if (end_psi < 70 * pi / 180) {
-                lEH = end_psi - 5 * pi / 180;
-                uEH = end_psi + 5 * pi / 180;
+                lEH0 = end_psi - 5 * pi / 180;
+                uEH0 = end_psi + 5 * pi / 180;
             }
         }
         // ---- per-station coefficients (setConstraintMatrix :84-98, :143-151, :166-187)
@@ -274,14 +285,25 @@ struct Kp3 {
                 invalid = 1;
             s.dsS()[i] = st.ds;
         }
-        if (!(0.0 <= pm.margin) || !(-pm.kmax <= pm.kmax) || !(lEH <= uEH)) invalid = 1;
+        if (!(0.0 <= pm.margin) || !(-pm.kmax <= pm.kmax) || !(lEH0 <= uEH0)) invalid = 1;
         invalid = c.any(invalid);
 
         int status = PQP_UNSOLVED;
         int iter = 0;
-        double vEY = 0, vEH = 0, WEY = 0, WEH = 0;   // end rows (thread of station N-1)
+        // end rows (only the thread of station N-1 touches them) and held controls (threads j < ch): in shared memory
+        double *const er = s.endr();
+        double *const uS0 = s.ubs(0), *const uS1 = s.ubs(1), *const uS2 = s.ubs(2), *const uS3 = s.ubs(3);
+#define vEY er[0]
+#define vEH er[1]
+#define WEY er[2]
+#define WEH er[3]
+#define lEH er[4]
+#define uEH er[5]
+#define PQP_UBV uS0[tid]
+#define PQP_UBW uS1[tid]
+#define PQP_UBX uS2[tid]
+#define PQP_UBSG uS3[tid]
         st.xa = st.xb = st.xc = st.xs = 0.0;
-        ub.x = 0.0; ub.v = 0.0; ub.W = 0.0; ub.sg = 0.0;
         double cost_c = 1.0;
         if (invalid) {
             status = PQP_INVALID_PROBLEM;
@@ -380,8 +402,12 @@ struct Kp3 {
             if (ub.live) {
                 ws[9 * (size_t)N + tid] = eUB;
                 ws[13 * (size_t)N + ch + 2 + tid] = Du;
-                ub.sg = pm.sigma / (Du * Du);
+                PQP_UBSG = pm.sigma / (Du * Du);
             }
+            // (the shared-memory state of the end rows and the held controls is set up only now: in the long-path classes it
+            // sits in the tails of exchange rows the Ruiz sweeps have just used)
+            if (tid == 0) { er[0] = 0.0; er[1] = 0.0; er[2] = 0.0; er[3] = 0.0; er[4] = lEH0; er[5] = uEH0; }
+            if (ub.live) { PQP_UBX = 0.0; PQP_UBV = 0.0; PQP_UBW = 0.0; }
             // cold start: OSQP's first iteration from zero leaves x = 0, v = 0 (see pqp_kp_core.cuh)
             st.vD0 = st.vD1 = st.vD2 = st.vKB = st.vSB = st.vH1 = st.vH3 = 0.0;
             st.vS4m = st.vS4p = st.vS2m = st.vS2p = 0.0;
@@ -416,7 +442,7 @@ struct Kp3 {
                     st.ksinv = 1.0 / (cost_c * pm.w_s + st.sgs + st.WSB + 2.0 * st.WS4 + 2.0 * st.WS2);
                     s.ex(0)[i] = st.WD0; s.ex(1)[i] = st.WD1; s.ex(2)[i] = st.WD2;   // neighbours need these
                 }
-                if (ub.live) ub.W = kp_w_box(ws[9 * (size_t)N + tid], -kOsqpInfty, kOsqpInfty, rho);
+                if (ub.live) PQP_UBW = kp_w_box(ws[9 * (size_t)N + tid], -kOsqpInfty, kOsqpInfty, rho);
                 // zero the factor storage (identity on padded rows)
                 for (int k = tid; k < IMAX * (BW + 1) * M; k += kT) {
                     const int p = k % M, kd = k / M, dd = kd % (BW + 1), kk = kd / (BW + 1);
@@ -465,7 +491,7 @@ struct Kp3 {
                     const int p = ub.pos / d.CS;
                     double *fcol = s.fac() + p;
                     const int ku = ub.pos - (p * d.CS + 3);
-                    double du = cost_c * (keep * pm.w_cr) + ub.sg + ub.W;
+                    double du = cost_c * (keep * pm.w_cr) + PQP_UBSG + PQP_UBW;
                     int ii1 = tid * keep + keep;
                     if (ii1 > N - 1) ii1 = N - 1;
                     for (int ii = tid * keep; ii <= ii1; ++ii) {
@@ -546,7 +572,7 @@ struct Kp3 {
                         else if (sp_c == 4) { PQP_TC(kat) += -rW1 * rq; PQP_TC(kat + 1) += -rW1; PQP_TC(kat + 2) += -rW1 * rds; }
                         else { PQP_TC(kat + 2) += -rW2; PQP_TC(kur) += -rW2 * rds; }
 #undef PQP_TC
-                        K2::local_solve(tcol, 1, s.fac() + sp_p, Mst);
+                        K2::local_solve_mem(tcol, s.fac() + sp_p, Mst);   // in place in shared memory
                     }
                 }
                 c.sync();
@@ -741,27 +767,30 @@ struct Kp3 {
                 }
                 PQP_RT(6)
                 if constexpr (kDense) {
-                    // ---- dense interior inverses: task (p, j) = column j of K_p^-1 from the band factor,
-                    //      kept in registers until every thread is done with the factor, then written
-                    //      over it row-major: kinv[(p * IMAX + k) * kRow + j] (symmetric: column j = row j).
-                    constexpr int kTasks = (IMAX * MMAX + kT - 1) / kT;
-                    double xc[kTasks][IMAX];
-#pragma unroll
-                    for (int t = 0; t < kTasks; ++t) {
-                        const int q = tid + t * kT;
-                        if (q < IMAX * M) K2::local_solve_unit(q / M, xc[t], s.fac() + (q % M), Mst);
+                    // ---- dense interior inverses, row-major over the band factor: row r = p * IMAX + j of the
+                    //      region is column j of K_p^-1 (symmetric: = row j).  Rows whose slots lie BEHIND the band factor
+                    //      (the refactorisation scratch there is dead by now) are solved in place in shared memory; the
+                    //      first kStaged rows overlap the factor every thread is still reading: one per thread, solved
+                    //      in registers and written once everybody is done.
+                    c.sync();   // the separator-system phases above are done with the scratch behind the band factor
+                    const int bandEnd = IMAX * (BW + 1) * M;
+                    const int nStaged = (bandEnd + kRow - 1) / kRow;        // <= kT for every dense class (static_assert below)
+                    static_assert((IMAX * (BW + 1) * MMAX + kRow - 1) / kRow <= kT, "one staged row per thread");
+                    for (int r = nStaged + tid; r < IMAX * M; r += kT) {
+                        const int p = r / IMAX, j = r - p * IMAX;
+                        double *kv = s.fac() + (size_t)r * kRow;
+                        K2::local_solve_unit_mem(j, kv, s.fac() + p, Mst);
+                        kv[IMAX] = 0.0;
                     }
+                    double xc[IMAX];
+                    const bool staged = tid < nStaged && tid < IMAX * M;
+                    if (staged) K2::local_solve_unit(tid % IMAX, xc, s.fac() + tid / IMAX, Mst);
                     c.sync();
+                    if (staged) {
+                        double *kv = s.fac() + (size_t)tid * kRow;
 #pragma unroll
-                    for (int t = 0; t < kTasks; ++t) {
-                        const int q = tid + t * kT;
-                        if (q < IMAX * M) {
-                            const int j = q / M, p = q % M;
-                            double *kv = s.fac() + (size_t)(p * IMAX + j) * kRow;   // row j
-#pragma unroll
-                            for (int k = 0; k < IMAX; ++k) kv[k] = xc[t][k];
-                            kv[IMAX] = 0.0;
-                        }
+                        for (int k = 0; k < IMAX; ++k) kv[k] = xc[k];
+                        kv[IMAX] = 0.0;
                     }
                 }
                 PQP_RT(7)
@@ -897,7 +926,7 @@ struct Kp3 {
                     tsl = (st.sgs * st.xs + rs) * st.ksinv;
                 }
                 if (ub.live) {
-                    double acc = ub.sg * ub.x + ub.W * (2.0 * clamp2(ub.v, -kOsqpInfty, kOsqpInfty) - ub.v);
+                    double acc = PQP_UBSG * PQP_UBX + PQP_UBW * (2.0 * clamp2(PQP_UBV, -kOsqpInfty, kOsqpInfty) - PQP_UBV);
                     for (int t = ub.t0; t <= ub.t1; ++t) acc += s.dsS()[t] * s.ex(2)[t + 1];
                     s.tr()[ub.pos] = acc;
                 }
@@ -1068,8 +1097,8 @@ struct Kp3 {
                     st.xs = alpha * tsl + (1.0 - alpha) * st.xs;
                 }
                 if (ub.live) {
-                    ub.v += alpha * (tu - clamp2(ub.v, -kOsqpInfty, kOsqpInfty));
-                    ub.x = alpha * tu + (1.0 - alpha) * ub.x;
+                    PQP_UBV += alpha * (tu - clamp2(PQP_UBV, -kOsqpInfty, kOsqpInfty));
+                    PQP_UBX = alpha * tu + (1.0 - alpha) * PQP_UBX;
                 }
                 PQP_PH(5)
                 // ---- (d) residuals, termination, adaptive rho
@@ -1095,7 +1124,7 @@ struct Kp3 {
                     // publish x (neighbours need station i-1 and the control) and read the scalings
                     c.sync();
                     if (st.live) { s.tr()[st.pos] = st.xa; s.tr()[st.pos + 1] = st.xb; s.tr()[st.pos + 2] = st.xc; }
-                    if (ub.live) s.tr()[ub.pos] = ub.x;
+                    if (ub.live) s.tr()[ub.pos] = PQP_UBX;
                     c.sync();
                     double pr = 0, nz = 0, nax = 0, prs = 0, nzs = 0, naxs = 0;
                     double dr = 0, npx = 0, naty = 0, drs = 0, npxs = 0, natys = 0;
@@ -1147,7 +1176,7 @@ struct Kp3 {
                         yD2 = PQP_DUAL(st.vD2, st.b2, st.b2, st.WD2);
                         s.ex(0)[i] = yD0; s.ex(1)[i] = yD1; s.ex(2)[i] = yD2;
                     }
-                    if (ub.live) PQP_ROW(ub.x, ub.v, -kOsqpInfty, kOsqpInfty, ws[9 * (size_t)N + tid])
+                    if (ub.live) PQP_ROW(PQP_UBX, PQP_UBV, -kOsqpInfty, kOsqpInfty, ws[9 * (size_t)N + tid])
                     c.sync();
                     if (st.live) {
                         const double yKB = PQP_DUAL(st.vKB, -pm.kmax, pm.kmax, st.WKB);
@@ -1178,9 +1207,9 @@ struct Kp3 {
                         PQP_VAR(pm.w_s * st.xs, rs, dW[3])
                     }
                     if (ub.live) {
-                        double aty = PQP_DUAL(ub.v, -kOsqpInfty, kOsqpInfty, ub.W);
+                        double aty = PQP_DUAL(PQP_UBV, -kOsqpInfty, kOsqpInfty, PQP_UBW);
                         for (int t = ub.t0; t <= ub.t1; ++t) aty += s.dsS()[t] * s.ex(2)[t + 1];
-                        PQP_VAR((keep * pm.w_cr) * ub.x, aty, ws[13 * (size_t)N + ch + 2 + tid])
+                        PQP_VAR((keep * pm.w_cr) * PQP_UBX, aty, ws[13 * (size_t)N + ch + 2 + tid])
                     }
 #undef PQP_ROW
 #undef PQP_DUAL
@@ -1293,8 +1322,10 @@ struct Kp3 {
                             PQP_RESC(st.vS4p, st.lS4p, kOsqpInfty)
                             PQP_RESC(st.vS2m, -kOsqpInfty, st.uS2m)
                             PQP_RESC(st.vS2p, st.lS2p, kOsqpInfty)
-                            PQP_RESC(vEY, -1.0, 1.0)
-                            PQP_RESC(vEH, lEH, uEH)
+                            if (st.last) {
+                                PQP_RESC(vEY, -1.0, 1.0)
+                                PQP_RESC(vEH, lEH, uEH)
+                            }
 #undef PQP_RESC
                             rho = rho_new;
                             c.sync();
@@ -1389,6 +1420,16 @@ struct Kp3 {
         c.sync();
     }
 #undef PQP_F
+#undef vEY
+#undef vEH
+#undef WEY
+#undef WEH
+#undef lEH
+#undef uEH
+#undef PQP_UBV
+#undef PQP_UBW
+#undef PQP_UBX
+#undef PQP_UBSG
 };
 
 }  // namespace pqp
