@@ -147,6 +147,32 @@ struct Kp3 {
         bool live;
     };
 
+    // Dense interior inverses over the band factor (see the call site).  Out of line: what it needs in registers stays out
+    // of the solve's own allocation.
+    PQP_NOINLINE static void dense_build(const Cta &c, double *fac, int M, int tid) {
+        const int Mst = M;
+        c.sync();   // the separator-system phases before it are done with the scratch behind the band factor
+        const int bandEnd = IMAX * (BW + 1) * M;
+        const int nStaged = (bandEnd + kRow - 1) / kRow;        // <= kT for every dense class
+        static_assert(!kDense || (IMAX * (BW + 1) * MMAX + kRow - 1) / kRow <= kT, "one staged row per thread");
+        for (int r = nStaged + tid; r < IMAX * M; r += kT) {
+            const int p = r / IMAX, j = r - p * IMAX;
+            double *kv = fac + (size_t)r * kRow;
+            K2::local_solve_unit_mem(j, kv, fac + p, Mst);
+            kv[IMAX] = 0.0;
+        }
+        double xc[IMAX];
+        const bool staged = tid < nStaged && tid < IMAX * M;
+        if (staged) K2::local_solve_unit(tid % IMAX, xc, fac + tid / IMAX, Mst);
+        c.sync();
+        if (staged) {
+            double *kv = fac + (size_t)tid * kRow;
+#pragma unroll
+            for (int k = 0; k < IMAX; ++k) kv[k] = xc[k];
+            kv[IMAX] = 0.0;
+        }
+    }
+
     // ---- the whole per-path solve ----------------------------------------------------------------
     PQP_DEV static void solve_path(const Cta &c, const DevParams &pm, const BatchView &bv, int prob, double *smem,
                                    size_t smem_cap) {
@@ -772,26 +798,7 @@ struct Kp3 {
                     //      (the refactorisation scratch there is dead by now) are solved in place in shared memory; the
                     //      first kStaged rows overlap the factor every thread is still reading: one per thread, solved
                     //      in registers and written once everybody is done.
-                    c.sync();   // the separator-system phases above are done with the scratch behind the band factor
-                    const int bandEnd = IMAX * (BW + 1) * M;
-                    const int nStaged = (bandEnd + kRow - 1) / kRow;        // <= kT for every dense class (static_assert below)
-                    static_assert((IMAX * (BW + 1) * MMAX + kRow - 1) / kRow <= kT, "one staged row per thread");
-                    for (int r = nStaged + tid; r < IMAX * M; r += kT) {
-                        const int p = r / IMAX, j = r - p * IMAX;
-                        double *kv = s.fac() + (size_t)r * kRow;
-                        K2::local_solve_unit_mem(j, kv, s.fac() + p, Mst);
-                        kv[IMAX] = 0.0;
-                    }
-                    double xc[IMAX];
-                    const bool staged = tid < nStaged && tid < IMAX * M;
-                    if (staged) K2::local_solve_unit(tid % IMAX, xc, s.fac() + tid / IMAX, Mst);
-                    c.sync();
-                    if (staged) {
-                        double *kv = s.fac() + (size_t)tid * kRow;
-#pragma unroll
-                        for (int k = 0; k < IMAX; ++k) kv[k] = xc[k];
-                        kv[IMAX] = 0.0;
-                    }
+                    dense_build(c, s.fac(), M, tid);
                 }
                 PQP_RT(7)
                 if constexpr (kScratchOnVec) {
