@@ -411,7 +411,15 @@ int oracle_plan_path(const pqp_params *prm, const pqp_distance_map *map, int for
     info.status = PQP_INVALID_PROBLEM;
     if (nv >= 2) {
         pqp_state *sol = (pqp_state *)malloc(sizeof(pqp_state) * (size_t)nv);
-        oracle_solve_path(prm, formulation, nv, ref, bounds, x0, end_heading, NULL, NULL, sol, NULL, &info);
+        /* reference_path_->updateLimits() (path_optimizer.cpp:102): only KPC uses the limits */
+        double *mk = NULL, *mkp = NULL;
+        if (formulation == PQP_FORM_KPC) {
+            mk = (double *)malloc(sizeof(double) * (size_t)nv);
+            mkp = (double *)malloc(sizeof(double) * (size_t)nv);
+            oracle_update_limits(prm, 0, nv, ref, mk, mkp);
+        }
+        oracle_solve_path(prm, formulation, nv, ref, bounds, x0, end_heading, mk, mkp, sol, NULL, &info);
+        free(mk); free(mkp);
         if (info.status == PQP_SOLVED) {
             if (output_mode == PQP_OUTPUT_RAW) {
                 ok = oracle_finish_raw(prm, map, nv, sol, collision_check, n_out);

@@ -11,7 +11,7 @@ CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.environ.get("PQP_LIB_OUT") or os.path.join(_HERE, "libpqp.so")   # PQP_LIB_OUT / PQP_NVCC_EXTRA: A/B builds (diagnostics)
 OBJ = os.path.join(_HERE, "_obj" + os.environ.get("PQP_OBJ_SUFFIX", ""))
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-diag-suppress", "550"]
+              "-Xcompiler", "-fPIC", "-diag-suppress", "550,177"]
 
 
 def sources():

@@ -29,7 +29,8 @@ namespace {
 // keep_control_steps <= 4 (station spacing >= 0.24 m) and up to 408 stations map onto one of the thread-per-station
 // (Kp3) instantiations; anything else runs on the one-warp generic kernel (last).
 typedef PqpVariant Variant;
-constexpr int kNumVariants = 9;
+constexpr int kNumKp = 9;          // "KP" classes: thread-per-station kernels, then the one-warp kernel (index kNumKp - 1)
+constexpr int kNumVariants = 11;   // + the "KPC" thread-per-station classes
 struct VariantTable {
     Variant v[kNumVariants];
     VariantTable() {
@@ -38,6 +39,7 @@ struct VariantTable {
         pqp_variant_k3_17_6_8_34(&v[k++]); pqp_variant_k3_23_7_8_34(&v[k++]); pqp_variant_k3_27_7_8_34(&v[k++]);
         pqp_variant_k3_27_7_10_34(&v[k++]); pqp_variant_k3_37_7_12_34(&v[k++]); pqp_variant_k3_37_7_13_34(&v[k++]);
         pqp_variant_k1_generic(&v[k++]);
+        pqp_variant_k3c_23_7_4_17(&v[k++]); pqp_variant_k3c_23_7_8_34(&v[k++]);
     }
 };
 const Variant *variants() {
@@ -54,8 +56,9 @@ unsigned skip_mask() {
     return m;
 }
 
-int pick_variant(int n, int keep) {
-    for (int v = 0; v < kNumVariants; ++v)
+int pick_variant(int n, int keep, int form = PQP_FORM_KP) {
+    const int v0 = form == PQP_FORM_KPC ? kNumKp : 0, v1 = form == PQP_FORM_KPC ? kNumVariants : kNumKp;
+    for (int v = v0; v < v1; ++v)
         if (!((skip_mask() >> v) & 1u) && kVariants[v].fits(n, keep)) return v;
     return -1;
 }
@@ -64,8 +67,16 @@ int pick_variant(int n, int keep) {
 // point that sees the lengths on the host selects it: the first class that takes (n, keep); when that class needs more
 // shared memory than the device offers, the one-warp kernel if the path fits there; else the smallest launch of the
 // one-warp kernel, which reports PQP_INVALID_PROBLEM for the path.  Returns false in that last case.
-bool class_for(const pqp_handle *h, int n, int keep, int *v_out, size_t *need_out) {
-    int v = kNumVariants - 1;
+// "KPC" has thread-per-station classes only (up to 256 stations): false + *v_out = -1 means the path takes the host-assembled
+// generic kernel.
+bool class_for(const pqp_handle *h, int n, int keep, int *v_out, size_t *need_out, int form = PQP_FORM_KP) {
+    if (form == PQP_FORM_KPC) {
+        const int pv = n >= 2 ? pick_variant(n, 4, form) : -1;
+        *v_out = pv;
+        *need_out = pv >= 0 ? kVariants[pv].smem(n, 4) : 0;
+        return pv >= 0 && *need_out <= (size_t)h->smem_optin;
+    }
+    int v = kNumKp - 1;
     if (n >= 2) {
         const int pv = pick_variant(n, keep);
         if (pv >= 0) v = pv;
@@ -74,7 +85,7 @@ bool class_for(const pqp_handle *h, int n, int keep, int *v_out, size_t *need_ou
     size_t need = kVariants[v].smem(ne, ke);
     bool ok = n >= 2 && keep >= 1 && keep <= 10;
     if (need > (size_t)h->smem_optin) {
-        v = kNumVariants - 1;
+        v = kNumKp - 1;
         need = (keep <= 10) ? kVariants[v].smem(ne, ke) : (size_t)h->smem_optin + 1;
         if (need > (size_t)h->smem_optin) { need = kVariants[v].smem(2, 1); ok = false; }
     }
@@ -86,14 +97,16 @@ bool class_for(const pqp_handle *h, int n, int keep, int *v_out, size_t *need_ou
 // One class for a whole device-resident batch of which the host only knows bounds: it must take EVERY (n, keep) with
 // 2 <= n <= nmax, k_lo <= keep <= k_hi (neither fits() nor the shared-memory need is monotone in n: the separator and
 // interior counts change with it), and is launched with the largest shared-memory need over that range.
-bool device_class(pqp_handle *h, int nmax, int k_lo, int k_hi, int *v_out, size_t *smem_out) {
-    if (h->dc_nmax == nmax && h->dc_klo == k_lo && h->dc_khi == k_hi && h->dc_skip == (int)skip_mask()) {
+bool device_class(pqp_handle *h, int nmax, int k_lo, int k_hi, int *v_out, size_t *smem_out, int form = PQP_FORM_KP) {
+    if (form == PQP_FORM_KPC) k_lo = k_hi = 4;
+    if (h->dc_nmax == nmax && h->dc_klo == k_lo && h->dc_khi == k_hi && h->dc_skip == (int)skip_mask() && h->dc_form == form) {
         *v_out = h->dc_v; *smem_out = h->dc_smem;
         return h->dc_v >= 0;
     }
     int v = -1;
     size_t smem = 0;
-    for (int cand = 0; cand < kNumVariants && v < 0; ++cand) {
+    const int c0 = form == PQP_FORM_KPC ? kNumKp : 0, c1 = form == PQP_FORM_KPC ? kNumVariants : kNumKp;
+    for (int cand = c0; cand < c1 && v < 0; ++cand) {
         if ((skip_mask() >> cand) & 1u) continue;
         bool all = true;
         size_t need = 0;
@@ -105,6 +118,7 @@ bool device_class(pqp_handle *h, int nmax, int k_lo, int k_hi, int *v_out, size_
         if (all && need <= (size_t)h->smem_optin) { v = cand; smem = need; }
     }
     h->dc_nmax = nmax; h->dc_klo = k_lo; h->dc_khi = k_hi; h->dc_skip = (int)skip_mask(); h->dc_v = v; h->dc_smem = smem;
+    h->dc_form = form;
     *v_out = v; *smem_out = smem;
     return v >= 0;
 }
@@ -118,16 +132,16 @@ static int launch_variant(pqp_handle *h, int v, const pqp::BatchView &bv, int co
 }
 
 int pqp_launch_kp_classes(pqp_handle *h, const pqp::BatchView &bv, int batch, const int32_t *n, const int32_t *off,
-                          const pqp_state *ref, const int32_t *keep_in, cudaStream_t st, int *launches) {
+                          const pqp_state *ref, const int32_t *keep_in, cudaStream_t st, int *launches, int form) {
     static_assert(kNumVariants <= PQP_MAX_VARIANTS, "class plan arrays");
     // keep_control_steps per path
     std::vector<int32_t> keepv((size_t)batch);
     for (int b = 0; b < batch; ++b)
-        keepv[b] = keep_in ? keep_in[b] : (n[b] >= 2 ? pqp_keep_control_steps(PQP_FORM_KP, ref + off[b], n[b]) : 1);
+        keepv[b] = form == PQP_FORM_KPC ? 4 : keep_in ? keep_in[b] : (n[b] >= 2 ? pqp_keep_control_steps(PQP_FORM_KP, ref + off[b], n[b]) : 1);
     // The plan (class per path, longest-first order inside a class) only depends on (n, keep): a caller that solves
     // batches of the same shape back to back reuses it, and the order array already on the device with it.
     pqp_handle::ClassPlan &pl = h->plan;
-    const bool same = pl.valid && pl.skip == (int)skip_mask() && pl.n.size() == (size_t)batch &&
+    const bool same = pl.valid && pl.form == form && pl.skip == (int)skip_mask() && pl.n.size() == (size_t)batch &&
                       std::equal(pl.n.begin(), pl.n.end(), n) && pl.keep == keepv;
     if (!same) {
         // the pinned order array may still be the source of an earlier asynchronous upload
@@ -139,7 +153,10 @@ int pqp_launch_kp_classes(pqp_handle *h, const pqp::BatchView &bv, int batch, co
         for (int b = 0; b < batch; ++b) {
             int v;
             size_t need;
-            class_for(h, n[b], keepv[b], &v, &need);
+            if (!class_for(h, n[b], keepv[b], &v, &need, form) && form == PQP_FORM_KPC) {
+                set_err("a KPC path has no thread-per-station class (more than 256 stations): use pqp_solve_batch (host buffers)");
+                return PQP_ERR_UNSUPPORTED;
+            }
             cls[b] = v;
             pl.smem_v[v] = std::max(pl.smem_v[v], need);
             pl.count_v[v]++;
@@ -155,6 +172,7 @@ int pqp_launch_kp_classes(pqp_handle *h, const pqp::BatchView &bv, int batch, co
         pl.n.assign(n, n + batch);
         pl.keep = keepv;
         pl.skip = (int)skip_mask();
+        pl.form = form;
         pl.stream = st;
         pl.valid = true;
     }
@@ -274,6 +292,7 @@ void pqp_destroy(pqp_handle *h) {
     cudaFree(h->d_n); cudaFree(h->d_off); cudaFree(h->d_order); cudaFree(h->d_status); cudaFree(h->d_iters);
     cudaFree(h->d_ref); cudaFree(h->d_out); cudaFree(h->d_bounds);
     cudaFree(h->d_x0); cudaFree(h->d_end); cudaFree(h->d_frenet); cudaFree(h->d_ws);
+    cudaFree(h->d_max_k); cudaFree(h->d_max_kp);
     cudaFreeHost(h->h_off); cudaFreeHost(h->h_order);
     cudaFree(h->d_gen); cudaFreeHost(h->h_gen);
     if (h->env && h->env_free) h->env_free(h->env);
@@ -326,6 +345,7 @@ int pqp_create(pqp_handle **out, const pqp_params *params, int device, int max_b
     } while (0)
     PQP_TRY(cudaDeviceGetAttribute(&h->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
     PQP_TRY(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device));
+    pqp_k1_set_smem_cap(h->smem_optin);
     // fails with cudaErrorNoKernelImageForDevice / InvalidDeviceFunction on anything but sm_100
     for (int v = 0; v < kNumVariants; ++v)
         PQP_TRY(cudaFuncSetAttribute(kVariants[v].fn, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin));
@@ -371,6 +391,18 @@ int pqp_class_info(int n_points, int keep, int smem_optin, int *variant, int *th
     const bool ok = class_for(&fake, n_points, keep, &v, &need);
     if (variant) *variant = v;
     if (threads) *threads = kVariants[v].threads;
+    if (smem_bytes) *smem_bytes = (int64_t)need;
+    return ok ? PQP_OK : PQP_ERR_UNSUPPORTED;
+}
+
+int pqp_class_info_kpc(int n_points, int smem_optin, int *variant, int *threads, int64_t *smem_bytes) {
+    pqp_handle fake;
+    fake.smem_optin = smem_optin > 0 ? smem_optin : 232448;
+    int v;
+    size_t need;
+    const bool ok = class_for(&fake, n_points, 4, &v, &need, PQP_FORM_KPC);
+    if (variant) *variant = v;
+    if (threads) *threads = ok ? kVariants[v].threads : 0;
     if (smem_bytes) *smem_bytes = (int64_t)need;
     return ok ? PQP_OK : PQP_ERR_UNSUPPORTED;
 }
@@ -437,14 +469,18 @@ int pqp_solve_batch_device(pqp_handle *h, int formulation, int batch, int total_
                            const double *d_max_k, const double *d_max_kp, pqp_state *d_out_states,
                            double *d_out_frenet, int32_t *d_status, int32_t *d_iters, void *stream,
                            pqp_stats *stats) {
-    (void)d_max_k; (void)d_max_kp; (void)total_points;
+    (void)total_points;
     if (!h || batch < 0 || !d_n_points || !d_offsets || !d_ref || !d_bounds || !d_x0 || !d_end_heading ||
         !d_out_states || !d_status) {
         set_err("pqp_solve_batch_device: bad argument");
         return PQP_ERR_ARG;
     }
-    if (formulation != PQP_FORM_KP) {
-        set_err("K / KPC are assembled on the host: use pqp_solve_batch (host buffers) for them");
+    if (formulation == PQP_FORM_KPC && (!d_max_k || !d_max_kp)) {
+        set_err("KPC needs d_max_k and d_max_kp (pqp_update_limits_device)");
+        return PQP_ERR_ARG;
+    }
+    if (formulation != PQP_FORM_KP && formulation != PQP_FORM_KPC) {
+        set_err("K is assembled on the host: use pqp_solve_batch (host buffers) for it");
         return PQP_ERR_UNSUPPORTED;
     }
     if (batch == 0) return PQP_OK;
@@ -454,6 +490,7 @@ int pqp_solve_batch_device(pqp_handle *h, int formulation, int batch, int total_
     bv.batch = batch; bv.n_points = d_n_points; bv.offsets = d_offsets; bv.ref = d_ref; bv.bounds = d_bounds;
     bv.x0 = d_x0; bv.end_heading = d_end_heading; bv.out_states = d_out_states; bv.out_frenet = d_out_frenet;
     bv.status = d_status; bv.iters = d_iters;
+    bv.max_k = d_max_k; bv.max_kp = d_max_kp;
     // The host does not see n_points / keep here: the kernel shape class and the shared memory are
     // chosen from the caller's bounds; a path that does not fit reports PQP_INVALID_PROBLEM.
     bv.workspace = h->d_ws;
@@ -467,7 +504,7 @@ int pqp_solve_batch_device(pqp_handle *h, int formulation, int batch, int total_
     const int k_lo = (min_keep >= 1) ? std::min(min_keep, k_hi) : 1;
     int v = -1;
     size_t smem = 0;
-    if (!device_class(h, nmax, k_lo, k_hi, &v, &smem)) {
+    if (!device_class(h, nmax, k_lo, k_hi, &v, &smem, formulation)) {
         set_err("no single kernel shape class takes every (n_points <= max_n_points, min_keep..max_keep): "
                 "tighten the bounds or use pqp_solve_batch_device_classes");
         return PQP_ERR_UNSUPPORTED;
@@ -492,14 +529,17 @@ int pqp_solve_batch_device_classes(pqp_handle *h, int formulation, int batch, in
                                    const double *d_max_k, const double *d_max_kp, pqp_state *d_out_states,
                                    double *d_out_frenet, int32_t *d_status, int32_t *d_iters, void *stream,
                                    pqp_stats *stats) {
-    (void)d_max_k; (void)d_max_kp;
-    if (!h || batch < 0 || !h_n_points || !h_keep || !d_n_points || !d_offsets || !d_ref || !d_bounds || !d_x0 ||
-        !d_end_heading || !d_out_states || !d_status) {
+    if (!h || batch < 0 || !h_n_points || (!h_keep && formulation != PQP_FORM_KPC) || !d_n_points || !d_offsets || !d_ref ||
+        !d_bounds || !d_x0 || !d_end_heading || !d_out_states || !d_status) {
         set_err("pqp_solve_batch_device_classes: bad argument");
         return PQP_ERR_ARG;
     }
-    if (formulation != PQP_FORM_KP) {
-        set_err("K / KPC are assembled on the host: use pqp_solve_batch (host buffers) for them");
+    if (formulation == PQP_FORM_KPC && (!d_max_k || !d_max_kp)) {
+        set_err("KPC needs d_max_k and d_max_kp (pqp_update_limits_device)");
+        return PQP_ERR_ARG;
+    }
+    if (formulation != PQP_FORM_KP && formulation != PQP_FORM_KPC) {
+        set_err("K is assembled on the host: use pqp_solve_batch (host buffers) for it");
         return PQP_ERR_UNSUPPORTED;
     }
     if (batch == 0) return PQP_OK;
@@ -513,9 +553,10 @@ int pqp_solve_batch_device_classes(pqp_handle *h, int formulation, int batch, in
     bv.batch = batch; bv.n_points = d_n_points; bv.offsets = d_offsets; bv.ref = d_ref; bv.bounds = d_bounds;
     bv.x0 = d_x0; bv.end_heading = d_end_heading; bv.out_states = d_out_states; bv.out_frenet = d_out_frenet;
     bv.status = d_status; bv.iters = d_iters; bv.workspace = h->d_ws; bv.debug = nullptr;
+    bv.max_k = d_max_k; bv.max_kp = d_max_kp;
     if (stats) PQP_CUDA(cudaEventRecord(h->ev[0], st));
     int launches = 0;
-    int rc = pqp_launch_kp_classes(h, bv, batch, h_n_points, nullptr, nullptr, h_keep, st, &launches);
+    int rc = pqp_launch_kp_classes(h, bv, batch, h_n_points, nullptr, nullptr, h_keep, st, &launches, formulation);
     if (rc != PQP_OK) return rc;
     if (stats) {
         memset(stats, 0, sizeof(*stats));
@@ -675,7 +716,13 @@ int pqp_solve_batch(pqp_handle *h, int formulation, int batch, const int32_t *n_
     }
     if (stats) memset(stats, 0, sizeof(*stats));
     if (batch == 0) return PQP_OK;
-    if (formulation != PQP_FORM_KP)
+    bool kpc_classes = formulation == PQP_FORM_KPC && max_k && max_kp && batch <= h->max_batch;
+    for (int b = 0; b < batch && kpc_classes; ++b) {
+        int v;
+        size_t need;
+        kpc_classes = class_for(h, n_points[b], 4, &v, &need, PQP_FORM_KPC);
+    }
+    if (formulation != PQP_FORM_KP && !kpc_classes)   // "K", and "KPC" batches with a path beyond the thread-per-station classes
         return solve_batch_generic(h, formulation, batch, n_points, ref, bounds, x0, end_heading, max_k, max_kp, out_states,
                                    out_frenet, status, iters, stats);
     if (batch > h->max_batch) {
@@ -696,7 +743,7 @@ int pqp_solve_batch(pqp_handle *h, int formulation, int batch, const int32_t *n_
         const int keep = (n >= 2) ? pqp_keep_control_steps(formulation, ref + h->h_off[b], n) : 1;
         int v;
         size_t need;
-        class_for(h, n, keep, &v, &need);
+        class_for(h, n, keep, &v, &need, formulation);
         cls[b] = v;
         need_b[b] = need;
     }
@@ -742,6 +789,13 @@ int pqp_solve_batch(pqp_handle *h, int formulation, int batch, const int32_t *n_
     bv.status = h->d_status; bv.iters = h->d_iters;
     bv.workspace = h->d_ws;
     bv.debug = nullptr;
+    if (kpc_classes) {
+        if (!h->d_max_k) {
+            PQP_CUDA(cudaMalloc(&h->d_max_k, (size_t)h->max_total * sizeof(double)));
+            PQP_CUDA(cudaMalloc(&h->d_max_kp, (size_t)h->max_total * sizeof(double)));
+        }
+        bv.max_k = h->d_max_k; bv.max_kp = h->d_max_kp;
+    }
 #ifdef PQP_PHASE_TIMING
     static long long *d_dbg = nullptr;
     if (!d_dbg) cudaMalloc(&d_dbg, sizeof(long long) * 32 * 65536);
@@ -788,6 +842,10 @@ int pqp_solve_batch(pqp_handle *h, int formulation, int batch, const int32_t *n_
         PQP_CUDA_DRAIN(cudaMemcpyAsync(h->d_bounds + o0, bounds + o0, nT * sizeof(pqp_station_bounds), cudaMemcpyHostToDevice, st));
         PQP_CUDA_DRAIN(cudaMemcpyAsync(h->d_x0 + 3 * (size_t)pb, x0 + 3 * (size_t)pb, nB * 3 * sizeof(double), cudaMemcpyHostToDevice, st));
         PQP_CUDA_DRAIN(cudaMemcpyAsync(h->d_end + pb, end_heading + pb, nB * sizeof(double), cudaMemcpyHostToDevice, st));
+        if (kpc_classes) {
+            PQP_CUDA_DRAIN(cudaMemcpyAsync(h->d_max_k + o0, max_k + o0, nT * sizeof(double), cudaMemcpyHostToDevice, st));
+            PQP_CUDA_DRAIN(cudaMemcpyAsync(h->d_max_kp + o0, max_kp + o0, nT * sizeof(double), cudaMemcpyHostToDevice, st));
+        }
         if (!ev1_done) { PQP_CUDA_DRAIN(cudaEventRecord(h->ev[1], st)); ev1_done = true; }
         // One launch per class of the chunk; a mixed-length chunk has several: they go out on the class lanes (forked
         // after the chunk's upload, joined before its download), longest class first, so that they overlap instead of
@@ -876,7 +934,8 @@ int pqp_solve_batch(pqp_handle *h, int formulation, int batch, const int32_t *n_
         PQP_CUDA(cudaEventElapsedTime(&stats->h2d_ms, h->ev[0], h->ev[1]));
         PQP_CUDA(cudaEventElapsedTime(&stats->kernel_ms, h->ev[1], h->ev[2]));
         PQP_CUDA(cudaEventElapsedTime(&stats->d2h_ms, h->ev[2], h->ev[3]));
-        stats->h2d_bytes = (int64_t)(B * sizeof(int32_t) * 3 + sizeof(int32_t) + T * (sizeof(pqp_state) + sizeof(pqp_station_bounds)) + B * 4 * sizeof(double));
+        stats->h2d_bytes = (int64_t)(B * sizeof(int32_t) * 3 + sizeof(int32_t) + T * (sizeof(pqp_state) + sizeof(pqp_station_bounds)) + B * 4 * sizeof(double) +
+                                     (kpc_classes ? T * 2 * sizeof(double) : 0));
         stats->d2h_bytes = (int64_t)(T * sizeof(pqp_state) + (out_frenet ? T * 3 * sizeof(double) : 0) + B * sizeof(int32_t) * 2);
         stats->kernel_launches = launches;
         for (size_t b = 0; b < B; ++b) {

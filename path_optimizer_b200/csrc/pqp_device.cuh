@@ -44,6 +44,8 @@ struct BatchView {
     const pqp_station_bounds *bounds;  // [sum N]
     const double *x0;                  // [B][3]
     const double *end_heading;         // [B]
+    const double *max_k = nullptr;     // [sum N] KPC only: ReferencePath::getMaxKList (per station)
+    const double *max_kp = nullptr;    // [sum N] KPC only: getMaxKpList; like the reference the solver reads entry j of a path for control j
     pqp_state *out_states;             // [sum N]
     double *out_frenet;                // [sum N][3] or nullptr
     int32_t *status;                   // [B]

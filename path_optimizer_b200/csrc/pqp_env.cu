@@ -96,12 +96,13 @@ struct BoundsArgs {
     const double *knots, *xc, *yc;
     pqp_station_bounds *out;
     int32_t *n_valid;              // pre-set to n_points; atomicMin with the first blocked station
+    int first_path;                // grid.y is capped at 65535: a larger batch is launched in tiles of paths
 };
 
 // grid (ceil(4*maxN/128), batch): thread = (station, circle) of path blockIdx.y
 __global__ void __launch_bounds__(128)
 pqp_bounds_kernel(const __grid_constant__ BoundsArgs a) {
-    const int b = blockIdx.y;
+    const int b = a.first_path + blockIdx.y;
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const int i = t >> 2, j = t & 3;
     const int n = a.n_points[b];
@@ -316,8 +317,9 @@ int launch_bounds_kernel(pqp_handle *h, EnvState *e, int mode, int batch, int ma
     a.out = h->d_bounds;
     a.n_valid = e->d_nvalid;
     PQP_CUDA(cudaMemcpyAsync(e->d_nvalid, h->d_n, (size_t)batch * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
-    if (max_n > 0) {
-        dim3 grid((unsigned)((4 * max_n + 127) / 128), (unsigned)batch);
+    for (int first = 0; max_n > 0 && first < batch; first += 65535) {
+        a.first_path = first;
+        dim3 grid((unsigned)((4 * max_n + 127) / 128), (unsigned)std::min(65535, batch - first));
         pqp_bounds_kernel<<<grid, 128, 0, st>>>(a);
         PQP_CUDA(cudaGetLastError());
     }
@@ -628,8 +630,8 @@ int pqp_plan_batch(pqp_handle *h, int formulation, int bounds_mode, int output_m
         pqp_set_err("pqp_plan_batch: bad argument");
         return PQP_ERR_ARG;
     }
-    if (formulation != PQP_FORM_KP) {
-        pqp_set_err("pqp_plan_batch chains the device-resident KP solve; K / KPC are assembled on the host "
+    if (formulation != PQP_FORM_KP && formulation != PQP_FORM_KPC) {
+        pqp_set_err("pqp_plan_batch chains the device-resident KP / KPC solve; K is assembled on the host "
                     "(use pqp_update_bounds_batch + pqp_solve_batch + pqp_finish_raw_batch)");
         return PQP_ERR_UNSUPPORTED;
     }
@@ -667,7 +669,18 @@ int pqp_plan_batch(pqp_handle *h, int formulation, int bounds_mode, int output_m
         bv.batch = batch; bv.n_points = e->d_nvalid; bv.offsets = h->d_off; bv.ref = h->d_ref; bv.bounds = h->d_bounds;
         bv.x0 = h->d_x0; bv.end_heading = h->d_end; bv.out_states = h->d_out; bv.out_frenet = nullptr;
         bv.status = h->d_status; bv.iters = h->d_iters; bv.workspace = h->d_ws; bv.debug = nullptr;
-        rc = pqp_launch_kp_classes(h, bv, batch, nv.data(), h->h_off, ref, nullptr, st, &qp_launches);
+        if (formulation == PQP_FORM_KPC) {
+            // updateLimits (reference_path_impl.cpp:203-235) between updateBounds and the QP, as solveWithoutSmoothing
+            // does (path_optimizer.cpp:100-105): limits from the v, a fields of the uploaded reference states
+            if (!h->d_max_k) {
+                PQP_CUDA(cudaMalloc(&h->d_max_k, (size_t)h->max_total * sizeof(double)));
+                PQP_CUDA(cudaMalloc(&h->d_max_kp, (size_t)h->max_total * sizeof(double)));
+            }
+            rc = pqp_update_limits_device(h, 0, (int)T, h->d_ref, h->d_max_k, h->d_max_kp, st);
+            if (rc != PQP_OK) return rc;
+            bv.max_k = h->d_max_k; bv.max_kp = h->d_max_kp;
+        }
+        rc = pqp_launch_kp_classes(h, bv, batch, nv.data(), h->h_off, ref, nullptr, st, &qp_launches, formulation);
         if (rc != PQP_OK) return rc;
     }
     PQP_CUDA(cudaEventRecord(e->ev[3], st));

@@ -35,12 +35,12 @@ struct pqp_handle {
     // NCCL communicator bound to this handle's device (pqp_multi.cu; void*: nccl.h stays out of this header)
     void *nccl_comm = nullptr;
     // cached choice of pqp_solve_batch_device for (max_n_points, min_keep, max_keep)
-    int dc_nmax = -1, dc_klo = -1, dc_khi = -1, dc_skip = -1, dc_v = -1;
+    int dc_nmax = -1, dc_klo = -1, dc_khi = -1, dc_skip = -1, dc_v = -1, dc_form = 0;
     size_t dc_smem = 0;
     // class plan of the last pqp_launch_kp_classes call (reused while the batch shape stays the same)
     struct ClassPlan {
         bool valid = false;
-        int skip = 0;
+        int skip = 0, form = 0;
         cudaStream_t stream = nullptr;
         std::vector<int32_t> n, keep;
         int count_v[PQP_MAX_VARIANTS] = {}, start_v[PQP_MAX_VARIANTS + 1] = {};
@@ -51,6 +51,7 @@ struct pqp_handle {
     pqp_state *d_ref = nullptr, *d_out = nullptr;
     pqp_station_bounds *d_bounds = nullptr;
     double *d_x0 = nullptr, *d_end = nullptr, *d_frenet = nullptr, *d_ws = nullptr;
+    double *d_max_k = nullptr, *d_max_kp = nullptr;   // KPC limits of the host-buffer / plan entry points (allocated on first use)
     // pinned host scratch for the small per-batch arrays
     int32_t *h_off = nullptr, *h_order = nullptr;
     // generic-kernel staging (grow-only): one device blob + one pinned host blob
@@ -67,7 +68,7 @@ struct pqp_handle {
 // them from the host copy `ref` of the reference states.  Used by pqp_plan_batch after the bounds stage and by
 // pqp_solve_batch_device_classes.
 int pqp_launch_kp_classes(pqp_handle *h, const pqp::BatchView &bv, int batch, const int32_t *n, const int32_t *off,
-                          const pqp_state *ref, const int32_t *keep, cudaStream_t st, int *launches);
+                          const pqp_state *ref, const int32_t *keep, cudaStream_t st, int *launches, int form = 0 /* PQP_FORM_KP; 2 = KPC (bv.max_k / max_kp set) */);
 
 // thread-local error text returned by pqp_last_error()
 extern thread_local char pqp_g_err[512];

@@ -11,7 +11,7 @@
 #ifndef PQP_KP3_MAXNREG
 #define PQP_KP3_MAXNREG 0
 #endif
-template <int IMAX, int BW, int NW, int MMAX>
+template <int IMAX, int BW, int NW, int MMAX, int FORM = 0>
 __global__ void
 #if PQP_KP3_MAXNREG
 __maxnreg__(PQP_KP3_MAXNREG)   // (diagnostics: registers are per SM sub-partition, 16 K for the warps that share one)
@@ -24,8 +24,8 @@ pqp_kp3_solve_kernel(const __grid_constant__ pqp::DevParams prm, const __grid_co
     int prob = blockIdx.x;
     if (order) prob = order[prob];
     pqp::Cta c{pqp::Warp(), pqp::CtaSync(), (int)(threadIdx.x >> 5), NW, pqp_smem};
-    constexpr int kRes = pqp::Kp3<IMAX, BW, NW, MMAX>::kCtaScratch;
-    pqp::Kp3<IMAX, BW, NW, MMAX>::solve_path(c, prm, bv, prob, pqp_smem + kRes, (size_t)smem_doubles - kRes);
+    constexpr int kRes = pqp::Kp3<IMAX, BW, NW, MMAX, FORM>::kCtaScratch;
+    pqp::Kp3<IMAX, BW, NW, MMAX, FORM>::solve_path(c, prm, bv, prob, pqp_smem + kRes, (size_t)smem_doubles - kRes);
 }
 
 #define PQP_KP3_TU(I, B, W, MM)                                                                                   \
@@ -36,4 +36,14 @@ pqp_kp3_solve_kernel(const __grid_constant__ pqp::DevParams prm, const __grid_co
     void pqp_variant_k3_##I##_##B##_##W##_##MM(PqpVariant *out) {                                                 \
         *out = PqpVariant{I, B, W * 32, (const void *)pqp_kp3_solve_kernel<I, B, W, MM>, tu_smem, tu_fits,        \
                           "pqp_kp3_solve_kernel<" #I "," #B "," #W "," #MM ">"};                                  \
+    }
+
+// The same for the "KPC" formulation (SolverKpAsInputConstrained): Kp3<..., FORM = 2>, keep_control_steps fixed at 4.
+#define PQP_KP3C_TU(I, B, W, MM)                                                                                  \
+    typedef pqp::Kp3<I, B, W, MM, 2> TuK;                                                                         \
+    static size_t tu_smem(int n, int keep) { return (TuK::kCtaScratch + TuK::smem_doubles(TuK::dims(n, keep))) * sizeof(double); } \
+    static bool tu_fits(int n, int keep) { return keep == 4 && TuK::fits(n, keep); }                              \
+    void pqp_variant_k3c_##I##_##B##_##W##_##MM(PqpVariant *out) {                                                \
+        *out = PqpVariant{I, B, W * 32, (const void *)pqp_kp3_solve_kernel<I, B, W, MM, 2>, tu_smem, tu_fits,     \
+                          "pqp_kp3_solve_kernel<" #I "," #B "," #W "," #MM ",KPC>"};                              \
     }

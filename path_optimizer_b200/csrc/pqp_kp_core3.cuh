@@ -47,10 +47,20 @@ PQP_HD Kp3Dims kp3_dims_raw(int N, int keep, int mmax = 17) {
 
 // MMAX = most separators a path may have: 17 (two CTAs of four warps per SM) or 34 for the eight-warp form, which
 // keeps the interiors of a 200-station path at 17 unknowns instead of 37 (the interior solves are the serial part).
-template <int IMAX, int BW, int NW, int MMAX = 17>
+// FORM = 0: "KP" (SolverKpAsInput); FORM = 2: "KPC" (SolverKpAsInputConstrained, solver_kp_as_input_constrained.cpp:13-221):
+// the same banded reduced KKT -- its extra slacks (curvature slack per station, curvature-rate slack per held control)
+// couple to kappa / u through soft-row PAIRS of equal weight and opposite sign and therefore decouple exactly, like the
+// corridor slack -- with another row set per station: three hard circles (d1, d2, d4), one soft pair (d3), a soft
+// pair instead of the curvature box, keep_control_steps fixed at 4, the end offset row free.
+template <int IMAX, int BW, int NW, int MMAX = 17, int FORM = 0>
 struct Kp3 {
+    static constexpr bool kKPC = (FORM == 2);
+    static constexpr int kWE = kKPC ? 10 : 9;    // row scalings E kept per station in the workspace
+    static constexpr int kWD = kKPC ? 5 : 4;     // column scalings D per station
+    static constexpr int kWR = kKPC ? 12 : 11;   // parked dual rows per station
+    static constexpr int kUbF = kKPC ? 11 : 4;   // shared-memory fields per held control
     static constexpr int kT = NW * 32;     // threads = max stations
-    using K2 = Kp2<IMAX, BW, NW * 100 + MMAX>;   // reuses the unrolled interior factor / solve (own copies per kernel)
+    using K2 = Kp2<IMAX, BW, NW * 100 + MMAX + 1000 * FORM>;   // reuses the unrolled interior factor / solve (own copies per kernel)
     // Small interiors keep a DENSE inverse (row-major, [interior][row][kRow]) in place of the band
     // factor once a refactorisation is done: y = K_I^-1 r_I then is a mat-vec spread over every thread
     // of the CTA instead of M serial banded substitutions on warp 0 (the longest phase of an iteration).
@@ -67,6 +77,7 @@ struct Kp3 {
     // 227 KB a CTA can opt into: their refactorisation scratch is overlaid on the rhs / y vectors (free while a
     // refactorisation runs; both are zeroed again at its end so that the padded entries stay finite).
     static constexpr bool kScratchOnVec = !kDense && (NW > 8) && kTwoLevel && (2 * ((IMAX + 3) | 1) >= kRed2 + 27 + 12);
+    static_assert(!(kKPC && kScratchOnVec), "the long-path classes have no room for the KPC control state");
     // exchange rows of kT doubles: 0..5, ds, separator rhs; the long-path classes park the separator rhs in row 5
     // (only the Ruiz sweeps and diagnostic builds use that row otherwise)
     static constexpr int kExRows = kScratchOnVec ? 7 : 8;
@@ -100,11 +111,11 @@ struct Kp3 {
         // in the unused tails of the separator rows 3 (x_S: 3M <= 102 entries used), 4 (<= 51 used) and 5 (<= 102 used).
         PQP_DEV int chp() const { return (ch + 1) & ~1; }
         PQP_DEV double *endr() const { return kScratchOnVec ? ex(4) + 56 : ex(kExRows); }   // vEY vEH WEY WEH lEH uEH . .
-        PQP_DEV double *ubs(int f) const {                                                 // f: 0 v, 1 W, 2 x, 3 sigma
+        PQP_DEV double *ubs(int f) const {                                                 // f: 0 v, 1 W, 2 x, 3 sigma (, 4.. KPC)
             if (!kScratchOnVec) return ex(kExRows) + 8 + f * chp();
             return f == 0 ? ex(4) + 64 : f == 3 ? ex(4) + 64 + chp() : f == 1 ? ex(3) + 104 : ex(5) + 104;
         }
-        PQP_HD static int aux_doubles(int ch_) { return kScratchOnVec ? 0 : 8 + 4 * ((ch_ + 1) & ~1); }
+        PQP_HD static int aux_doubles(int ch_) { return kScratchOnVec ? 0 : 8 + kUbF * ((ch_ + 1) & ~1); }
         PQP_DEV double *fac() const { return ex(kExRows) + aux_doubles(ch); }   // [IMAX*(BW+1)*M]; kDense: then K_I^-1 [M][IMAX][kRow]
         PQP_DEV double *T() const { return fac() + kFacSlots * M; }       // spikes T[c][pos], c < 6: [6*nv]
         PQP_DEV int nSd() const { return kTwoLevel ? 3 * ((M + 1) / 2) : nS; }   // order of the dense separator inverse
@@ -139,6 +150,9 @@ struct Kp3 {
         double dst, qt;             // transition i-1 -> i
         double sga, sgb, sgc, sgs, ksinv;
         double xa, xb, xc, xs;      // iterate
+        // KPC only: soft curvature-limit pair (kappa + sk >= -mk, kappa - sk <= mk), the box of its slack sk, the third
+        // hard circle row (d4); the KP names H3 / S4 then stand for the d2 hard row and the d3 soft pair
+        double vKL, vKU, WK, mk, vSK, WSK, uSK, xk, sgk, kkinv, vH4, WH4, lH4, uH4;
         int pos, posp, posup;       // padded index of a_i, a_{i-1}, u of transition i-1
         bool live, first, last, sep;
     };
@@ -188,7 +202,9 @@ struct Kp3 {
         const pqp_station_bounds *bnd = bv.bounds + off;
         pqp_state *out = bv.out_states + off;
         int keep = 1;
-        {
+        if constexpr (kKPC) {
+            keep = 4;               // solver_kp_as_input_constrained.cpp:17
+        } else {
             double interval = 0.0;  // solver.cpp:21-27, solver_kp_as_input.cpp:17
             for (int i = 1; i < N && i < 10; ++i) {
                 const double dd = ref[i].s - ref[i - 1].s;
@@ -202,7 +218,7 @@ struct Kp3 {
         const double qnan = nan("");
         const bool shape_ok = fits(N, keep);
         const Kp3Dims d = dims(shape_ok ? N : 2, shape_ok ? keep : 1);
-        if (!shape_ok || smem_doubles(d) > smem_cap || !bv.workspace) {
+        if (!shape_ok || smem_doubles(d) > smem_cap || !bv.workspace || (kKPC && (!bv.max_k || !bv.max_kp))) {
             if (tid == 0) {
                 bv.status[prob] = PQP_INVALID_PROBLEM;
                 if (bv.iters) bv.iters[prob] = 0;
@@ -224,6 +240,11 @@ struct Kp3 {
         double *ws = kp_ws_base(bv.workspace, off, prob);  // E[9] per station, [9N..] EUB, EEnd; then D
         double *wold = kp_ws_wold(ws, N);                  // w = v - clamp(v) of the previous iterate (infeasibility check)
         const KpDims ka = kp_dims(N, keep);
+        // workspace layout of the scalings: E per station [kWE], E of the control rows, the two end rows, D per station, D per control
+        const size_t oEU = (size_t)kWE * N, oEnd = oEU + (size_t)(kKPC ? 2 : 1) * ch, oD = oEnd + 2, oDu = oD + (size_t)kWD * N;
+        // per-form row coefficients: hard rows H1, H3 (, H4), soft pairs S4 (, S2); bounds of the end-offset row
+        const double cH1 = pm.d1, cH3 = kKPC ? pm.d2 : pm.d3, cS4 = kKPC ? pm.d3 : pm.d4, cS2 = pm.d2, cH4 = pm.d4;
+        const double lEY = kKPC ? -kOsqpInfty : -1.0, uEY = kKPC ? kOsqpInfty : 1.0;   // :204-205: end e_y is not constrained in KPC
         // ---- station / control ownership and padded positions
         St st;
         const int i = tid;
@@ -284,6 +305,8 @@ struct Kp3 {
         st.b0 = st.b1 = st.b2 = 0.0;
         st.lH1 = st.lH3 = -1.0; st.uH1 = st.uH3 = 1.0;
         st.uS4m = st.uS2m = 0.0; st.lS4p = st.lS2p = 0.0;
+        st.vKL = st.vKU = st.WK = st.mk = st.vSK = st.WSK = st.uSK = st.xk = st.sgk = st.kkinv = 0.0;
+        st.vH4 = st.WH4 = 0.0; st.lH4 = -1.0; st.uH4 = 1.0;
         if (st.live) {
             const double kap = ref[i].k;
             if (!st.last) {
@@ -302,10 +325,20 @@ struct Kp3 {
             }
             const pqp_station_bounds bb = bnd[i];
             st.lH1 = bb.c0_lb; st.uH1 = bb.c0_ub;
-            st.lH3 = bb.c2_lb; st.uH3 = bb.c2_ub;
-            st.uS4m = bb.c3_ub - pm.margin; st.lS4p = bb.c3_lb + pm.margin;
-            st.uS2m = bb.c1_ub - pm.margin; st.lS2p = bb.c1_lb + pm.margin;
-            if (!(bb.c0_lb <= bb.c0_ub) || !(bb.c2_lb <= bb.c2_ub)) invalid = 1;
+            if constexpr (kKPC) {   // solver_kp_as_input_constrained.cpp:185-200: hard c0, c1, c3; soft c2
+                st.lH3 = bb.c1_lb; st.uH3 = bb.c1_ub;
+                st.lH4 = bb.c3_lb; st.uH4 = bb.c3_ub;
+                st.uS4m = bb.c2_ub - pm.margin; st.lS4p = bb.c2_lb + pm.margin;
+                st.uS2m = 0.0; st.lS2p = 0.0;
+                st.mk = bv.max_k[off + i];                               // :160-172
+                st.uSK = fmax(pm.kmax - st.mk, 0.0);
+                if (!(bb.c3_lb <= bb.c3_ub) || !(-st.mk <= kOsqpInfty) || !(-kOsqpInfty <= st.mk) || !(0.0 <= st.uSK)) invalid = 1;
+            } else {
+                st.lH3 = bb.c2_lb; st.uH3 = bb.c2_ub;
+                st.uS4m = bb.c3_ub - pm.margin; st.lS4p = bb.c3_lb + pm.margin;
+                st.uS2m = bb.c1_ub - pm.margin; st.lS2p = bb.c1_lb + pm.margin;
+            }
+            if (!(st.lH1 <= st.uH1) || !(st.lH3 <= st.uH3)) invalid = 1;
             if (!(-kOsqpInfty <= st.uS4m) || !(st.lS4p <= kOsqpInfty) || !(-kOsqpInfty <= st.uS2m) ||
                 !(st.lS2p <= kOsqpInfty))
                 invalid = 1;
@@ -319,6 +352,11 @@ struct Kp3 {
         // end rows (only the thread of station N-1 touches them) and held controls (threads j < ch): in shared memory
         double *const er = s.endr();
         double *const uS0 = s.ubs(0), *const uS1 = s.ubs(1), *const uS2 = s.ubs(2), *const uS3 = s.ubs(3);
+        // KPC: the control has a soft rate-limit pair (u + p >= -mkp, u - p <= mkp) and the box of its slack p >= 0:
+        // field 0 v(KPL) 1 W(KP pair) 2 x(u) 3 sigma(u) | 4 v(KPU) 5 v(box p) 6 W(box p) 7 x(p) 8 sigma(p) 9 1 / pivot(p) 10 mkp
+        double *const uSx = s.ubs(4);   // fields 4.. at uSx[(f - 4) * s.chp() + tid]
+        const int uCp = s.chp();
+#define PQP_UBF(f) uSx[((f) - 4) * uCp + tid]
 #define vEY er[0]
 #define vEH er[1]
 #define WEY er[2]
@@ -340,7 +378,89 @@ struct Kp3 {
             // ================= Ruiz equilibration + cost scaling (OSQP scale_data) =================
             double Da = 1, Db = 1, Dc = 1, Dsv = 1, Du = 1, Dt = 1;
             double e0 = 1, e1 = 1, e2 = 1, eKB = 1, eSB = 1, eH1 = 1, eH3 = 1, eS4 = 1, eS2 = 1, eUB = 1, eEY = 1, eEH = 1;
+            double Dk = 1, Dp = 1, eSK = 1, eH4 = 1, eSKP = 1;   // KPC: sk, p columns; sk box, d4 hard row, p box  (eKB = the kappa pair, eUB = the rate pair)
             const double ad1 = fabs(pm.d1), ad2 = fabs(pm.d2), ad3 = fabs(pm.d3), ad4 = fabs(pm.d4);
+            if constexpr (kKPC) {
+                const double aH1 = fabs(cH1), aH3 = fabs(cH3), aH4 = fabs(cH4), aS4 = fabs(cS4);
+                const double wk_ = 500.0, wp_ = 25000.0 * keep;   // w_k_slack, w_kp_slack * keep_control_steps_ (:52-53,63)
+                for (int sweep = 0; sweep < pm.scaling; ++sweep) {
+                    if (st.live) {
+                        s.ex(0)[i] = Da; s.ex(1)[i] = Db; s.ex(2)[i] = Dc;
+                        s.ex(3)[i] = e0; s.ex(4)[i] = e1; s.ex(5)[i] = e2;
+                    }
+                    if (ub.live) s.tr()[tid] = Du;
+                    c.sync();
+                    double fDa = 1, fDb = 1, fDc = 1, fDs = 1, fDu = 1, fDk = 1, fDp = 1;
+                    double f0 = 1, f1 = 1, f2 = 1, fK = 1, fSB = 1, fSK = 1, fH1 = 1, fH3 = 1, fH4 = 1, fS4 = 1, fKP = 1, fSKP = 1, fEY = 1, fEH = 1;
+                    if (st.live) {
+                        double Aa = fmax(fmax(e0, eH1), fmax(eH3, fmax(eH4, eS4)));
+                        double Ab = fmax(fmax(e1, eH1 * aH1), fmax(eH3 * aH3, fmax(eH4 * aH4, eS4 * aS4)));
+                        double Ac = fmax(e2, eKB);
+                        if (!st.last) {
+                            const double e0n = s.ex(3)[i + 1], e1n = s.ex(4)[i + 1], e2n = s.ex(5)[i + 1];
+                            const double aq = fabs(st.q10);
+                            Aa = fmax(Aa, fmax(e0n, e1n * aq));
+                            Ab = fmax(Ab, fmax(e0n * st.ds, e1n));
+                            Ac = fmax(Ac, fmax(e1n * st.ds, e2n));
+                        } else {
+                            Aa = fmax(Aa, eEY);
+                            Ab = fmax(Ab, eEH);
+                        }
+                        const double As = fmax(eSB, eS4);
+                        const double Ak = fmax(eSK, eKB);
+                        fDa = 1.0 / sqrt(limit_scaling(fmax(cost_c * pm.w_pq * Da * Da, Aa * Da)));
+                        fDb = 1.0 / sqrt(limit_scaling(Ab * Db));
+                        fDc = 1.0 / sqrt(limit_scaling(fmax(cost_c * pm.w_c * Dc * Dc, Ac * Dc)));
+                        fDs = 1.0 / sqrt(limit_scaling(fmax(cost_c * pm.w_s * Dsv * Dsv, As * Dsv)));
+                        fDk = 1.0 / sqrt(limit_scaling(fmax(cost_c * wk_ * Dk * Dk, Ak * Dk)));
+                        double r0, r1, r2;
+                        if (st.first) {
+                            r0 = e0 * Da; r1 = e1 * Db; r2 = e2 * Dc;
+                        } else {
+                            const double Dat = s.ex(0)[i - 1], Dbt = s.ex(1)[i - 1], Dct = s.ex(2)[i - 1];
+                            const double Dut = s.tr()[(i - 1) / keep];
+                            const double aqt = fabs(st.qt);
+                            r0 = e0 * fmax(Da, fmax(Dat, st.dst * Dbt));
+                            r1 = e1 * fmax(fmax(Db, aqt * Dat), fmax(Dbt, st.dst * Dct));
+                            r2 = e2 * fmax(Dc, fmax(Dct, st.dst * Dut));
+                        }
+                        f0 = 1.0 / sqrt(limit_scaling(r0));
+                        f1 = 1.0 / sqrt(limit_scaling(r1));
+                        f2 = 1.0 / sqrt(limit_scaling(r2));
+                        fK = 1.0 / sqrt(limit_scaling(eKB * fmax(Dc, Dk)));
+                        fSB = 1.0 / sqrt(limit_scaling(eSB * Dsv));
+                        fSK = 1.0 / sqrt(limit_scaling(eSK * Dk));
+                        fH1 = 1.0 / sqrt(limit_scaling(eH1 * fmax(Da, aH1 * Db)));
+                        fH3 = 1.0 / sqrt(limit_scaling(eH3 * fmax(Da, aH3 * Db)));
+                        fH4 = 1.0 / sqrt(limit_scaling(eH4 * fmax(Da, aH4 * Db)));
+                        fS4 = 1.0 / sqrt(limit_scaling(eS4 * fmax(Da, fmax(aS4 * Db, Dsv))));
+                        if (st.last) {
+                            fEY = 1.0 / sqrt(limit_scaling(eEY * Da));
+                            fEH = 1.0 / sqrt(limit_scaling(eEH * Db));
+                        }
+                    }
+                    if (ub.live) {
+                        double Au = eUB;
+                        for (int t = ub.t0; t <= ub.t1; ++t) Au = fmax(Au, s.ex(5)[t + 1] * s.dsS()[t]);
+                        fDu = 1.0 / sqrt(limit_scaling(fmax(cost_c * (keep * pm.w_cr) * Du * Du, Au * Du)));
+                        fDp = 1.0 / sqrt(limit_scaling(fmax(cost_c * wp_ * Dp * Dp, fmax(eSKP, eUB) * Dp)));
+                        fKP = 1.0 / sqrt(limit_scaling(eUB * fmax(Du, Dp)));
+                        fSKP = 1.0 / sqrt(limit_scaling(eSKP * Dp));
+                    }
+                    Da *= fDa; Db *= fDb; Dc *= fDc; Dsv *= fDs; Du *= fDu; Dk *= fDk; Dp *= fDp;
+                    e0 *= f0; e1 *= f1; e2 *= f2; eKB *= fK; eSB *= fSB; eSK *= fSK; eH1 *= fH1; eH3 *= fH3; eH4 *= fH4; eS4 *= fS4;
+                    eUB *= fKP; eSKP *= fSKP; eEY *= fEY; eEH *= fEH;
+                    double part = 0.0;   // (the N - ch unused slack variables of the reference have zero cost and no row: D = 1, nothing here)
+                    if (st.live)
+                        part += cost_c * pm.w_pq * Da * Da + cost_c * pm.w_c * Dc * Dc + cost_c * pm.w_s * Dsv * Dsv +
+                                cost_c * wk_ * Dk * Dk;
+                    if (ub.live) part += cost_c * (keep * pm.w_cr) * Du * Du + cost_c * wp_ * Dp * Dp;
+                    const double mean = c.sum(part) / (double)(6 * N + ch);   // (contains CTA barriers)
+                    double ct = fmax(mean, 1.0);
+                    ct = limit_scaling(ct);
+                    cost_c = cost_c * (1.0 / ct);
+                }
+            } else
             for (int sweep = 0; sweep < pm.scaling; ++sweep) {
                 // publish what neighbours need: D of this station, E of its dynamics rows, Du
                 if (st.live) {
@@ -417,23 +537,34 @@ struct Kp3 {
             }
             // publish E, D to the workspace (read back at residual checks / refactorisations)
             if (st.live) {
-                double *w9 = ws + 9 * (size_t)i;
-                w9[0] = e0; w9[1] = e1; w9[2] = e2; w9[3] = eKB; w9[4] = eSB; w9[5] = eH1; w9[6] = eH3; w9[7] = eS4; w9[8] = eS2;
-                double *wD = ws + 9 * (size_t)N + ch + 2 + 4 * (size_t)i;
+                double *w9 = ws + (size_t)kWE * i;
+                w9[0] = e0; w9[1] = e1; w9[2] = e2; w9[3] = eKB; w9[4] = eSB; w9[5] = eH1; w9[6] = eH3; w9[7] = eS4;
+                w9[8] = kKPC ? eH4 : eS2;
+                double *wD = ws + oD + (size_t)kWD * i;
                 wD[0] = Da; wD[1] = Db; wD[2] = Dc; wD[3] = Dsv;
+                if constexpr (kKPC) { w9[9] = eSK; wD[4] = Dk; st.sgk = pm.sigma / (Dk * Dk); }
                 st.sga = pm.sigma / (Da * Da); st.sgb = pm.sigma / (Db * Db);
                 st.sgc = pm.sigma / (Dc * Dc); st.sgs = pm.sigma / (Dsv * Dsv);
-                if (st.last) { ws[9 * (size_t)N + ch] = eEY; ws[9 * (size_t)N + ch + 1] = eEH; }
+                if (st.last) { ws[oEnd] = eEY; ws[oEnd + 1] = eEH; }
             }
             if (ub.live) {
-                ws[9 * (size_t)N + tid] = eUB;
-                ws[13 * (size_t)N + ch + 2 + tid] = Du;
+                ws[oEU + tid] = eUB;
+                ws[oDu + tid] = Du;
                 PQP_UBSG = pm.sigma / (Du * Du);
+                if constexpr (kKPC) {
+                    ws[oEU + ch + tid] = eSKP;
+                    ws[oDu + ch + tid] = Dp;
+                    PQP_UBF(8) = pm.sigma / (Dp * Dp);
+                    PQP_UBF(10) = bv.max_kp[off + tid];   // :173-182 (entry j of the path's list for control j)
+                }
             }
             // (the shared-memory state of the end rows and the held controls is set up only now: in the long-path classes it
             // sits in the tails of exchange rows the Ruiz sweeps have just used)
             if (tid == 0) { er[0] = 0.0; er[1] = 0.0; er[2] = 0.0; er[3] = 0.0; er[4] = lEH0; er[5] = uEH0; }
-            if (ub.live) { PQP_UBX = 0.0; PQP_UBV = 0.0; PQP_UBW = 0.0; }
+            if (ub.live) {
+                PQP_UBX = 0.0; PQP_UBV = 0.0; PQP_UBW = 0.0;
+                if constexpr (kKPC) { PQP_UBF(4) = 0.0; PQP_UBF(5) = 0.0; PQP_UBF(6) = 0.0; PQP_UBF(7) = 0.0; PQP_UBF(9) = 0.0; }
+            }
             // cold start: OSQP's first iteration from zero leaves x = 0, v = 0 (see pqp_kp_core.cuh)
             st.vD0 = st.vD1 = st.vD2 = st.vKB = st.vSB = st.vH1 = st.vH3 = 0.0;
             st.vS4m = st.vS4p = st.vS2m = st.vS2p = 0.0;
@@ -453,22 +584,42 @@ struct Kp3 {
 #endif
                 // ---- row weights W = rho_row E^2 from the workspace E
                 if (st.live) {
-                    const double *w9 = ws + 9 * (size_t)i;
+                    const double *w9 = ws + (size_t)kWE * i;
                     st.WD0 = kp_w_eq(w9[0], rho); st.WD1 = kp_w_eq(w9[1], rho); st.WD2 = kp_w_eq(w9[2], rho);
-                    st.WKB = kp_w_box(w9[3], -pm.kmax, pm.kmax, rho);
                     st.WSB = kp_w_box(w9[4], 0.0, pm.margin, rho);
                     st.WH1 = kp_w_box(w9[5], st.lH1, st.uH1, rho);
                     st.WH3 = kp_w_box(w9[6], st.lH3, st.uH3, rho);
                     st.WS4 = kp_w_box(w9[7], -kOsqpInfty, st.uS4m, rho);
-                    st.WS2 = kp_w_box(w9[8], -kOsqpInfty, st.uS2m, rho);
-                    if (st.last) {
-                        WEY = kp_w_box(ws[9 * (size_t)N + ch], -1.0, 1.0, rho);
-                        WEH = kp_w_box(ws[9 * (size_t)N + ch + 1], lEH, uEH, rho);
+                    if constexpr (kKPC) {
+                        st.WK = kp_w_box(w9[3], -st.mk, kOsqpInfty, rho);      // both rows of the pair fall in the same rho class
+                        st.WH4 = kp_w_box(w9[8], st.lH4, st.uH4, rho);
+                        st.WSK = kp_w_box(w9[9], 0.0, st.uSK, rho);
+                    } else {
+                        st.WKB = kp_w_box(w9[3], -pm.kmax, pm.kmax, rho);
+                        st.WS2 = kp_w_box(w9[8], -kOsqpInfty, st.uS2m, rho);
                     }
-                    st.ksinv = 1.0 / (cost_c * pm.w_s + st.sgs + st.WSB + 2.0 * st.WS4 + 2.0 * st.WS2);
+                    if (st.last) {
+                        WEY = kp_w_box(ws[oEnd], lEY, uEY, rho);
+                        WEH = kp_w_box(ws[oEnd + 1], lEH, uEH, rho);
+                    }
+                    if constexpr (kKPC) {
+                        st.ksinv = 1.0 / (cost_c * pm.w_s + st.sgs + st.WSB + 2.0 * st.WS4);
+                        st.kkinv = 1.0 / (cost_c * 500.0 + st.sgk + st.WSK + 2.0 * st.WK);
+                    } else {
+                        st.ksinv = 1.0 / (cost_c * pm.w_s + st.sgs + st.WSB + 2.0 * st.WS4 + 2.0 * st.WS2);
+                    }
                     s.ex(0)[i] = st.WD0; s.ex(1)[i] = st.WD1; s.ex(2)[i] = st.WD2;   // neighbours need these
                 }
-                if (ub.live) PQP_UBW = kp_w_box(ws[9 * (size_t)N + tid], -kOsqpInfty, kOsqpInfty, rho);
+                if (ub.live) {
+                    if constexpr (kKPC) {
+                        const double mkp = PQP_UBF(10);
+                        PQP_UBW = kp_w_box(ws[oEU + tid], -mkp, kOsqpInfty, rho);
+                        PQP_UBF(6) = kp_w_box(ws[oEU + ch + tid], 0.0, kOsqpInfty, rho);
+                        PQP_UBF(9) = 1.0 / (cost_c * (25000.0 * keep) + PQP_UBF(8) + PQP_UBF(6) + 2.0 * PQP_UBW);
+                    } else {
+                        PQP_UBW = kp_w_box(ws[oEU + tid], -kOsqpInfty, kOsqpInfty, rho);
+                    }
+                }
                 // zero the factor storage (identity on padded rows)
                 for (int k = tid; k < IMAX * (BW + 1) * M; k += kT) {
                     const int p = k % M, kd = k / M, dd = kd % (BW + 1), kk = kd / (BW + 1);
@@ -488,12 +639,20 @@ struct Kp3 {
                 const double d1 = pm.d1, d2 = pm.d2, d3 = pm.d3, d4 = pm.d4;
                 double da = 0, db = 0, dc = 0, kba = 0, kca = 0, kcb = 0;
                 if (st.live) {
+                    if constexpr (kKPC) {
+                        da = cost_c * pm.w_pq + st.sga + st.WD0 + N0 + N1 * st.q10 * st.q10 + st.WH1 + st.WH3 + st.WH4 + 2.0 * st.WS4;
+                        db = st.sgb + st.WD1 + N0 * st.ds * st.ds + N1 + st.WH1 * cH1 * cH1 + st.WH3 * cH3 * cH3 +
+                             st.WH4 * cH4 * cH4 + 2.0 * st.WS4 * cS4 * cS4;
+                        dc = cost_c * pm.w_c + st.sgc + st.WD2 + N1 * st.ds * st.ds + N2 + 2.0 * st.WK;
+                        kba = N0 * st.ds + N1 * st.q10 + st.WH1 * cH1 + st.WH3 * cH3 + st.WH4 * cH4 + 2.0 * st.WS4 * cS4;
+                    } else {
                     da = cost_c * pm.w_pq + st.sga + st.WD0 + N0 + N1 * st.q10 * st.q10 + st.WH1 + st.WH3 + 2.0 * st.WS4 + 2.0 * st.WS2;
                     db = st.sgb + st.WD1 + N0 * st.ds * st.ds + N1 + st.WH1 * d1 * d1 + st.WH3 * d3 * d3 +
                          2.0 * st.WS4 * d4 * d4 + 2.0 * st.WS2 * d2 * d2;
                     dc = cost_c * pm.w_c + st.sgc + st.WD2 + N1 * st.ds * st.ds + N2 + st.WKB;
-                    if (st.last) { da += WEY; db += WEH; }
                     kba = N0 * st.ds + N1 * st.q10 + st.WH1 * d1 + st.WH3 * d3 + 2.0 * st.WS4 * d4 + 2.0 * st.WS2 * d2;
+                    }
+                    if (st.last) { da += WEY; db += WEH; }
                     kca = N1 * st.q10 * st.ds;
                     kcb = N1 * st.ds;
                     if (!st.sep) {
@@ -517,7 +676,7 @@ struct Kp3 {
                     const int p = ub.pos / d.CS;
                     double *fcol = s.fac() + p;
                     const int ku = ub.pos - (p * d.CS + 3);
-                    double du = cost_c * (keep * pm.w_cr) + PQP_UBSG + PQP_UBW;
+                    double du = cost_c * (keep * pm.w_cr) + PQP_UBSG + (kKPC ? 2.0 : 1.0) * PQP_UBW;
                     int ii1 = tid * keep + keep;
                     if (ii1 > N - 1) ii1 = N - 1;
                     for (int ii = tid * keep; ii <= ii1; ++ii) {
@@ -821,6 +980,32 @@ struct Kp3 {
             // of the iteration before it, which keeps the hot part of the loop free of this code.
             auto is_check = [&](int k) { return (pm.check_termination && (k % pm.check_termination == 0)) || k == pm.max_iter; };
             auto park_w = [&]() {
+                if constexpr (kKPC) {
+                    if (st.live) {
+                        double *wo = wold + i;
+                        wo[0] = st.vD0 - st.b0; wo[N] = st.vD1 - st.b1; wo[2 * N] = st.vD2 - st.b2;
+                        wo[3 * N] = st.vKL - fmax(st.vKL, -st.mk);
+                        wo[4 * N] = st.vKU - fmin(st.vKU, st.mk);
+                        wo[5 * N] = st.vSB - clamp2(st.vSB, 0.0, pm.margin);
+                        wo[6 * N] = st.vSK - clamp2(st.vSK, 0.0, st.uSK);
+                        wo[7 * N] = st.vH1 - clamp2(st.vH1, st.lH1, st.uH1);
+                        wo[8 * N] = st.vH3 - clamp2(st.vH3, st.lH3, st.uH3);
+                        wo[9 * N] = st.vH4 - clamp2(st.vH4, st.lH4, st.uH4);
+                        wo[10 * N] = st.vS4m - fmin(st.vS4m, st.uS4m);
+                        wo[11 * N] = st.vS4p - fmax(st.vS4p, st.lS4p);
+                        if (st.last) {
+                            wold[kWR * N] = vEY - clamp2(vEY, lEY, uEY);
+                            wold[kWR * N + 1] = vEH - clamp2(vEH, lEH, uEH);
+                        }
+                    }
+                    if (ub.live) {
+                        double *wc = wold + kWR * N + 2 + tid;
+                        const double mkp = PQP_UBF(10);
+                        wc[0] = PQP_UBV - fmax(PQP_UBV, -mkp);
+                        wc[ch] = PQP_UBF(4) - fmin(PQP_UBF(4), mkp);
+                        wc[2 * ch] = PQP_UBF(5) - fmax(PQP_UBF(5), 0.0);
+                    }
+                } else
                 if (st.live) {
                     double *wo = wold + i;
                     wo[0] = st.vD0 - st.b0; wo[N] = st.vD1 - st.b1; wo[2 * N] = st.vD2 - st.b2;
@@ -833,8 +1018,8 @@ struct Kp3 {
                     wo[9 * N] = st.vS2m - fmin(st.vS2m, st.uS2m);
                     wo[10 * N] = st.vS2p - fmax(st.vS2p, st.lS2p);
                     if (st.last) {
-                        wold[11 * N] = vEY - clamp2(vEY, -1.0, 1.0);
-                        wold[11 * N + 1] = vEH - clamp2(vEH, lEH, uEH);
+                        wold[kWR * N] = vEY - clamp2(vEY, -1.0, 1.0);
+                        wold[kWR * N + 1] = vEH - clamp2(vEH, lEH, uEH);
                     }
                 }
             };
@@ -893,9 +1078,63 @@ struct Kp3 {
                 c.sync();
                 PQP_PH(0)
                 double tsl = 0.0;   // x-tilde of the slack (decouples exactly)
+                double tskp = 0.0;  // KPC: x-tilde of the rate slack of this thread's held control
                 // z = clamp(v) of the station-local rows is needed twice per iteration (here and in the update (c)):
                 // computed once, carried across the solve phases
                 double zKB = 0, zSB = 0, zH1 = 0, zH3 = 0, z4m = 0, z4p = 0, z2m = 0, z2p = 0;
+                double zKU = 0, zSK = 0, zH4 = 0, tsk = 0.0;   // KPC (zKB then holds the kappa-pair's lower row, z2m / z2p are unused)
+                if constexpr (kKPC) {
+                  if (st.live) {
+                    zKB = fmax(st.vKL, -st.mk);
+                    zKU = fmin(st.vKU, st.mk);
+                    zSB = clamp2(st.vSB, 0.0, pm.margin);
+                    zSK = clamp2(st.vSK, 0.0, st.uSK);
+                    zH1 = clamp2(st.vH1, st.lH1, st.uH1);
+                    zH3 = clamp2(st.vH3, st.lH3, st.uH3);
+                    zH4 = clamp2(st.vH4, st.lH4, st.uH4);
+                    z4m = fmin(st.vS4m, st.uS4m);
+                    z4p = fmax(st.vS4p, st.lS4p);
+                    const double gKL = st.WK * (2.0 * zKB - st.vKL);
+                    const double gKU = st.WK * (2.0 * zKU - st.vKU);
+                    const double gSB = st.WSB * (2.0 * zSB - st.vSB);
+                    const double gSK = st.WSK * (2.0 * zSK - st.vSK);
+                    const double gH1 = st.WH1 * (2.0 * zH1 - st.vH1);
+                    const double gH3 = st.WH3 * (2.0 * zH3 - st.vH3);
+                    const double gH4 = st.WH4 * (2.0 * zH4 - st.vH4);
+                    const double g4m = st.WS4 * (2.0 * z4m - st.vS4m);
+                    const double g4p = st.WS4 * (2.0 * z4p - st.vS4p);
+                    const double s4 = g4m + g4p;
+                    double ra = -gD0 + gH1 + gH3 + gH4 + s4;
+                    double rb = -gD1 + cH1 * gH1 + cH3 * gH3 + cH4 * gH4 + cS4 * s4;
+                    double rc = -gD2 + gKL + gKU;
+                    const double rs = gSB - g4m + g4p;
+                    const double rk = gSK + gKL - gKU;
+                    if (!st.last) {
+                        const double n0 = s.ex(0)[i + 1], n1 = s.ex(1)[i + 1], n2 = s.ex(2)[i + 1];
+                        ra += n0 + st.q10 * n1;
+                        rb += st.ds * n0 + n1;
+                        rc += st.ds * n1 + n2;
+                    } else {
+                        ra += WEY * (2.0 * clamp2(vEY, lEY, uEY) - vEY);
+                        rb += WEH * (2.0 * clamp2(vEH, lEH, uEH) - vEH);
+                    }
+                    s.tr()[st.pos] = st.sga * st.xa + ra;
+                    s.tr()[st.pos + 1] = st.sgb * st.xb + rb;
+                    s.tr()[st.pos + 2] = st.sgc * st.xc + rc;
+                    tsl = (st.sgs * st.xs + rs) * st.ksinv;
+                    tsk = (st.sgk * st.xk + rk) * st.kkinv;
+                  }
+                  if (ub.live) {   // rate pair (u + p >= -mkp, u - p <= mkp), p >= 0: p decouples like the other slacks
+                    const double mkp = PQP_UBF(10), vL = PQP_UBV, vU = PQP_UBF(4), vP = PQP_UBF(5);
+                    const double gL = PQP_UBW * (2.0 * fmax(vL, -mkp) - vL);
+                    const double gU = PQP_UBW * (2.0 * fmin(vU, mkp) - vU);
+                    const double gP = PQP_UBF(6) * (2.0 * fmax(vP, 0.0) - vP);
+                    double acc = PQP_UBSG * PQP_UBX + gL + gU;
+                    for (int t = ub.t0; t <= ub.t1; ++t) acc += s.dsS()[t] * s.ex(2)[t + 1];
+                    s.tr()[ub.pos] = acc;
+                    tskp = (PQP_UBF(8) * PQP_UBF(7) + (gP + gL - gU)) * PQP_UBF(9);
+                  }
+                } else {
                 if (st.live) {
                     zKB = clamp2(st.vKB, -pm.kmax, pm.kmax);
                     zSB = clamp2(st.vSB, 0.0, pm.margin);
@@ -936,6 +1175,7 @@ struct Kp3 {
                     double acc = PQP_UBSG * PQP_UBX + PQP_UBW * (2.0 * clamp2(PQP_UBV, -kOsqpInfty, kOsqpInfty) - PQP_UBV);
                     for (int t = ub.t0; t <= ub.t1; ++t) acc += s.dsS()[t] * s.ex(2)[t + 1];
                     s.tr()[ub.pos] = acc;
+                }
                 }
                 c.sync();
                 PQP_PH(1)
@@ -1082,10 +1322,27 @@ struct Kp3 {
                         zD1 += st.qt * at + bt + st.dst * ct;
                         zD2 += ct + st.dst * ut;
                     }
-                    const double e4 = ta + d4 * tb, e2 = ta + d2 * tb;
                     st.vD0 += alpha * (zD0 - st.b0);
                     st.vD1 += alpha * (zD1 - st.b1);
                     st.vD2 += alpha * (zD2 - st.b2);
+                    if constexpr (kKPC) {
+                        const double e4 = ta + cS4 * tb;
+                        st.vKL += alpha * ((tc + tsk) - zKB);
+                        st.vKU += alpha * ((tc - tsk) - zKU);
+                        st.vSB += alpha * (tsl - zSB);
+                        st.vSK += alpha * (tsk - zSK);
+                        st.vH1 += alpha * ((ta + cH1 * tb) - zH1);
+                        st.vH3 += alpha * ((ta + cH3 * tb) - zH3);
+                        st.vH4 += alpha * ((ta + cH4 * tb) - zH4);
+                        st.vS4m += alpha * ((e4 - tsl) - z4m);
+                        st.vS4p += alpha * ((e4 + tsl) - z4p);
+                        if (st.last) {
+                            vEY += alpha * (ta - clamp2(vEY, lEY, uEY));
+                            vEH += alpha * (tb - clamp2(vEH, lEH, uEH));
+                        }
+                        st.xk = alpha * tsk + (1.0 - alpha) * st.xk;
+                    } else {
+                    const double e4 = ta + d4 * tb, e2 = ta + d2 * tb;
                     st.vKB += alpha * (tc - zKB);
                     st.vSB += alpha * (tsl - zSB);
                     st.vH1 += alpha * ((ta + d1 * tb) - zH1);
@@ -1098,13 +1355,22 @@ struct Kp3 {
                         vEY += alpha * (ta - clamp2(vEY, -1.0, 1.0));
                         vEH += alpha * (tb - clamp2(vEH, lEH, uEH));
                     }
+                    }
                     st.xa = alpha * ta + (1.0 - alpha) * st.xa;
                     st.xb = alpha * tb + (1.0 - alpha) * st.xb;
                     st.xc = alpha * tc + (1.0 - alpha) * st.xc;
                     st.xs = alpha * tsl + (1.0 - alpha) * st.xs;
                 }
                 if (ub.live) {
-                    PQP_UBV += alpha * (tu - clamp2(PQP_UBV, -kOsqpInfty, kOsqpInfty));
+                    if constexpr (kKPC) {
+                        const double mkp = PQP_UBF(10), vL = PQP_UBV, vU = PQP_UBF(4), vP = PQP_UBF(5);
+                        PQP_UBV = vL + alpha * ((tu + tskp) - fmax(vL, -mkp));
+                        PQP_UBF(4) = vU + alpha * ((tu - tskp) - fmin(vU, mkp));
+                        PQP_UBF(5) = vP + alpha * (tskp - fmax(vP, 0.0));
+                        PQP_UBF(7) = alpha * tskp + (1.0 - alpha) * PQP_UBF(7);
+                    } else {
+                        PQP_UBV += alpha * (tu - clamp2(PQP_UBV, -kOsqpInfty, kOsqpInfty));
+                    }
                     PQP_UBX = alpha * tu + (1.0 - alpha) * PQP_UBX;
                 }
                 PQP_PH(5)
@@ -1117,16 +1383,16 @@ struct Kp3 {
                     // the row / column scalings (and the parked dual direction) live in the global workspace: fetch them
                     // first, as independent loads, so that their L2 latency overlaps the barriers and the stencils below
                     const int iw = st.live ? i : 0;
-                    double eW[9], dW[4], wo[11];
+                    double eW[kWE], dW[kWD], wo[kWR];
                     {
-                        const double *w9g = ws + 9 * (size_t)iw;
-                        const double *wDg = ws + 9 * (size_t)N + ch + 2 + 4 * (size_t)iw;
+                        const double *w9g = ws + (size_t)kWE * iw;
+                        const double *wDg = ws + oD + (size_t)kWD * iw;
 #pragma unroll
-                        for (int k = 0; k < 9; ++k) eW[k] = w9g[k];
+                        for (int k = 0; k < kWE; ++k) eW[k] = w9g[k];
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) dW[k] = wDg[k];
+                        for (int k = 0; k < kWD; ++k) dW[k] = wDg[k];
 #pragma unroll
-                        for (int k = 0; k < 11; ++k) wo[k] = chk ? wold[(size_t)k * N + iw] : 0.0;
+                        for (int k = 0; k < kWR; ++k) wo[k] = chk ? wold[(size_t)k * N + iw] : 0.0;
                     }
                     // publish x (neighbours need station i-1 and the control) and read the scalings
                     c.sync();
@@ -1162,10 +1428,22 @@ struct Kp3 {
                             aD1 += st.qt * at + bt + st.dst * ct;
                             aD2 += ct + st.dst * ut;
                         }
-                        const double e4 = st.xa + d4 * st.xb, e2 = st.xa + d2 * st.xb;
                         PQP_ROW(aD0, st.vD0, st.b0, st.b0, eW[0])
                         PQP_ROW(aD1, st.vD1, st.b1, st.b1, eW[1])
                         PQP_ROW(aD2, st.vD2, st.b2, st.b2, eW[2])
+                        if constexpr (kKPC) {
+                            const double e4 = st.xa + cS4 * st.xb;
+                            PQP_ROW(st.xc + st.xk, st.vKL, -st.mk, kOsqpInfty, eW[3])
+                            PQP_ROW(st.xc - st.xk, st.vKU, -kOsqpInfty, st.mk, eW[3])
+                            PQP_ROW(st.xs, st.vSB, 0.0, pm.margin, eW[4])
+                            PQP_ROW(st.xk, st.vSK, 0.0, st.uSK, eW[9])
+                            PQP_ROW(st.xa + cH1 * st.xb, st.vH1, st.lH1, st.uH1, eW[5])
+                            PQP_ROW(st.xa + cH3 * st.xb, st.vH3, st.lH3, st.uH3, eW[6])
+                            PQP_ROW(st.xa + cH4 * st.xb, st.vH4, st.lH4, st.uH4, eW[8])
+                            PQP_ROW(e4 - st.xs, st.vS4m, -kOsqpInfty, st.uS4m, eW[7])
+                            PQP_ROW(e4 + st.xs, st.vS4p, st.lS4p, kOsqpInfty, eW[7])
+                        } else {
+                        const double e4 = st.xa + d4 * st.xb, e2 = st.xa + d2 * st.xb;
                         PQP_ROW(st.xc, st.vKB, -pm.kmax, pm.kmax, eW[3])
                         PQP_ROW(st.xs, st.vSB, 0.0, pm.margin, eW[4])
                         PQP_ROW(st.xa + d1 * st.xb, st.vH1, st.lH1, st.uH1, eW[5])
@@ -1174,17 +1452,70 @@ struct Kp3 {
                         PQP_ROW(e4 + st.xs, st.vS4p, st.lS4p, kOsqpInfty, eW[7])
                         PQP_ROW(e2 - st.xs, st.vS2m, -kOsqpInfty, st.uS2m, eW[8])
                         PQP_ROW(e2 + st.xs, st.vS2p, st.lS2p, kOsqpInfty, eW[8])
+                        }
                         if (st.last) {
-                            PQP_ROW(st.xa, vEY, -1.0, 1.0, ws[9 * (size_t)N + ch])
-                            PQP_ROW(st.xb, vEH, lEH, uEH, ws[9 * (size_t)N + ch + 1])
+                            PQP_ROW(st.xa, vEY, lEY, uEY, ws[oEnd])
+                            PQP_ROW(st.xb, vEH, lEH, uEH, ws[oEnd + 1])
                         }
                         yD0 = PQP_DUAL(st.vD0, st.b0, st.b0, st.WD0);
                         yD1 = PQP_DUAL(st.vD1, st.b1, st.b1, st.WD1);
                         yD2 = PQP_DUAL(st.vD2, st.b2, st.b2, st.WD2);
                         s.ex(0)[i] = yD0; s.ex(1)[i] = yD1; s.ex(2)[i] = yD2;
                     }
-                    if (ub.live) PQP_ROW(PQP_UBX, PQP_UBV, -kOsqpInfty, kOsqpInfty, ws[9 * (size_t)N + tid])
+                    if (ub.live) {
+                        if constexpr (kKPC) {
+                            const double mkp = PQP_UBF(10), xp = PQP_UBF(7);
+                            PQP_ROW(PQP_UBX + xp, PQP_UBV, -mkp, kOsqpInfty, ws[oEU + tid])
+                            PQP_ROW(PQP_UBX - xp, PQP_UBF(4), -kOsqpInfty, mkp, ws[oEU + tid])
+                            PQP_ROW(xp, PQP_UBF(5), 0.0, kOsqpInfty, ws[oEU + ch + tid])
+                        } else {
+                            PQP_ROW(PQP_UBX, PQP_UBV, -kOsqpInfty, kOsqpInfty, ws[oEU + tid])
+                        }
+                    }
                     c.sync();
+                    if constexpr (kKPC) {
+                      if (st.live) {
+                        const double yKL = PQP_DUAL(st.vKL, -st.mk, kOsqpInfty, st.WK);
+                        const double yKU = PQP_DUAL(st.vKU, -kOsqpInfty, st.mk, st.WK);
+                        const double ySB = PQP_DUAL(st.vSB, 0.0, pm.margin, st.WSB);
+                        const double ySK = PQP_DUAL(st.vSK, 0.0, st.uSK, st.WSK);
+                        const double yH1 = PQP_DUAL(st.vH1, st.lH1, st.uH1, st.WH1);
+                        const double yH3 = PQP_DUAL(st.vH3, st.lH3, st.uH3, st.WH3);
+                        const double yH4 = PQP_DUAL(st.vH4, st.lH4, st.uH4, st.WH4);
+                        const double y4m = PQP_DUAL(st.vS4m, -kOsqpInfty, st.uS4m, st.WS4);
+                        const double y4p = PQP_DUAL(st.vS4p, st.lS4p, kOsqpInfty, st.WS4);
+                        const double s4 = y4m + y4p;
+                        double ra = -yD0 + yH1 + yH3 + yH4 + s4;
+                        double rb = -yD1 + cH1 * yH1 + cH3 * yH3 + cH4 * yH4 + cS4 * s4;
+                        double rc = -yD2 + yKL + yKU;
+                        const double rs = ySB - y4m + y4p;
+                        const double rk = ySK + yKL - yKU;
+                        if (!st.last) {
+                            const double n0 = s.ex(0)[i + 1], n1 = s.ex(1)[i + 1], n2 = s.ex(2)[i + 1];
+                            ra += n0 + st.q10 * n1;
+                            rb += st.ds * n0 + n1;
+                            rc += st.ds * n1 + n2;
+                        } else {
+                            ra += PQP_DUAL(vEY, lEY, uEY, WEY);
+                            rb += PQP_DUAL(vEH, lEH, uEH, WEH);
+                        }
+                        PQP_VAR(pm.w_pq * st.xa, ra, dW[0])
+                        PQP_VAR(0.0, rb, dW[1])
+                        PQP_VAR(pm.w_c * st.xc, rc, dW[2])
+                        PQP_VAR(pm.w_s * st.xs, rs, dW[3])
+                        PQP_VAR(500.0 * st.xk, rk, dW[4])
+                      }
+                      if (ub.live) {
+                        const double mkp = PQP_UBF(10);
+                        const double yL = PQP_DUAL(PQP_UBV, -mkp, kOsqpInfty, PQP_UBW);
+                        const double yU = PQP_DUAL(PQP_UBF(4), -kOsqpInfty, mkp, PQP_UBW);
+                        const double yP = PQP_DUAL(PQP_UBF(5), 0.0, kOsqpInfty, PQP_UBF(6));
+                        double aty = yL + yU;
+                        for (int t = ub.t0; t <= ub.t1; ++t) aty += s.dsS()[t] * s.ex(2)[t + 1];
+                        PQP_VAR((keep * pm.w_cr) * PQP_UBX, aty, ws[oDu + tid])
+                        PQP_VAR((25000.0 * keep) * PQP_UBF(7), yP + yL - yU, ws[oDu + ch + tid])
+                      }
+                    } else {
                     if (st.live) {
                         const double yKB = PQP_DUAL(st.vKB, -pm.kmax, pm.kmax, st.WKB);
                         const double ySB = PQP_DUAL(st.vSB, 0.0, pm.margin, st.WSB);
@@ -1216,7 +1547,8 @@ struct Kp3 {
                     if (ub.live) {
                         double aty = PQP_DUAL(PQP_UBV, -kOsqpInfty, kOsqpInfty, PQP_UBW);
                         for (int t = ub.t0; t <= ub.t1; ++t) aty += s.dsS()[t] * s.ex(2)[t + 1];
-                        PQP_VAR((keep * pm.w_cr) * PQP_UBX, aty, ws[13 * (size_t)N + ch + 2 + tid])
+                        PQP_VAR((keep * pm.w_cr) * PQP_UBX, aty, ws[oDu + tid])
+                    }
                     }
 #undef PQP_ROW
 #undef PQP_DUAL
@@ -1237,6 +1569,55 @@ struct Kp3 {
                         c.sync();   // the dual-residual pass has consumed ex(0..2)
                         if (st.live) { s.ex(0)[i] = gD0; s.ex(1)[i] = gD1; s.ex(2)[i] = gD2; }
                         c.sync();
+                        if constexpr (kKPC) {
+                          // project a row's g on the cone of its finite bounds and accumulate ||g||, u'g+ + l'g-
+                          auto cone = [&](double g, double l_, double u_) {
+                              const bool ui = u_ >= kOsqpInfty, li = l_ <= -kOsqpInfty;
+                              if (ui) g = li ? 0.0 : fmin(g, 0.0);
+                              else if (li) g = fmax(g, 0.0);
+                              c_nrm = fmax(c_nrm, fabs(g));
+                              c_lhs += (ui ? 0.0 : u_) * fmax(g, 0.0) + (li ? 0.0 : l_) * fmin(g, 0.0);
+                              return g;
+                          };
+                          if (st.live) {
+                            const double gKL = cone(PQP_G(st.vKL, -st.mk, kOsqpInfty, st.WK, wo[3]), -st.mk, kOsqpInfty);
+                            const double gKU = cone(PQP_G(st.vKU, -kOsqpInfty, st.mk, st.WK, wo[4]), -kOsqpInfty, st.mk);
+                            const double gSB = cone(PQP_G(st.vSB, 0.0, pm.margin, st.WSB, wo[5]), 0.0, pm.margin);
+                            const double gSK = cone(PQP_G(st.vSK, 0.0, st.uSK, st.WSK, wo[6]), 0.0, st.uSK);
+                            const double gH1 = cone(PQP_G(st.vH1, st.lH1, st.uH1, st.WH1, wo[7]), st.lH1, st.uH1);
+                            const double gH3 = cone(PQP_G(st.vH3, st.lH3, st.uH3, st.WH3, wo[8]), st.lH3, st.uH3);
+                            const double gH4 = cone(PQP_G(st.vH4, st.lH4, st.uH4, st.WH4, wo[9]), st.lH4, st.uH4);
+                            const double g4m = cone(PQP_G(st.vS4m, -kOsqpInfty, st.uS4m, st.WS4, wo[10]), -kOsqpInfty, st.uS4m);
+                            const double g4p = cone(PQP_G(st.vS4p, st.lS4p, kOsqpInfty, st.WS4, wo[11]), st.lS4p, kOsqpInfty);
+                            PQP_ACC(gD0, st.b0, st.b0) PQP_ACC(gD1, st.b1, st.b1) PQP_ACC(gD2, st.b2, st.b2)
+                            const double s4 = g4m + g4p;
+                            double ra = -gD0 + gH1 + gH3 + gH4 + s4;
+                            double rb = -gD1 + cH1 * gH1 + cH3 * gH3 + cH4 * gH4 + cS4 * s4;
+                            double rc = -gD2 + gKL + gKU;
+                            const double rs = gSB - g4m + g4p;
+                            const double rk = gSK + gKL - gKU;
+                            if (!st.last) {
+                                const double n0 = s.ex(0)[i + 1], n1 = s.ex(1)[i + 1], n2 = s.ex(2)[i + 1];
+                                ra += n0 + st.q10 * n1;
+                                rb += st.ds * n0 + n1;
+                                rc += st.ds * n1 + n2;
+                            } else {
+                                ra += cone(PQP_G(vEY, lEY, uEY, WEY, wold[kWR * N]), lEY, uEY);
+                                rb += cone(PQP_G(vEH, lEH, uEH, WEH, wold[kWR * N + 1]), lEH, uEH);
+                            }
+                            c_cert = fmax(fmax(fmax(fabs(ra), fabs(rb)), fmax(fabs(rc), fabs(rs))), fabs(rk));
+                          }
+                          if (ub.live) {
+                            const double mkp = PQP_UBF(10);
+                            const double *wc = wold + kWR * N + 2 + tid;
+                            const double gL = cone(PQP_G(PQP_UBV, -mkp, kOsqpInfty, PQP_UBW, wc[0]), -mkp, kOsqpInfty);
+                            const double gU = cone(PQP_G(PQP_UBF(4), -kOsqpInfty, mkp, PQP_UBW, wc[ch]), -kOsqpInfty, mkp);
+                            const double gP = cone(PQP_G(PQP_UBF(5), 0.0, kOsqpInfty, PQP_UBF(6), wc[2 * ch]), 0.0, kOsqpInfty);
+                            double aty = gL + gU;
+                            for (int t = ub.t0; t <= ub.t1; ++t) aty += s.dsS()[t] * s.ex(2)[t + 1];
+                            c_cert = fmax(c_cert, fmax(fabs(aty), fabs(gP + gL - gU)));
+                          }
+                        } else {
                         if (st.live) {
                             const double gKB = PQP_G(st.vKB, -pm.kmax, pm.kmax, st.WKB, wo[3]);
                             const double gSB = PQP_G(st.vSB, 0.0, pm.margin, st.WSB, wo[4]);
@@ -1263,8 +1644,8 @@ struct Kp3 {
                                 rb += st.ds * n0 + n1;
                                 rc += st.ds * n1 + n2;
                             } else {
-                                const double gEY = PQP_G(vEY, -1.0, 1.0, WEY, wold[11 * N]);
-                                double gEH = PQP_G(vEH, lEH, uEH, WEH, wold[11 * N + 1]);
+                                const double gEY = PQP_G(vEY, -1.0, 1.0, WEY, wold[kWR * N]);
+                                double gEH = PQP_G(vEH, lEH, uEH, WEH, wold[kWR * N + 1]);
                                 PQP_ACC(gEY, -1.0, 1.0)
                                 if (uEH >= kOsqpInfty) gEH = (lEH <= -kOsqpInfty) ? 0.0 : fmin(gEH, 0.0);
                                 else if (lEH <= -kOsqpInfty) gEH = fmax(gEH, 0.0);
@@ -1278,6 +1659,7 @@ struct Kp3 {
                             double aty = 0.0;
                             for (int t = ub.t0; t <= ub.t1; ++t) aty += s.dsS()[t] * s.ex(2)[t + 1];
                             c_cert = fmax(c_cert, fabs(aty));
+                        }
                         }
 #undef PQP_G
 #undef PQP_ACC
@@ -1321,16 +1703,29 @@ struct Kp3 {
                             st.vD0 = st.b0 + (st.vD0 - st.b0) * ratio;
                             st.vD1 = st.b1 + (st.vD1 - st.b1) * ratio;
                             st.vD2 = st.b2 + (st.vD2 - st.b2) * ratio;
-                            PQP_RESC(st.vKB, -pm.kmax, pm.kmax)
+                            if constexpr (kKPC) {
+                                PQP_RESC(st.vKL, -st.mk, kOsqpInfty)
+                                PQP_RESC(st.vKU, -kOsqpInfty, st.mk)
+                                PQP_RESC(st.vSK, 0.0, st.uSK)
+                                PQP_RESC(st.vH4, st.lH4, st.uH4)
+                                if (ub.live) {
+                                    const double mkp = PQP_UBF(10);
+                                    PQP_RESC(PQP_UBV, -mkp, kOsqpInfty)
+                                    PQP_RESC(PQP_UBF(4), -kOsqpInfty, mkp)
+                                    PQP_RESC(PQP_UBF(5), 0.0, kOsqpInfty)
+                                }
+                            } else {
+                                PQP_RESC(st.vKB, -pm.kmax, pm.kmax)
+                                PQP_RESC(st.vS2m, -kOsqpInfty, st.uS2m)
+                                PQP_RESC(st.vS2p, st.lS2p, kOsqpInfty)
+                            }
                             PQP_RESC(st.vSB, 0.0, pm.margin)
                             PQP_RESC(st.vH1, st.lH1, st.uH1)
                             PQP_RESC(st.vH3, st.lH3, st.uH3)
                             PQP_RESC(st.vS4m, -kOsqpInfty, st.uS4m)
                             PQP_RESC(st.vS4p, st.lS4p, kOsqpInfty)
-                            PQP_RESC(st.vS2m, -kOsqpInfty, st.uS2m)
-                            PQP_RESC(st.vS2p, st.lS2p, kOsqpInfty)
                             if (st.last) {
-                                PQP_RESC(vEY, -1.0, 1.0)
+                                PQP_RESC(vEY, lEY, uEY)
                                 PQP_RESC(vEH, lEH, uEH)
                             }
 #undef PQP_RESC
@@ -1437,6 +1832,7 @@ struct Kp3 {
 #undef PQP_UBW
 #undef PQP_UBX
 #undef PQP_UBSG
+#undef PQP_UBF
 };
 
 }  // namespace pqp

@@ -40,14 +40,17 @@ def lib():
         _lib = C.CDLL(build())
         _lib.kp_emu_solve_batch.argtypes = [C.POINTER(Params), C.c_int] + [C.c_void_p] * 10 + [C.c_int, C.c_int, C.c_int]
         _lib.kp_emu_solve_batch.restype = C.c_int
+        _lib.kp_emu_set_limits.argtypes = [C.c_void_p, C.c_void_p]
+        _lib.kp_emu_set_limits.restype = None
         _lib.gen_emu_solve_batch.argtypes = [C.POINTER(Params), C.c_int, C.c_int] + [C.c_void_p] * 12
         _lib.gen_emu_solve_batch.restype = C.c_int
     return _lib
 
 
-def solve_batch(params, batch, smem_bytes=227 * 1024, variant=0, nwarps=4):
+def solve_batch(params, batch, smem_bytes=227 * 1024, variant=0, nwarps=4, max_k=None, max_kp=None):
     """variant 0 = one-warp generic core (pqp_kp_core.cuh); 5..7 = Kp3<17,6,4>, <23,7,4>, <27,7,8>; 8, 9 = the 34-separator eight-warp classes Kp3<17,6,8,34>, <23,7,8,34>;
-    10, 11, 12 = the long-path classes Kp3<37,7,13,34>, <37,7,12,34>, <27,7,10,34>."""
+    10, 11, 12 = the long-path classes Kp3<37,7,13,34>, <37,7,12,34>, <27,7,10,34>;
+    20, 21 = the "KPC" classes Kp3<23,7,4,17,KPC>, <23,7,8,34,KPC> (need max_k / max_kp)."""
     B = len(batch["n_points"])
     total = int(batch["offsets"][-1])
     ref = np.ascontiguousarray(batch["ref"], dtype=STATE_DTYPE)
@@ -56,6 +59,10 @@ def solve_batch(params, batch, smem_bytes=227 * 1024, variant=0, nwarps=4):
     frenet = np.zeros((total, 3))
     status = np.zeros(B, dtype=np.int32)
     iters = np.zeros(B, dtype=np.int32)
+    if max_k is not None:
+        max_k = np.ascontiguousarray(max_k, dtype=np.float64)
+        max_kp = np.ascontiguousarray(max_kp, dtype=np.float64)
+    lib().kp_emu_set_limits(ptr(max_k), ptr(max_kp))
     lib().kp_emu_solve_batch(C.byref(params), B, ptr(batch["n_points"]), ptr(batch["offsets"]), ptr(ref),
                              ptr(bounds), ptr(batch["x0"]), ptr(batch["end_heading"]), ptr(out),
                              ptr(frenet), ptr(status), ptr(iters), smem_bytes, variant, nwarps)

@@ -37,11 +37,16 @@ void *lane_main(void *p) {
     case 10: pqp::Kp3<37, 7, 13, 34>::solve_path(c, *a->prm, *a->bv, a->prob, sm, cap); break;
     case 11: pqp::Kp3<37, 7, 12, 34>::solve_path(c, *a->prm, *a->bv, a->prob, sm, cap); break;
     case 12: pqp::Kp3<27, 7, 10, 34>::solve_path(c, *a->prm, *a->bv, a->prob, sm, cap); break;
+    case 20: pqp::Kp3<23, 7, 4, 17, 2>::solve_path(c, *a->prm, *a->bv, a->prob, sm, cap); break;    // "KPC" classes
+    case 21: pqp::Kp3<23, 7, 8, 34, 2>::solve_path(c, *a->prm, *a->bv, a->prob, sm, cap); break;
     default: pqp::kp_solve_path(w, *a->prm, *a->bv, a->prob, sm, cap);   // generic core: one warp
     }
     return nullptr;
 }
 }  // namespace
+
+static const double *g_emu_max_k = nullptr, *g_emu_max_kp = nullptr;
+extern "C" void kp_emu_set_limits(const double *max_k, const double *max_kp) { g_emu_max_k = max_k; g_emu_max_kp = max_kp; }
 
 extern "C" int kp_emu_solve_batch(const pqp_params *params, int batch, const int32_t *n_points,
                                   const int32_t *offsets, const pqp_state *ref,
@@ -54,11 +59,14 @@ extern "C" int kp_emu_solve_batch(const pqp_params *params, int batch, const int
     if (variant == 10) nwarps = 13;
     if (variant == 11) nwarps = 12;
     if (variant == 12) nwarps = 10;
+    if (variant == 20) nwarps = 4;
+    if (variant == 21) nwarps = 8;
     pqp::DevParams prm = pqp::dev_params_from(*params);
     pqp::BatchView bv;
     bv.batch = batch; bv.n_points = n_points; bv.offsets = offsets; bv.ref = ref; bv.bounds = bounds;
     bv.x0 = x0; bv.end_heading = end_heading; bv.out_states = out_states; bv.out_frenet = out_frenet;
     bv.status = status; bv.iters = iters; bv.debug = nullptr;
+    bv.max_k = g_emu_max_k; bv.max_kp = g_emu_max_kp;
     const size_t ws_n = pqp::kp2_ws_doubles((size_t)offsets[batch], (size_t)batch);
     bv.workspace = (double *)malloc(ws_n * sizeof(double));
     for (size_t k = 0; k < ws_n; ++k) bv.workspace[k] = nan("");

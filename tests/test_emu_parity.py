@@ -169,3 +169,42 @@ def test_emu_parameter_sweep(oracle_params, case):
     o = oracle.solve_batch(p, 0, b)
     assert np.array_equal(e["status"], o["status"]) and np.array_equal(e["iters"], o["iters"])
     np.testing.assert_allclose(e["frenet"], o["frenet"], rtol=0, atol=TOL)
+
+
+@pytest.mark.parametrize("variant,n_points", [(20, [2, 3, 9, 60, 128]), (21, [200, 256])])
+def test_emu_kpc_thread_per_station(oracle_params, variant, n_points):
+    """"KPC" (SolverKpAsInputConstrained) on the thread-per-station skeleton, assembled in the kernel: same status,
+    iteration count and iterates as the oracle's restatement of solver_kp_as_input_constrained.cpp, including limits
+    from a speed profile with standstill stations (DBL_MAX limits: rows free on that side)."""
+    b = synth.curvy_corridors(len(n_points), n_points=n_points)
+    total = int(b["offsets"][-1])
+    ref = b["ref"].copy()
+    ref["v"] = 4.0 + 3.0 * np.sin(np.arange(total) * 0.05)
+    ref["a"] = 0.5 * np.cos(np.arange(total) * 0.05)
+    ref["v"][::11] = 0.0
+    mk, mkp = oracle.update_limits(oracle_params, ref)
+    e = emu.solve_batch(oracle_params, b, variant=variant, max_k=mk, max_kp=mkp)
+    o = oracle.solve_batch(oracle_params, 2, b, threads=4, max_k=mk, max_kp=mkp)
+    assert np.array_equal(e["status"], o["status"]) and np.array_equal(e["iters"], o["iters"])
+    assert (o["status"] == 1).any()
+    np.testing.assert_allclose(e["frenet"], o["frenet"], rtol=0, atol=TOL)
+    for f in "xyzks":
+        np.testing.assert_allclose(e["states"][f], o["states"][f], rtol=0, atol=TOL)
+
+
+def test_emu_kpc_infeasible_and_parameters(oracle_params):
+    b = synth.infeasible_corridors(4, 60)
+    mk, mkp = _limits(b)
+    e = emu.solve_batch(oracle_params, b, variant=20, max_k=mk, max_kp=mkp)
+    o = oracle.solve_batch(oracle_params, 2, b, threads=4, max_k=mk, max_kp=mkp)
+    assert np.array_equal(e["status"], o["status"]) and np.array_equal(e["iters"], o["iters"])
+    assert (o["status"] != 1).any()
+    p = oracle_params.copy()
+    p.constraint_end_heading = 0; p.KP_deviation_weight = 0.7; p.KP_slack_weight = 10.0
+    p.check_termination = 7; p.adaptive_rho_interval = 35
+    b = synth.curvy_corridors(2, n_points=[60, 100])
+    mk, mkp = _limits(b)
+    e = emu.solve_batch(p, b, variant=20, max_k=mk, max_kp=mkp)
+    o = oracle.solve_batch(p, 2, b, threads=4, max_k=mk, max_kp=mkp)
+    assert np.array_equal(e["status"], o["status"]) and np.array_equal(e["iters"], o["iters"])
+    np.testing.assert_allclose(e["frenet"], o["frenet"], rtol=0, atol=TOL)

@@ -156,3 +156,94 @@ def test_device_entry_with_loose_hints(oracle_params, nmax, ds):
     ref = oracle.solve_batch(oracle_params, 0, batch, threads=8)
     assert np.array_equal(dres["status"], ref["status"]) and np.array_equal(dres["iters"], ref["iters"])
     s.close()
+
+
+def _kpc_limits(oracle_params, batch, still=True):
+    total = int(batch["offsets"][-1])
+    batch["ref"]["v"] = 4.0 + 3.0 * np.sin(np.arange(total) * 0.05)
+    batch["ref"]["a"] = 0.5 * np.cos(np.arange(total) * 0.05)
+    if still:
+        batch["ref"]["v"][::13] = 0.0
+    return oracle.update_limits(oracle_params, batch["ref"])
+
+
+def test_kpc_thread_per_station_classes_and_fallback(oracle_params):
+    """"KPC" runs on the thread-per-station kernel classes up to 256 stations (assembled in the kernel); a batch with a
+    longer path takes the host-assembled generic kernel.  Both against the oracle; the device entry point gives the
+    same bits as the host-buffer one."""
+    import torch
+    from path_optimizer_b200 import _lib
+    L = _lib.load()
+    v, t, sm = C.c_int(), C.c_int(), C.c_int64()
+    assert L.pqp_class_info_kpc(100, 0, C.byref(v), C.byref(t), C.byref(sm)) == 0
+    assert L.pqp_class_name(v.value).decode() == "pqp_kp3_solve_kernel<23,7,4,17,KPC>"
+    assert L.pqp_class_info_kpc(200, 0, C.byref(v), C.byref(t), C.byref(sm)) == 0 and t.value == 256
+    assert L.pqp_class_info_kpc(300, 0, C.byref(v), C.byref(t), C.byref(sm)) != 0
+    rng = np.random.default_rng(4)
+    n_points = rng.integers(2, 257, size=64)
+    n_points[:4] = [2, 3, 128, 256]
+    batch = synth.curvy_corridors(64, n_points=n_points)
+    mk, mkp = _kpc_limits(oracle_params, batch)
+    total = int(batch["offsets"][-1])
+    s = _solver(64, total)
+    res = s.solve(batch, formulation="KPC", max_k=mk, max_kp=mkp)
+    assert res["stats"].kernel_launches >= 2            # thread-per-station classes (the generic path launches once)
+    ref = oracle.solve_batch(oracle_params, 2, batch, threads=8, max_k=mk, max_kp=mkp)
+    assert np.array_equal(res["status"], ref["status"]) and np.array_equal(res["iters"], ref["iters"])
+    np.testing.assert_allclose(res["frenet"], ref["frenet"], rtol=0, atol=TOL)
+    for f in "xyzks":
+        np.testing.assert_allclose(res["states"][f], ref["states"][f], rtol=0, atol=TOL)
+    # device-resident entry (limits computed on the device) == host-buffer entry
+    dev = torch.device("cuda", 0)
+
+    def up(a):
+        return torch.from_numpy(np.frombuffer(np.ascontiguousarray(a).tobytes(), dtype=np.uint8).copy()).to(dev)
+    d_n, d_off, d_ref, d_bnd = up(batch["n_points"]), up(batch["offsets"]), up(batch["ref"]), up(batch["bounds"])
+    d_x0, d_end = up(batch["x0"]), up(batch["end_heading"])
+    d_mk = torch.zeros(total, dtype=torch.float64, device=dev)
+    d_mkp = torch.zeros(total, dtype=torch.float64, device=dev)
+    d_out = torch.zeros(total * STATE_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+    d_fr = torch.zeros(total * 3, dtype=torch.float64, device=dev)
+    d_st = torch.zeros(64, dtype=torch.int32, device=dev)
+    d_it = torch.zeros(64, dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()
+    assert L.pqp_update_limits_device(s._h, 0, total, d_ref.data_ptr(), d_mk.data_ptr(), d_mkp.data_ptr(), None) == 0
+    hn = np.ascontiguousarray(batch["n_points"], dtype=np.int32)
+    rc = L.pqp_solve_batch_device_classes(s._h, 2, 64, total, hn.ctypes.data_as(C.c_void_p), None, d_n.data_ptr(),
+                                          d_off.data_ptr(), d_ref.data_ptr(), d_bnd.data_ptr(), d_x0.data_ptr(), d_end.data_ptr(),
+                                          d_mk.data_ptr(), d_mkp.data_ptr(), d_out.data_ptr(), d_fr.data_ptr(), d_st.data_ptr(),
+                                          d_it.data_ptr(), None, None)
+    assert rc == 0, _lib.last_error()
+    torch.cuda.synchronize()
+    assert np.array_equal(d_st.cpu().numpy(), res["status"]) and np.array_equal(d_it.cpu().numpy(), res["iters"])
+    assert np.array_equal(d_fr.cpu().numpy().reshape(-1, 3), res["frenet"], equal_nan=True)
+    # one path beyond 256 stations: the whole batch takes the generic kernel, still the oracle's answer
+    n2 = np.array([40, 300, 100], dtype=np.int32)
+    b2 = synth.curvy_corridors(3, n_points=n2)
+    mk2, mkp2 = _kpc_limits(oracle_params, b2, still=False)
+    r2 = s.solve(b2, formulation="KPC", max_k=mk2, max_kp=mkp2)
+    o2 = oracle.solve_batch(oracle_params, 2, b2, threads=4, max_k=mk2, max_kp=mkp2)
+    assert r2["stats"].kernel_launches == 1
+    assert np.array_equal(r2["status"], o2["status"]) and np.array_equal(r2["iters"], o2["iters"])
+    np.testing.assert_allclose(r2["frenet"], o2["frenet"], rtol=0, atol=TOL)
+    s.close()
+
+
+def test_kpc_plan_chain(oracle_params):
+    """solveWithoutSmoothing with optimization_method "KPC": updateBounds -> updateLimits (from the v, a fields of the
+    reference states) -> QP -> raw tail, chained on the device, against the oracle's chain."""
+    field = synth.disc_field_map()
+    b = synth.map_reference_paths(24, 150)
+    total = int(b["offsets"][-1])
+    b["ref"]["v"] = 5.0 + 2.0 * np.sin(np.arange(total) * 0.03)
+    b["ref"]["a"] = 0.3 * np.cos(np.arange(total) * 0.04)
+    s = _solver(24, total)
+    s.set_map(field)
+    r = s.plan(b, formulation="KPC")
+    o = oracle.plan(oracle_params, field, b, formulation=2)
+    assert np.array_equal(r["status"], o["status"]) and np.array_equal(r["iters"], o["iters"])
+    assert np.array_equal(r["ok"], o["ok"]) and np.array_equal(r["n_out"], o["n_out"])
+    assert (o["status"] == SOLVED).sum() >= 12
+    for f in "xyzks":
+        np.testing.assert_allclose(r["states"][f], o["states"][f], rtol=0, atol=TOL)
+    s.close()
