@@ -546,7 +546,8 @@ def run_ours(args, rank, world, local_rank):
         if world == 1:
             line["cpu_baseline"] = cpu_baseline(args)
             if args.config == 2 and not args.no_extras:
-                line["extras"] = {"configs": extras_configs(torch, local_rank, flush, stream, barrier)}
+                line["extras"] = {"configs": extras_configs(torch, local_rank, flush, stream, barrier),
+                                  "formulations": extras_formulations(local_rank)}
         print(json.dumps(line), flush=True)
     w.close()
     if world > 1:
@@ -596,6 +597,38 @@ def extras_configs(torch, local_rank, flush, stream, barrier):
             torch.cuda.empty_cache()
         except Exception as ex:  # context only: never fail the bench line on it
             out[str(cfg)] = {"error": repr(ex)[:300]}
+    return out
+
+
+def extras_formulations(device, reps=3):
+    """The other two type strings of OsqpSolver::create on the config-2 shape (1024 x 100, host buffers, host wall clock):
+    "KPC" runs on the thread-per-station classes (assembled in the kernel), "K" is assembled sparse on the host and solved
+    by the generic one-warp kernel."""
+    out = {}
+    try:
+        from path_optimizer_b200 import planner
+        b = synth.curvy_corridors(1024, 100)
+        total = 1024 * 100
+        ref = b["ref"].copy()
+        ref["v"] = 4.0 + 3.0 * np.sin(np.arange(total) * 0.05)
+        ref["a"] = 0.5 * np.cos(np.arange(total) * 0.05)
+        s = planner.PathPlanner(device=device, max_batch=1024, max_total_points=total)
+        mk, mkp = planner.update_limits(s.params, ref)
+        for form, kw in (("KP", {}), ("KPC", dict(max_k=mk, max_kp=mkp)), ("K", {})):
+            s.solve(b, form, **kw)
+            best = None
+            for _ in range(reps):
+                t0 = time.perf_counter()
+                r = s.solve(b, form, **kw)
+                ms = (time.perf_counter() - t0) * 1e3
+                best = ms if best is None else min(best, ms)
+            out[form] = {"workload": "1024 paths x 100 stations, curved corridors, host buffers", "ms_per_call": best,
+                         "solves_per_sec": 1024 / (best * 1e-3), "kernel_span_ms": r["stats"].kernel_ms,
+                         "kernel_launches": int(r["stats"].kernel_launches), "iters_per_solve_mean": float(r["iters"].mean()),
+                         "solved_fraction": float((r["status"] == 1).mean())}
+        s.close()
+    except Exception as ex:
+        out["error"] = repr(ex)[:300]
     return out
 
 

@@ -30,7 +30,7 @@ namespace {
 // (Kp3) instantiations; anything else runs on the one-warp generic kernel (last).
 typedef PqpVariant Variant;
 constexpr int kNumKp = 9;          // "KP" classes: thread-per-station kernels, then the one-warp kernel (index kNumKp - 1)
-constexpr int kNumVariants = 11;   // + the "KPC" thread-per-station classes
+constexpr int kNumVariants = 12;   // + the "KPC" thread-per-station classes
 struct VariantTable {
     Variant v[kNumVariants];
     VariantTable() {
@@ -39,7 +39,7 @@ struct VariantTable {
         pqp_variant_k3_17_6_8_34(&v[k++]); pqp_variant_k3_23_7_8_34(&v[k++]); pqp_variant_k3_27_7_8_34(&v[k++]);
         pqp_variant_k3_27_7_10_34(&v[k++]); pqp_variant_k3_37_7_12_34(&v[k++]); pqp_variant_k3_37_7_13_34(&v[k++]);
         pqp_variant_k1_generic(&v[k++]);
-        pqp_variant_k3c_23_7_4_17(&v[k++]); pqp_variant_k3c_23_7_8_34(&v[k++]);
+        pqp_variant_k3c_13_7_8_34(&v[k++]); pqp_variant_k3c_23_7_4_17(&v[k++]); pqp_variant_k3c_23_7_8_34(&v[k++]);
     }
 };
 const Variant *variants() {

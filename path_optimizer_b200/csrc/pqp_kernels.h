@@ -24,6 +24,7 @@ PQP_DECLARE_VARIANT(k3_27_7_10_34)
 PQP_DECLARE_VARIANT(k3_37_7_12_34)
 PQP_DECLARE_VARIANT(k3_37_7_13_34)
 // thread-per-station kernels of the "KPC" formulation Kp3<IMAX, BW, NW, MMAX, KPC>
+PQP_DECLARE_VARIANT(k3c_13_7_8_34)
 PQP_DECLARE_VARIANT(k3c_23_7_4_17)
 PQP_DECLARE_VARIANT(k3c_23_7_8_34)
 // one-warp generic KP kernel (any keep <= 10) and the generic banded-QP kernel of "K" / "KPC"

@@ -39,6 +39,7 @@ void *lane_main(void *p) {
     case 12: pqp::Kp3<27, 7, 10, 34>::solve_path(c, *a->prm, *a->bv, a->prob, sm, cap); break;
     case 20: pqp::Kp3<23, 7, 4, 17, 2>::solve_path(c, *a->prm, *a->bv, a->prob, sm, cap); break;    // "KPC" classes
     case 21: pqp::Kp3<23, 7, 8, 34, 2>::solve_path(c, *a->prm, *a->bv, a->prob, sm, cap); break;
+    case 22: pqp::Kp3<13, 7, 8, 34, 2>::solve_path(c, *a->prm, *a->bv, a->prob, sm, cap); break;
     default: pqp::kp_solve_path(w, *a->prm, *a->bv, a->prob, sm, cap);   // generic core: one warp
     }
     return nullptr;
@@ -60,7 +61,7 @@ extern "C" int kp_emu_solve_batch(const pqp_params *params, int batch, const int
     if (variant == 11) nwarps = 12;
     if (variant == 12) nwarps = 10;
     if (variant == 20) nwarps = 4;
-    if (variant == 21) nwarps = 8;
+    if (variant == 21 || variant == 22) nwarps = 8;
     pqp::DevParams prm = pqp::dev_params_from(*params);
     pqp::BatchView bv;
     bv.batch = batch; bv.n_points = n_points; bv.offsets = offsets; bv.ref = ref; bv.bounds = bounds;

@@ -171,7 +171,7 @@ def test_emu_parameter_sweep(oracle_params, case):
     np.testing.assert_allclose(e["frenet"], o["frenet"], rtol=0, atol=TOL)
 
 
-@pytest.mark.parametrize("variant,n_points", [(20, [2, 3, 9, 60, 128]), (21, [200, 256])])
+@pytest.mark.parametrize("variant,n_points", [(20, [2, 3, 9, 60, 128]), (21, [200, 256]), (22, [5, 100, 136])])
 def test_emu_kpc_thread_per_station(oracle_params, variant, n_points):
     """"KPC" (SolverKpAsInputConstrained) on the thread-per-station skeleton, assembled in the kernel: same status,
     iteration count and iterates as the oracle's restatement of solver_kp_as_input_constrained.cpp, including limits
