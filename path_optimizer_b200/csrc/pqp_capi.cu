@@ -67,14 +67,20 @@ int pick_variant(int n, int keep, int form = PQP_FORM_KP) {
 // point that sees the lengths on the host selects it: the first class that takes (n, keep); when that class needs more
 // shared memory than the device offers, the one-warp kernel if the path fits there; else the smallest launch of the
 // one-warp kernel, which reports PQP_INVALID_PROBLEM for the path.  Returns false in that last case.
-// "KPC" has thread-per-station classes only (up to 256 stations): false + *v_out = -1 means the path takes the host-assembled
-// generic kernel.
+// "KPC" has thread-per-station classes only (up to 256 stations, more than the host-assembled generic kernel can hold in
+// one SM): a longer path is launched on the last class with the smallest shared-memory size, where the kernel's own shape
+// check reports PQP_INVALID_PROBLEM for it.  Returns false in that case.
 bool class_for(const pqp_handle *h, int n, int keep, int *v_out, size_t *need_out, int form = PQP_FORM_KP) {
     if (form == PQP_FORM_KPC) {
         const int pv = n >= 2 ? pick_variant(n, 4, form) : -1;
-        *v_out = pv;
-        *need_out = pv >= 0 ? kVariants[pv].smem(n, 4) : 0;
-        return pv >= 0 && *need_out <= (size_t)h->smem_optin;
+        if (pv >= 0 && kVariants[pv].smem(n, 4) <= (size_t)h->smem_optin) {
+            *v_out = pv;
+            *need_out = kVariants[pv].smem(n, 4);
+            return true;
+        }
+        *v_out = kNumVariants - 1;
+        *need_out = kVariants[kNumVariants - 1].smem(2, 4);
+        return false;
     }
     int v = kNumKp - 1;
     if (n >= 2) {
@@ -153,10 +159,7 @@ int pqp_launch_kp_classes(pqp_handle *h, const pqp::BatchView &bv, int batch, co
         for (int b = 0; b < batch; ++b) {
             int v;
             size_t need;
-            if (!class_for(h, n[b], keepv[b], &v, &need, form) && form == PQP_FORM_KPC) {
-                set_err("a KPC path has no thread-per-station class (more than 256 stations): use pqp_solve_batch (host buffers)");
-                return PQP_ERR_UNSUPPORTED;
-            }
+            class_for(h, n[b], keepv[b], &v, &need, form);
             cls[b] = v;
             pl.smem_v[v] = std::max(pl.smem_v[v], need);
             pl.count_v[v]++;
@@ -716,13 +719,14 @@ int pqp_solve_batch(pqp_handle *h, int formulation, int batch, const int32_t *n_
     }
     if (stats) memset(stats, 0, sizeof(*stats));
     if (batch == 0) return PQP_OK;
-    bool kpc_classes = formulation == PQP_FORM_KPC && max_k && max_kp && batch <= h->max_batch;
-    for (int b = 0; b < batch && kpc_classes; ++b) {
-        int v;
-        size_t need;
-        kpc_classes = class_for(h, n_points[b], 4, &v, &need, PQP_FORM_KPC);
+    if (formulation == PQP_FORM_KPC && (!max_k || !max_kp)) {
+        set_err("KPC needs max_k and max_kp (ReferencePath::getMaxKList / getMaxKpList; pqp_update_limits)");
+        return PQP_ERR_ARG;
     }
-    if (formulation != PQP_FORM_KP && !kpc_classes)   // "K", and "KPC" batches with a path beyond the thread-per-station classes
+    // PQP_GENERIC_KPC=1 (diagnostics): route "KPC" through the host-assembled generic kernel, as "K" always is
+    static const bool generic_kpc = [] { const char *e = getenv("PQP_GENERIC_KPC"); return e && *e == '1'; }();
+    const bool kpc_classes = formulation == PQP_FORM_KPC && !generic_kpc;
+    if (formulation != PQP_FORM_KP && !kpc_classes)
         return solve_batch_generic(h, formulation, batch, n_points, ref, bounds, x0, end_heading, max_k, max_kp, out_states,
                                    out_frenet, status, iters, stats);
     if (batch > h->max_batch) {
