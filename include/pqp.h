@@ -273,8 +273,9 @@ const char *pqp_version(void);
 /* Largest n_points a path may have on this device (one path must fit one SM's shared memory; longer paths report
  * PQP_INVALID_PROBLEM).  The limit depends on keep_control_steps: pqp_max_points_keep gives it for one value
  * (1..10; e.g. 408 at keep = 3 on the thread-per-station classes, then the one-warp kernel up to 414), pqp_max_points
- * the minimum over keep = 1..10, i.e. a length every spacing can take.  KP only (0 otherwise: K / KPC paths are
- * bounded by the generic kernel's shared memory, which depends on the assembled band). */
+ * the minimum over keep = 1..10, i.e. a length every spacing can take.  KP and KPC (KPC: 256 stations, the largest
+ * in-kernel KPC class); 0 for K, whose paths are bounded by the generic kernel's shared memory, which depends on the
+ * assembled band. */
 int pqp_max_points(pqp_handle *h, int formulation);
 int pqp_max_points_keep(pqp_handle *h, int formulation, int keep);
 

@@ -429,13 +429,13 @@ int pqp_device_class_info(int max_n_points, int min_keep, int max_keep, int smem
 }
 
 int pqp_max_points_keep(pqp_handle *h, int formulation, int keep) {
-    if (!h || formulation != PQP_FORM_KP || keep < 1 || keep > 10) return 0;
-    // mirrors the per-path selection of pqp_solve_batch (class_for): preferred class, else the one-warp kernel
+    if (!h || (formulation != PQP_FORM_KP && formulation != PQP_FORM_KPC) || keep < 1 || keep > 10) return 0;
+    // mirrors the per-path selection of pqp_solve_batch (class_for): preferred class, else the one-warp kernel (KP only)
     int best = 0;
     for (int n = 2; n <= 4096; ++n) {
         int v;
         size_t need;
-        if (class_for(h, n, keep, &v, &need)) best = n;
+        if (class_for(h, n, keep, &v, &need, formulation)) best = n;
         else break;
     }
     return best;

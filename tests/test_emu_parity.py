@@ -127,7 +127,7 @@ def test_emu_generic_kernel_k_and_kpc(oracle_params, form):
 def test_emu_primal_infeasible(oracle_params, variant):
     """Corridors with no feasible path: OSQP's primal-infeasibility certificate fires (status -3) at the
     same check iteration as in the oracle, the output is NaN, feasible neighbours are untouched."""
-    b = synth.infeasible_corridors(6, 60)
+    b = synth.infeasible_corridors(6 if variant == 0 else 2, 60)
     e = emu.solve_batch(oracle_params, b, variant=variant)
     o = oracle.solve_batch(oracle_params, 0, b)
     assert np.array_equal(e["status"], o["status"]) and np.array_equal(e["iters"], o["iters"])
@@ -193,10 +193,14 @@ def test_emu_kpc_thread_per_station(oracle_params, variant, n_points):
 
 
 def test_emu_kpc_infeasible_and_parameters(oracle_params):
-    b = synth.infeasible_corridors(4, 60)
+    # (the emulator runs one pthread per lane: a 4000-iteration path costs ~20 s, so cap the iteration count here; the
+    # full-length run is the GPU test test_gpu_parity.py::test_k_and_kpc_formulations / test_primal_infeasible_corridors)
+    p = oracle_params.copy()
+    p.max_iter = 600
+    b = synth.infeasible_corridors(2, 60)
     mk, mkp = _limits(b)
-    e = emu.solve_batch(oracle_params, b, variant=20, max_k=mk, max_kp=mkp)
-    o = oracle.solve_batch(oracle_params, 2, b, threads=4, max_k=mk, max_kp=mkp)
+    e = emu.solve_batch(p, b, variant=20, max_k=mk, max_kp=mkp)
+    o = oracle.solve_batch(p, 2, b, threads=4, max_k=mk, max_kp=mkp)
     assert np.array_equal(e["status"], o["status"]) and np.array_equal(e["iters"], o["iters"])
     assert (o["status"] != 1).any()
     p = oracle_params.copy()

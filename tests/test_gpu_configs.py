@@ -225,6 +225,7 @@ def test_kpc_thread_per_station_classes_and_fallback(oracle_params):
     r2 = s.solve(b2, formulation="KPC", max_k=mk2, max_kp=mkp2)
     o2 = oracle.solve_batch(oracle_params, 2, b2, threads=4, max_k=mk2, max_kp=mkp2)
     assert r2["status"][1] == -100 and np.isnan(r2["frenet"][40:340]).all()
+    assert L.pqp_max_points_keep(s._h, 2, 4) == 256 and s.max_points("KPC") == 256 and s.max_points("K") == 0
     keep = np.array([0, 2])
     assert np.array_equal(r2["status"][keep], o2["status"][keep]) and np.array_equal(r2["iters"][keep], o2["iters"][keep])
     np.testing.assert_allclose(r2["frenet"][:40], o2["frenet"][:40], rtol=0, atol=TOL)
