@@ -190,8 +190,8 @@ int pqp_set_params(pqp_handle *h, const pqp_params *params);
  *   max_k, max_kp    [sum n_points] each, KPC only (ReferencePath::getMaxKList / getMaxKpList, one entry per
  *                    station; like the reference the solver reads the first ch entries of a path's max_kp); else NULL.
  *                    pqp_update_limits (pqp_env.h) derives them from the v, a fields of the reference states.
- * "KP" and "KPC" run on the thread-per-station kernel classes ("KPC" up to 256 stations per path; a batch with a longer
- * KPC path, and every "K" batch, is assembled sparse on the host and solved by the generic one-warp kernel).
+ * All three formulations are assembled inside thread-per-station kernel classes ("KP" up to 408 stations per path,
+ * "KPC" up to 256, "K" up to 416; a longer path reports PQP_INVALID_PROBLEM for itself).
  *   out_states       [sum n_points] optimized path: x, y, z(heading), k, s filled exactly as
  *                    getOptimizedPath does (solver_kp_as_input.cpp:26-43); v = a = 0
  *   out_frenet       optional [sum n_points][3] = (e_y, e_phi, kappa) raw QP solution
@@ -223,7 +223,8 @@ int pqp_solve_batch(pqp_handle *h, int formulation, int batch,
  * that exceeds the stated bounds reports PQP_INVALID_PROBLEM.  Asynchronous on `stream`
  * (a cudaStream_t, or NULL for the handle's own stream); no host synchronisation is done
  * unless `stats` is non-NULL.  Formulations: "KP", and "KPC" (d_max_k / d_max_kp then required, every path <= 256
- * stations; keep bounds are ignored: KPC holds a control for 4 stations); "K" returns PQP_ERR_UNSUPPORTED.
+ * stations; keep bounds are ignored: KPC holds a control for 4 stations), "K" (every path <= 416 stations; keep bounds
+ * ignored: one steering control per station).
  * No reference counterpart (the reference has no device). */
 int pqp_solve_batch_device(pqp_handle *h, int formulation, int batch, int total_points,
                            int max_n_points, int min_keep, int max_keep,
@@ -273,9 +274,8 @@ const char *pqp_version(void);
 /* Largest n_points a path may have on this device (one path must fit one SM's shared memory; longer paths report
  * PQP_INVALID_PROBLEM).  The limit depends on keep_control_steps: pqp_max_points_keep gives it for one value
  * (1..10; e.g. 408 at keep = 3 on the thread-per-station classes, then the one-warp kernel up to 414), pqp_max_points
- * the minimum over keep = 1..10, i.e. a length every spacing can take.  KP and KPC (KPC: 256 stations, the largest
- * in-kernel KPC class); 0 for K, whose paths are bounded by the generic kernel's shared memory, which depends on the
- * assembled band. */
+ * the minimum over keep = 1..10, i.e. a length every spacing can take.  KPC: 256 stations, K: 416 (their largest
+ * classes; keep does not matter for them). */
 int pqp_max_points(pqp_handle *h, int formulation);
 int pqp_max_points_keep(pqp_handle *h, int formulation, int keep);
 
@@ -285,7 +285,8 @@ int pqp_max_points_keep(pqp_handle *h, int formulation, int keep);
  * path (it would report PQP_INVALID_PROBLEM).  pqp_device_class_info: the single class pqp_solve_batch_device picks for
  * the caller's bounds.  smem_optin = the device's opt-in shared memory per block (0: B200's 232448). */
 int pqp_class_info(int n_points, int keep, int smem_optin, int *variant, int *threads, int64_t *smem_bytes);
-int pqp_class_info_kpc(int n_points, int smem_optin, int *variant, int *threads, int64_t *smem_bytes);   /* the same for a "KPC" path (keep_control_steps is 4); PQP_ERR_UNSUPPORTED: host-assembled generic kernel */
+int pqp_class_info_kpc(int n_points, int smem_optin, int *variant, int *threads, int64_t *smem_bytes);   /* the same for a "KPC" path (keep_control_steps is 4); PQP_ERR_UNSUPPORTED: longer than the largest KPC class (256 stations) */
+int pqp_class_info_form(int formulation, int n_points, int keep, int smem_optin, int *variant, int *threads, int64_t *smem_bytes);   /* any formulation ("K": keep ignored) */
 const char *pqp_class_name(int variant);   /* kernel name of a class-table index, as profilers print it ("" if out of range) */
 int pqp_device_class_info(int max_n_points, int min_keep, int max_keep, int smem_optin, int *variant, int *threads,
                           int64_t *smem_bytes);

@@ -30,7 +30,8 @@ namespace {
 // (Kp3) instantiations; anything else runs on the one-warp generic kernel (last).
 typedef PqpVariant Variant;
 constexpr int kNumKp = 9;          // "KP" classes: thread-per-station kernels, then the one-warp kernel (index kNumKp - 1)
-constexpr int kNumVariants = 12;   // + the "KPC" thread-per-station classes
+constexpr int kNumKpc = 12;        // + the "KPC" thread-per-station classes [kNumKp, kNumKpc)
+constexpr int kNumVariants = 15;   // + the "K" thread-per-station classes [kNumKpc, kNumVariants) (pqp_kk_core.cuh)
 struct VariantTable {
     Variant v[kNumVariants];
     VariantTable() {
@@ -40,6 +41,7 @@ struct VariantTable {
         pqp_variant_k3_27_7_10_34(&v[k++]); pqp_variant_k3_37_7_12_34(&v[k++]); pqp_variant_k3_37_7_13_34(&v[k++]);
         pqp_variant_k1_generic(&v[k++]);
         pqp_variant_k3c_13_7_8_34(&v[k++]); pqp_variant_k3c_23_7_4_17(&v[k++]); pqp_variant_k3c_23_7_8_34(&v[k++]);
+        pqp_variant_kk_4(&v[k++]); pqp_variant_kk_8(&v[k++]); pqp_variant_kk_13(&v[k++]);
     }
 };
 const Variant *variants() {
@@ -56,8 +58,15 @@ unsigned skip_mask() {
     return m;
 }
 
+// classes of a formulation: [v0, v1) of the table
+void form_range(int form, int *v0, int *v1) {
+    *v0 = form == PQP_FORM_KPC ? kNumKp : form == PQP_FORM_K ? kNumKpc : 0;
+    *v1 = form == PQP_FORM_KPC ? kNumKpc : form == PQP_FORM_K ? kNumVariants : kNumKp;
+}
+
 int pick_variant(int n, int keep, int form = PQP_FORM_KP) {
-    const int v0 = form == PQP_FORM_KPC ? kNumKp : 0, v1 = form == PQP_FORM_KPC ? kNumVariants : kNumKp;
+    int v0, v1;
+    form_range(form, &v0, &v1);
     for (int v = v0; v < v1; ++v)
         if (!((skip_mask() >> v) & 1u) && kVariants[v].fits(n, keep)) return v;
     return -1;
@@ -71,15 +80,18 @@ int pick_variant(int n, int keep, int form = PQP_FORM_KP) {
 // one SM): a longer path is launched on the last class with the smallest shared-memory size, where the kernel's own shape
 // check reports PQP_INVALID_PROBLEM for it.  Returns false in that case.
 bool class_for(const pqp_handle *h, int n, int keep, int *v_out, size_t *need_out, int form = PQP_FORM_KP) {
-    if (form == PQP_FORM_KPC) {
-        const int pv = n >= 2 ? pick_variant(n, 4, form) : -1;
-        if (pv >= 0 && kVariants[pv].smem(n, 4) <= (size_t)h->smem_optin) {
+    if (form == PQP_FORM_KPC || form == PQP_FORM_K) {
+        const int fk = form == PQP_FORM_KPC ? 4 : 1;
+        const int pv = n >= 2 ? pick_variant(n, fk, form) : -1;
+        if (pv >= 0 && kVariants[pv].smem(n, fk) <= (size_t)h->smem_optin) {
             *v_out = pv;
-            *need_out = kVariants[pv].smem(n, 4);
+            *need_out = kVariants[pv].smem(n, fk);
             return true;
         }
-        *v_out = kNumVariants - 1;
-        *need_out = kVariants[kNumVariants - 1].smem(2, 4);
+        int v0, v1;
+        form_range(form, &v0, &v1);
+        *v_out = v1 - 1;
+        *need_out = kVariants[v1 - 1].smem(2, fk);
         return false;
     }
     int v = kNumKp - 1;
@@ -105,13 +117,15 @@ bool class_for(const pqp_handle *h, int n, int keep, int *v_out, size_t *need_ou
 // interior counts change with it), and is launched with the largest shared-memory need over that range.
 bool device_class(pqp_handle *h, int nmax, int k_lo, int k_hi, int *v_out, size_t *smem_out, int form = PQP_FORM_KP) {
     if (form == PQP_FORM_KPC) k_lo = k_hi = 4;
+    if (form == PQP_FORM_K) k_lo = k_hi = 1;
     if (h->dc_nmax == nmax && h->dc_klo == k_lo && h->dc_khi == k_hi && h->dc_skip == (int)skip_mask() && h->dc_form == form) {
         *v_out = h->dc_v; *smem_out = h->dc_smem;
         return h->dc_v >= 0;
     }
     int v = -1;
     size_t smem = 0;
-    const int c0 = form == PQP_FORM_KPC ? kNumKp : 0, c1 = form == PQP_FORM_KPC ? kNumVariants : kNumKp;
+    int c0, c1;
+    form_range(form, &c0, &c1);
     for (int cand = c0; cand < c1 && v < 0; ++cand) {
         if ((skip_mask() >> cand) & 1u) continue;
         bool all = true;
@@ -143,7 +157,7 @@ int pqp_launch_kp_classes(pqp_handle *h, const pqp::BatchView &bv, int batch, co
     // keep_control_steps per path
     std::vector<int32_t> keepv((size_t)batch);
     for (int b = 0; b < batch; ++b)
-        keepv[b] = form == PQP_FORM_KPC ? 4 : keep_in ? keep_in[b] : (n[b] >= 2 ? pqp_keep_control_steps(PQP_FORM_KP, ref + off[b], n[b]) : 1);
+        keepv[b] = form == PQP_FORM_KPC ? 4 : form == PQP_FORM_K ? 1 : keep_in ? keep_in[b] : (n[b] >= 2 ? pqp_keep_control_steps(PQP_FORM_KP, ref + off[b], n[b]) : 1);
     // The plan (class per path, longest-first order inside a class) only depends on (n, keep): a caller that solves
     // batches of the same shape back to back reuses it, and the order array already on the device with it.
     pqp_handle::ClassPlan &pl = h->plan;
@@ -410,6 +424,19 @@ int pqp_class_info_kpc(int n_points, int smem_optin, int *variant, int *threads,
     return ok ? PQP_OK : PQP_ERR_UNSUPPORTED;
 }
 
+int pqp_class_info_form(int formulation, int n_points, int keep, int smem_optin, int *variant, int *threads, int64_t *smem_bytes) {
+    if (formulation != PQP_FORM_KP && formulation != PQP_FORM_KPC && formulation != PQP_FORM_K) return PQP_ERR_ARG;
+    pqp_handle fake;
+    fake.smem_optin = smem_optin > 0 ? smem_optin : 232448;
+    int v;
+    size_t need;
+    const bool ok = class_for(&fake, n_points, keep, &v, &need, formulation);
+    if (variant) *variant = v;
+    if (threads) *threads = ok ? kVariants[v].threads : 0;
+    if (smem_bytes) *smem_bytes = (int64_t)need;
+    return ok ? PQP_OK : PQP_ERR_UNSUPPORTED;
+}
+
 int pqp_device_class_info(int max_n_points, int min_keep, int max_keep, int smem_optin, int *variant, int *threads,
                           int64_t *smem_bytes) {
     pqp_handle fake;
@@ -429,7 +456,7 @@ int pqp_device_class_info(int max_n_points, int min_keep, int max_keep, int smem
 }
 
 int pqp_max_points_keep(pqp_handle *h, int formulation, int keep) {
-    if (!h || (formulation != PQP_FORM_KP && formulation != PQP_FORM_KPC) || keep < 1 || keep > 10) return 0;
+    if (!h || (formulation != PQP_FORM_KP && formulation != PQP_FORM_KPC && formulation != PQP_FORM_K) || keep < 1 || keep > 10) return 0;
     // mirrors the per-path selection of pqp_solve_batch (class_for): preferred class, else the one-warp kernel (KP only)
     int best = 0;
     for (int n = 2; n <= 4096; ++n) {
@@ -482,9 +509,9 @@ int pqp_solve_batch_device(pqp_handle *h, int formulation, int batch, int total_
         set_err("KPC needs d_max_k and d_max_kp (pqp_update_limits_device)");
         return PQP_ERR_ARG;
     }
-    if (formulation != PQP_FORM_KP && formulation != PQP_FORM_KPC) {
-        set_err("K is assembled on the host: use pqp_solve_batch (host buffers) for it");
-        return PQP_ERR_UNSUPPORTED;
+    if (formulation != PQP_FORM_KP && formulation != PQP_FORM_KPC && formulation != PQP_FORM_K) {
+        set_err("unknown formulation");
+        return PQP_ERR_ARG;
     }
     if (batch == 0) return PQP_OK;
     PQP_CUDA(cudaSetDevice(h->device));
@@ -532,7 +559,7 @@ int pqp_solve_batch_device_classes(pqp_handle *h, int formulation, int batch, in
                                    const double *d_max_k, const double *d_max_kp, pqp_state *d_out_states,
                                    double *d_out_frenet, int32_t *d_status, int32_t *d_iters, void *stream,
                                    pqp_stats *stats) {
-    if (!h || batch < 0 || !h_n_points || (!h_keep && formulation != PQP_FORM_KPC) || !d_n_points || !d_offsets || !d_ref ||
+    if (!h || batch < 0 || !h_n_points || (!h_keep && formulation == PQP_FORM_KP) || !d_n_points || !d_offsets || !d_ref ||
         !d_bounds || !d_x0 || !d_end_heading || !d_out_states || !d_status) {
         set_err("pqp_solve_batch_device_classes: bad argument");
         return PQP_ERR_ARG;
@@ -541,9 +568,9 @@ int pqp_solve_batch_device_classes(pqp_handle *h, int formulation, int batch, in
         set_err("KPC needs d_max_k and d_max_kp (pqp_update_limits_device)");
         return PQP_ERR_ARG;
     }
-    if (formulation != PQP_FORM_KP && formulation != PQP_FORM_KPC) {
-        set_err("K is assembled on the host: use pqp_solve_batch (host buffers) for it");
-        return PQP_ERR_UNSUPPORTED;
+    if (formulation != PQP_FORM_KP && formulation != PQP_FORM_KPC && formulation != PQP_FORM_K) {
+        set_err("unknown formulation");
+        return PQP_ERR_ARG;
     }
     if (batch == 0) return PQP_OK;
     if (batch > h->max_batch || total_points > h->max_total) {
@@ -723,10 +750,13 @@ int pqp_solve_batch(pqp_handle *h, int formulation, int batch, const int32_t *n_
         set_err("KPC needs max_k and max_kp (ReferencePath::getMaxKList / getMaxKpList; pqp_update_limits)");
         return PQP_ERR_ARG;
     }
-    // PQP_GENERIC_KPC=1 (diagnostics): route "KPC" through the host-assembled generic kernel, as "K" always is
+    // PQP_GENERIC_KPC=1 / PQP_GENERIC_K=1 (diagnostics): route "KPC" / "K" through the host-assembled generic kernel
+    // (round 1's path for them) instead of their thread-per-station classes
     static const bool generic_kpc = [] { const char *e = getenv("PQP_GENERIC_KPC"); return e && *e == '1'; }();
+    static const bool generic_k = [] { const char *e = getenv("PQP_GENERIC_K"); return e && *e == '1'; }();
     const bool kpc_classes = formulation == PQP_FORM_KPC && !generic_kpc;
-    if (formulation != PQP_FORM_KP && !kpc_classes)
+    const bool k_classes = formulation == PQP_FORM_K && !generic_k;
+    if (formulation != PQP_FORM_KP && !kpc_classes && !k_classes)
         return solve_batch_generic(h, formulation, batch, n_points, ref, bounds, x0, end_heading, max_k, max_kp, out_states,
                                    out_frenet, status, iters, stats);
     if (batch > h->max_batch) {

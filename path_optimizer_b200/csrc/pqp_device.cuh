@@ -28,6 +28,8 @@ struct DevParams {
     double d1, d2, d3, d4;
     double w_c, w_cr, w_pq, w_s;     // KP_curvature / curvature_rate / deviation / slack weights
     double kmax;                     // tan(max_steering_angle) / wheel_base
+    double k_w_c, k_w_cr, k_w_pq;    // "K" formulation: K_curvature / curvature_rate / deviation weights (solver_k_as_input.cpp:50-53)
+    double wheel_base, max_steer;    // "K": steering-angle control (setDynamicMatrix :89-103, bounds :180-183)
     double margin;                   // expected_safety_margin
     int constraint_end_heading;
     double rho, sigma, alpha, eps_abs, eps_rel, eps_prim_inf, eps_dual_inf;
@@ -62,6 +64,8 @@ inline DevParams dev_params_from(const pqp_params &p) {
     d.w_c = p.KP_curvature_weight; d.w_cr = p.KP_curvature_rate_weight;
     d.w_pq = p.KP_deviation_weight; d.w_s = p.KP_slack_weight;
     d.kmax = tan(p.max_steering_angle) / p.wheel_base;
+    d.k_w_c = p.K_curvature_weight; d.k_w_cr = p.K_curvature_rate_weight; d.k_w_pq = p.K_deviation_weight;
+    d.wheel_base = p.wheel_base; d.max_steer = p.max_steering_angle;
     d.margin = p.expected_safety_margin;
     d.constraint_end_heading = p.constraint_end_heading;
     d.rho = p.rho; d.sigma = p.sigma; d.alpha = p.alpha;

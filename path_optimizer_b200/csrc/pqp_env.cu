@@ -630,10 +630,9 @@ int pqp_plan_batch(pqp_handle *h, int formulation, int bounds_mode, int output_m
         pqp_set_err("pqp_plan_batch: bad argument");
         return PQP_ERR_ARG;
     }
-    if (formulation != PQP_FORM_KP && formulation != PQP_FORM_KPC) {
-        pqp_set_err("pqp_plan_batch chains the device-resident KP / KPC solve; K is assembled on the host "
-                    "(use pqp_update_bounds_batch + pqp_solve_batch + pqp_finish_raw_batch)");
-        return PQP_ERR_UNSUPPORTED;
+    if (formulation != PQP_FORM_KP && formulation != PQP_FORM_KPC && formulation != PQP_FORM_K) {
+        pqp_set_err("pqp_plan_batch: unknown formulation");
+        return PQP_ERR_ARG;
     }
     if (stats) memset(stats, 0, sizeof(*stats));
     EnvState *e;

@@ -27,6 +27,10 @@ PQP_DECLARE_VARIANT(k3_37_7_13_34)
 PQP_DECLARE_VARIANT(k3c_13_7_8_34)
 PQP_DECLARE_VARIANT(k3c_23_7_4_17)
 PQP_DECLARE_VARIANT(k3c_23_7_8_34)
+// thread-per-station block-cyclic-reduction kernels of the "K" formulation Kk<NW> (pqp_kk_core.cuh)
+PQP_DECLARE_VARIANT(kk_4)
+PQP_DECLARE_VARIANT(kk_8)
+PQP_DECLARE_VARIANT(kk_13)
 // one-warp generic KP kernel (any keep <= 10) and the generic banded-QP kernel of "K" / "KPC"
 PQP_DECLARE_VARIANT(k1_generic)
 const void *pqp_gen_kernel_fn();

@@ -1,0 +1,619 @@
+// pqp_kk_core.cuh -- thread-per-station solver for the "K" formulation (SolverKAsInput).
+//
+// Reference being replaced: src/solver/solver_k_as_input.cpp:14-207 (setHessianMatrix, setDynamicMatrix,
+// setConstraintMatrix, getOptimizedPath) + the OSQP solve behind src/solver/solver.cpp:46-77.
+//
+// The QP (N stations): unknowns e_phi_i, e_y_i (state), delta_i (steering, i < N-1), e_i (corridor slack of the second
+// circle); n = 4N-1, m = 11N-1.  Thread i owns station i: its 11 rows
+//     0  -e_phi_i + e_phi_{i-1} + q_{i-1} e_y_{i-1} + c_{i-1} delta_{i-1}  = b0      (dynamics, :89-121,156-167)
+//     1  -e_y_i   + ds_{i-1} e_phi_{i-1} + e_y_{i-1}                        = b1
+//     2  e_phi_i   free (end-heading window at the last station, :172-178)            (identity rows, :124-126,169-187)
+//     3  e_y_i     free
+//     4  delta_i   in +-max_steering_angle          (i < N-1)
+//     5  e_i       in [0, margin]
+//     6..8  d1|d3|d4 e_phi_i + e_y_i in the clearance of circles 0|2|3                (:129-137,189-199)
+//     9  d2 e_phi_i + e_y_i - e_i <= ub1 - margin,  10  d2 e_phi_i + e_y_i + e_i >= lb1 + margin   (:141-147,200-207)
+// and its 4 columns stay in registers for the whole solve.  OSQP's recurrence (Ruiz scaling, rho classes, ADMM,
+// termination, primal-infeasibility certificate, adaptive rho) is the one of pqp_gen_core.cuh -- same unscaled-weighted
+// form v = z + w, W = rho_row E^2 -- with the sparse gathers replaced by these stencils.
+//
+// Reduced KKT  c P + sigma D^-2 + A' W A : the slack e_i couples to (e_phi_i, e_y_i) only through rows 9 / 10, which have
+// equal weight (same rho class, bit-identical Ruiz factors) and opposite sign on e_i: the coupling cancels exactly and
+// e_i is a scalar division.  What remains is block tridiagonal by station with 3 x 3 blocks (e_phi, e_y, delta; the
+// curvature-rate term of P couples delta_i to delta_{i+1}).  It is factored and solved by block CYCLIC REDUCTION: at
+// level l the stations with index = 2^l (mod 2^(l+1)) are eliminated, each by its own thread, which keeps
+// A_j^-1, G_L = A_j^-1 C_{j,j-s}, G_R = A_j^-1 C_{j,j+s} (24 doubles) in registers.  One solve is ceil(log2 N) levels
+// down (each eliminated station pushes G' r to its two neighbours) and as many up (x_j = A_j^-1 r_j - G_L x_a - G_R x_b),
+// one barrier per level, no serial chain longer than a 3 x 3 product.
+#pragma once
+#include "pqp_kp_core.cuh"
+
+namespace pqp {
+
+template <int NW>
+struct Kk {
+    static constexpr int kT = NW * 32;            // threads = max stations
+    static constexpr int kP = kT + 2;             // pitch of the exchange rows: entry 0 = "station -1", entry N+1 = "station N" (zeros)
+    static constexpr int kCtaScratch = (NW <= 8) ? 128 : 256;
+    // shared memory (doubles): 3 x-rows + 2 dual rows + 2 weight rows + 1 delta-scale row (pitch kP); 6 push rows, 9 coupling
+    // rows, 18 G rows, 11 parked-dual rows, 11 E rows, 2 output rows (pitch kT)
+    static constexpr int kXRows = 8, kTRows = 6 + 9 + 18 + 11 + 11 + 2;
+    PQP_HD static size_t smem_doubles(int /*N*/) { return (size_t)kXRows * kP + (size_t)kTRows * kT; }
+    PQP_HD static bool fits(int N, int /*keep*/) { return N >= 2 && N <= kT; }
+
+    struct Sm {
+        double *b;
+        PQP_DEV double *xr(int c) const { return b + c * kP + 1; }            // c: 0 e_phi, 1 e_y, 2 delta; index i in [-1, N]
+        PQP_DEV double *gr(int c) const { return b + (3 + c) * kP + 1; }      // dual-like values of rows 0 / 1
+        PQP_DEV double *wr(int c) const { return b + (5 + c) * kP + 1; }      // W (or E) of rows 0 / 1
+        PQP_DEV double *dr() const { return b + 7 * kP + 1; }                 // D of delta (Ruiz sweeps)
+        PQP_DEV double *t(int k) const { return b + kXRows * kP + k * kT; }
+        PQP_DEV double *push(int k) const { return t(k); }                    // 0..2 to the left neighbour, 3..5 to the right
+        PQP_DEV double *cpl(int k) const { return t(6 + k); }                 // current coupling to the right neighbour (factor)
+        PQP_DEV double *gl(int k) const { return t(15 + k); }                 // G_L, G_R of the level being eliminated (factor)
+        PQP_DEV double *gR(int k) const { return t(24 + k); }
+        PQP_DEV double *wold(int k) const { return t(33 + k); }
+        PQP_DEV double *E(int k) const { return t(44 + k); }
+        PQP_DEV double *ox() const { return t(55); }
+        PQP_DEV double *oy() const { return t(56); }
+    };
+
+    // 3 x 3 helpers (row-major)
+    PQP_DEV static void mm(const double *a, const double *b, double *o) {          // o = a b
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int cc = 0; cc < 3; ++cc) o[r * 3 + cc] = a[r * 3] * b[cc] + a[r * 3 + 1] * b[3 + cc] + a[r * 3 + 2] * b[6 + cc];
+    }
+    PQP_DEV static void mtm(const double *a, const double *b, double *o) {         // o = a' b
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int cc = 0; cc < 3; ++cc) o[r * 3 + cc] = a[r] * b[cc] + a[3 + r] * b[3 + cc] + a[6 + r] * b[6 + cc];
+    }
+
+    PQP_DEV static void solve_path(const Cta &c, const DevParams &pm, const BatchView &bv, int prob, double *smem,
+                                   size_t smem_cap) {
+        const int tid = c.tid();
+        const int N = bv.n_points[prob];
+        const int off = bv.offsets[prob];
+        const pqp_state *ref = bv.ref + off;
+        const pqp_station_bounds *bnd = bv.bounds + off;
+        pqp_state *out = bv.out_states + off;
+        const double qnan = nan("");
+        if (!fits(N, 1) || smem_doubles(N) > smem_cap) {
+            if (tid == 0) {
+                bv.status[prob] = PQP_INVALID_PROBLEM;
+                if (bv.iters) bv.iters[prob] = 0;
+            }
+            for (int i = tid; i < N; i += kT) {
+                out[i].x = out[i].y = out[i].z = out[i].k = out[i].s = qnan;
+                out[i].v = out[i].a = 0.0;
+                if (bv.out_frenet) {
+                    double *f = bv.out_frenet + 3 * (size_t)(off + i);
+                    f[0] = f[1] = f[2] = qnan;
+                }
+            }
+            return;
+        }
+        Sm s{smem};
+        const int i = tid;
+        const bool live = i < N, first = (i == 0), last = (i == N - 1);
+        const bool hasd = live && !last;                 // delta_i exists
+        int Lv = 0;
+        while ((1 << Lv) < N) ++Lv;
+        int lev = Lv;                                    // level at which this station is eliminated (station 0: never)
+        if (i > 0) { lev = 0; while (!((i >> lev) & 1)) ++lev; }
+
+        // ---- per-station data ------------------------------------------------------------------------
+        // transition i-1 -> i (rows 0 / 1 of this station) and i -> i+1 (the same rows of the next station, seen from my columns)
+        double pa = 0, qp = 0, cp = 0, dsp = 0, pb = 0, na = 0, qn = 0, cn = 0, dsn = 0, nb = 0;
+        double lo[11], hi[11];
+#pragma unroll
+        for (int k = 0; k < 11; ++k) { lo[k] = -kOsqpInfty; hi[k] = kOsqpInfty; }
+        double Pdd = 0.0;                                // diagonal of R for delta_i
+        const double w_cr = pm.k_w_cr;
+        const bool dprev = hasd && i >= 1, dnext = hasd && (i + 1 <= N - 2);   // partners of delta_i in R
+        int invalid = 0;
+        if (live) {
+            if (!first) {
+                const double rk = ref[i - 1].k, rs = ref[i].s - ref[i - 1].s;
+                const double rd = atan(rk * pm.wheel_base);
+                pa = 1.0; pb = 1.0;
+                qp = -rs * pow(rk, 2);
+                dsp = rs;
+                cp = rs / pm.wheel_base / pow(cos(rd), 2);
+                lo[0] = hi[0] = rs * rd / pm.wheel_base / pow(cos(rd), 2);
+                lo[1] = hi[1] = 0.0;
+            } else {
+                lo[0] = hi[0] = -bv.x0[3 * (size_t)prob + 1];     // x0 << err[1], err[0]  (:156-159)
+                lo[1] = hi[1] = -bv.x0[3 * (size_t)prob];
+            }
+            if (!last) {
+                const double rk = ref[i].k, rs = ref[i + 1].s - ref[i].s;
+                const double rd = atan(rk * pm.wheel_base);
+                na = 1.0; nb = 1.0;
+                qn = -rs * pow(rk, 2);
+                dsn = rs;
+                cn = rs / pm.wheel_base / pow(cos(rd), 2);
+                lo[4] = -pm.max_steer; hi[4] = pm.max_steer;
+                const int nc = N - 1;
+                Pdd = (i == 0 || i == nc - 1) ? (pm.k_w_c + w_cr) : (w_cr * 2 + pm.k_w_c);
+            }
+            if (last && pm.constraint_end_heading) {
+                const double pi = 3.14159265358979323846;
+                const double end_psi = constraint_angle(bv.end_heading[prob] - ref[N - 1].z);
+                if (end_psi < 70 * pi / 180) {
+                    lo[2] = end_psi - 5 * pi / 180;
+                    hi[2] = end_psi + 5 * pi / 180;
+                }
+            }
+            lo[5] = 0.0; hi[5] = pm.margin;
+            const pqp_station_bounds bb = bnd[i];
+            lo[6] = bb.c0_lb; hi[6] = bb.c0_ub;
+            lo[7] = bb.c2_lb; hi[7] = bb.c2_ub;
+            lo[8] = bb.c3_lb; hi[8] = bb.c3_ub;
+            hi[9] = bb.c1_ub - pm.margin;
+            lo[10] = bb.c1_lb + pm.margin;
+#pragma unroll
+            for (int k = 0; k < 11; ++k)
+                if (!(lo[k] <= hi[k])) invalid = 1;
+        }
+        const double cf[5] = {pm.d1, pm.d3, pm.d4, pm.d2, pm.d2};     // e_phi coefficient of rows 6..10
+        // zero entries either side of the exchange rows
+        if (tid == 0) {
+            for (int r = 0; r < kXRows; ++r) { smem[r * kP] = 0.0; smem[r * kP + N + 1] = 0.0; }
+        }
+        invalid = c.any(invalid);
+
+        // A x for my rows: own (xf, xy, xd, xe), previous station's (e_phi, e_y, delta) from the exchange rows
+        auto rows_of = [&](double xf, double xy, double xd, double xe, double *ax) {
+            const double pf = s.xr(0)[i - 1], py = s.xr(1)[i - 1], pd = s.xr(2)[i - 1];
+            ax[0] = ((pa * pf + qp * py) - xf) + cp * pd;
+            ax[1] = (dsp * pf + pb * py) - xy;
+            ax[2] = xf; ax[3] = xy; ax[4] = xd; ax[5] = xe;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) ax[6 + k] = cf[k] * xf + xy;
+            ax[9] = (cf[3] * xf + xy) - xe;
+            ax[10] = (cf[4] * xf + xy) + xe;
+        };
+        // A' g for my columns: my rows' g, rows 0 / 1 of the next station from the exchange rows
+        auto cols_of = [&](const double *g, double *aty) {
+            const double g0n = s.gr(0)[i + 1], g1n = s.gr(1)[i + 1];
+            aty[0] = ((((((-g[0] + na * g0n) + dsn * g1n) + g[2]) + cf[0] * g[6]) + cf[1] * g[7]) + cf[2] * g[8]) + cf[3] * g[9] + cf[4] * g[10];
+            aty[1] = ((((((-g[1] + qn * g0n) + nb * g1n) + g[3]) + g[6]) + g[7]) + g[8]) + g[9] + g[10];
+            aty[2] = cn * g0n + g[4];
+            aty[3] = (g[5] - g[9]) + g[10];
+        };
+
+        int status = PQP_UNSOLVED, iter = 0;
+        double x[4] = {0, 0, 0, 0};                      // e_phi, e_y, delta, e
+        double v[11], W[11];
+#pragma unroll
+        for (int k = 0; k < 11; ++k) { v[k] = 0.0; W[k] = 0.0; }
+        double cost_c = 1.0;
+        if (invalid) {
+            status = PQP_INVALID_PROBLEM;
+        } else {
+            // ================= Ruiz equilibration + cost scaling (OSQP scale_data) =================
+            double D[4] = {1, 1, 1, 1}, E[11];
+#pragma unroll
+            for (int k = 0; k < 11; ++k) E[k] = 1.0;
+            const double Pd[4] = {0.0, pm.k_w_pq, Pdd, pm.w_s};
+            for (int sweep = 0; sweep < pm.scaling; ++sweep) {
+                if (live) {
+                    s.xr(0)[i] = D[0]; s.xr(1)[i] = D[1]; s.xr(2)[i] = hasd ? D[2] : 0.0;
+                    s.wr(0)[i] = E[0]; s.wr(1)[i] = E[1];
+                }
+                c.sync();
+                double fD[4] = {1, 1, 1, 1}, fE[11];
+#pragma unroll
+                for (int k = 0; k < 11; ++k) fE[k] = 1.0;
+                if (live) {
+                    const double E0n = s.wr(0)[i + 1], E1n = s.wr(1)[i + 1];
+                    const double Dfp = s.xr(0)[i - 1], Dyp = s.xr(1)[i - 1], Ddp = s.xr(2)[i - 1], Ddn = s.xr(2)[i + 1];
+                    double an[4];
+                    an[0] = fmax(fmax(E[0], E[2]), fmax(na * E0n, fabs(dsn) * E1n));
+                    an[1] = fmax(fmax(E[1], E[3]), fmax(fabs(qn) * E0n, nb * E1n));
+#pragma unroll
+                    for (int k = 0; k < 5; ++k) { an[0] = fmax(an[0], fabs(cf[k]) * E[6 + k]); an[1] = fmax(an[1], E[6 + k]); }
+                    an[2] = fmax(E[4], fabs(cn) * E0n);
+                    an[3] = fmax(E[5], fmax(E[9], E[10]));
+                    double pn[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) pn[q] = cost_c * fabs(Pd[q]) * D[q] * D[q];
+                    if (dprev) pn[2] = fmax(pn[2], cost_c * fabs(w_cr) * D[2] * Ddp);
+                    if (dnext) pn[2] = fmax(pn[2], cost_c * fabs(w_cr) * D[2] * Ddn);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) fD[q] = 1.0 / sqrt(limit_scaling(fmax(pn[q], an[q] * D[q])));
+                    double rn[11];
+                    rn[0] = fmax(fmax(D[0], pa * Dfp), fmax(fabs(qp) * Dyp, fabs(cp) * Ddp));
+                    rn[1] = fmax(D[1], fmax(fabs(dsp) * Dfp, pb * Dyp));
+                    rn[2] = D[0]; rn[3] = D[1]; rn[4] = D[2]; rn[5] = D[3];
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) rn[6 + k] = fmax(fabs(cf[k]) * D[0], D[1]);
+                    rn[9] = rn[10] = fmax(fmax(fabs(cf[3]) * D[0], D[1]), D[3]);
+#pragma unroll
+                    for (int k = 0; k < 11; ++k) fE[k] = 1.0 / sqrt(limit_scaling(rn[k] * E[k]));
+                }
+                c.sync();
+#pragma unroll
+                for (int q = 0; q < 4; ++q) D[q] *= fD[q];
+#pragma unroll
+                for (int k = 0; k < 11; ++k) E[k] *= fE[k];
+                if (hasd) s.dr()[i] = D[2];
+                else if (live) s.dr()[i] = 0.0;
+                c.sync();
+                double part = 0.0;
+                if (live) {
+                    const double Ddp = s.dr()[i - 1], Ddn = s.dr()[i + 1];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        if (q == 2 && !hasd) continue;
+                        double nrm = cost_c * fabs(Pd[q]) * D[q] * D[q];
+                        if (q == 2 && dprev) nrm = fmax(nrm, cost_c * fabs(w_cr) * D[2] * Ddp);
+                        if (q == 2 && dnext) nrm = fmax(nrm, cost_c * fabs(w_cr) * D[2] * Ddn);
+                        part += nrm;
+                    }
+                }
+                const double mean = c.sum(part) / (double)(4 * N - 1);
+                double ct = fmax(mean, 1.0);
+                ct = limit_scaling(ct);
+                cost_c = cost_c * (1.0 / ct);
+            }
+            double sg[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) sg[q] = pm.sigma / (D[q] * D[q]);
+            double rho = fmin(fmax(pm.rho, kRhoMin), kRhoMax);
+#pragma unroll
+            for (int k = 0; k < 11; ++k) {
+                W[k] = rho_bar(E[k] * lo[k], E[k] * hi[k], rho) * E[k] * E[k];
+                s.E(k)[tid] = E[k];
+            }
+            if (!live || last) W[4] = 0.0;               // no delta at the last station: the row does not exist
+            if (!live) {
+#pragma unroll
+                for (int k = 0; k < 11; ++k) W[k] = 0.0;
+            }
+
+            // ---- factorisation state: A_j^-1 (symmetric, 6), G_L, G_R of my elimination level; 1 / pivot of the slack
+            double Ai[6] = {1, 0, 0, 1, 0, 1}, GL[9], GR[9], inv_e = 1.0;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) GL[k] = GR[k] = 0.0;
+
+            auto factor = [&]() -> int {
+                int ok = 1;
+                if (live) { s.wr(0)[i] = W[0]; s.wr(1)[i] = W[1]; }
+                c.sync();
+                double A[9], C[9];
+#pragma unroll
+                for (int k = 0; k < 9; ++k) { A[k] = 0.0; C[k] = 0.0; }
+                A[0] = A[4] = A[8] = 1.0;
+                if (live) {
+                    const double W0n = s.wr(0)[i + 1], W1n = s.wr(1)[i + 1];   // 0 beyond the last station
+                    double sw = 0.0, swd = 0.0, swdd = 0.0;                      // sums over rows 6..10 of W, W d, W d^2
+#pragma unroll
+                    for (int k = 0; k < 5; ++k) { sw += W[6 + k]; swd += W[6 + k] * cf[k]; swdd += W[6 + k] * cf[k] * cf[k]; }
+                    const double u0[3] = {na, qn, cn}, u1[3] = {dsn, nb, 0.0};   // rows 0 / 1 of the next station on my columns
+                    A[0] = cost_c * Pd[0] + sg[0] + W[0] + W[2] + swdd + W0n * u0[0] * u0[0] + W1n * u1[0] * u1[0];
+                    A[1] = swd + W0n * u0[0] * u0[1] + W1n * u1[0] * u1[1];
+                    A[2] = W0n * u0[0] * u0[2];
+                    A[4] = cost_c * Pd[1] + sg[1] + W[1] + W[3] + sw + W0n * u0[1] * u0[1] + W1n * u1[1] * u1[1];
+                    A[5] = W0n * u0[1] * u0[2];
+                    A[8] = hasd ? (cost_c * Pd[2] + sg[2] + W[4] + W0n * u0[2] * u0[2]) : 1.0;
+                    A[3] = A[1]; A[6] = A[2]; A[7] = A[5];
+                    if (!last) {       // K[i, i+1]: rows 0 / 1 of the next station carry -1 on its e_phi / e_y; R couples the deltas
+#pragma unroll
+                        for (int r = 0; r < 3; ++r) { C[r * 3] = -(W0n * u0[r]); C[r * 3 + 1] = -(W1n * u1[r]); }
+                        if (dnext) C[8] = cost_c * (-w_cr);
+                    }
+                    inv_e = 1.0 / (cost_c * Pd[3] + sg[3] + W[5] + W[9] + W[10]);
+#pragma unroll
+                    for (int k = 0; k < 9; ++k) s.cpl(k)[i] = C[k];
+                }
+                c.sync();
+                for (int l = 0; l < Lv; ++l) {
+                    const int st = 1 << l;
+                    if (live && lev == l) {
+                        if (!(A[0] > 0.0)) ok = 0;
+                        double inv[9], Ca[9], Ct[9];
+                        inv3_spd(A, inv);
+                        Ai[0] = inv[0]; Ai[1] = inv[1]; Ai[2] = inv[2]; Ai[3] = inv[4]; Ai[4] = inv[5]; Ai[5] = inv[8];
+#pragma unroll
+                        for (int k = 0; k < 9; ++k) Ca[k] = s.cpl(k)[i - st];       // K[a, j]
+#pragma unroll
+                        for (int r = 0; r < 3; ++r)
+#pragma unroll
+                            for (int cc = 0; cc < 3; ++cc) Ct[r * 3 + cc] = Ca[cc * 3 + r];   // K[j, a]
+                        mm(inv, Ct, GL);
+                        if (i + st < N) mm(inv, C, GR);
+#pragma unroll
+                        for (int k = 0; k < 9; ++k) { s.gl(k)[i] = GL[k]; s.gR(k)[i] = GR[k]; }
+                    }
+                    c.sync();
+                    if (live && lev > l) {
+                        double Cn[9];
+#pragma unroll
+                        for (int k = 0; k < 9; ++k) Cn[k] = 0.0;
+                        if (i + st < N) {               // right neighbour j = i + st is eliminated
+                            double G[9], Pm[9];
+#pragma unroll
+                            for (int k = 0; k < 9; ++k) G[k] = s.gl(k)[i + st];
+                            mm(C, G, Pm);
+#pragma unroll
+                            for (int k = 0; k < 9; ++k) A[k] -= Pm[k];
+                            if (i + 2 * st < N) {
+#pragma unroll
+                                for (int k = 0; k < 9; ++k) G[k] = s.gR(k)[i + st];
+                                mm(C, G, Pm);
+#pragma unroll
+                                for (int k = 0; k < 9; ++k) Cn[k] = -Pm[k];
+                            }
+                        }
+                        if (i >= st && i > 0) {         // left neighbour j' = i - st is eliminated: K[i, j'] = cpl(j')'
+                            double Cj[9], G[9], Pm[9];
+#pragma unroll
+                            for (int k = 0; k < 9; ++k) { Cj[k] = s.cpl(k)[i - st]; G[k] = s.gR(k)[i - st]; }
+                            mtm(Cj, G, Pm);
+#pragma unroll
+                            for (int k = 0; k < 9; ++k) A[k] -= Pm[k];
+                        }
+                        // keep the block symmetric (upper part is authoritative)
+                        A[3] = A[1]; A[6] = A[2]; A[7] = A[5];
+                        // (only survivors write their coupling row; this level's readers of it were the eliminated
+                        // stations, before the barrier above)
+#pragma unroll
+                        for (int k = 0; k < 9; ++k) { C[k] = Cn[k]; s.cpl(k)[i] = Cn[k]; }
+                    }
+                    c.sync();
+                }
+                if (tid == 0) {
+                    if (!(A[0] > 0.0)) ok = 0;
+                    double inv[9];
+                    inv3_spd(A, inv);
+                    Ai[0] = inv[0]; Ai[1] = inv[1]; Ai[2] = inv[2]; Ai[3] = inv[4]; Ai[4] = inv[5]; Ai[5] = inv[8];
+                }
+                return !c.any(!ok);
+            };
+
+            // K x = r for the (e_phi, e_y, delta) blocks; r in / x out in registers, x also left in the exchange rows
+            auto kkt_solve = [&](double *r) {
+                for (int l = 0; l < Lv; ++l) {
+                    const int st = 1 << l;
+                    if (live && lev == l) {
+#pragma unroll
+                        for (int cc = 0; cc < 3; ++cc) {
+                            s.push(cc)[i] = GL[cc] * r[0] + GL[3 + cc] * r[1] + GL[6 + cc] * r[2];
+                            s.push(3 + cc)[i] = GR[cc] * r[0] + GR[3 + cc] * r[1] + GR[6 + cc] * r[2];
+                        }
+                    }
+                    c.sync();
+                    if (live && lev > l) {
+                        if (i + st < N) {
+#pragma unroll
+                            for (int cc = 0; cc < 3; ++cc) r[cc] -= s.push(cc)[i + st];
+                        }
+                        if (i > 0) {
+#pragma unroll
+                            for (int cc = 0; cc < 3; ++cc) r[cc] -= s.push(3 + cc)[i - st];
+                        }
+                    }
+                }
+                for (int l = Lv; l >= 0; --l) {
+                    if (live && lev == l) {
+                        double t0 = Ai[0] * r[0] + Ai[1] * r[1] + Ai[2] * r[2];
+                        double t1 = Ai[1] * r[0] + Ai[3] * r[1] + Ai[4] * r[2];
+                        double t2 = Ai[2] * r[0] + Ai[4] * r[1] + Ai[5] * r[2];
+                        if (l < Lv) {
+                            const int st = 1 << l;
+                            const double a0 = s.xr(0)[i - st], a1 = s.xr(1)[i - st], a2 = s.xr(2)[i - st];
+                            t0 -= GL[0] * a0 + GL[1] * a1 + GL[2] * a2;
+                            t1 -= GL[3] * a0 + GL[4] * a1 + GL[5] * a2;
+                            t2 -= GL[6] * a0 + GL[7] * a1 + GL[8] * a2;
+                            if (i + st < N) {
+                                const double b0 = s.xr(0)[i + st], b1 = s.xr(1)[i + st], b2 = s.xr(2)[i + st];
+                                t0 -= GR[0] * b0 + GR[1] * b1 + GR[2] * b2;
+                                t1 -= GR[3] * b0 + GR[4] * b1 + GR[5] * b2;
+                                t2 -= GR[6] * b0 + GR[7] * b1 + GR[8] * b2;
+                            }
+                        }
+                        r[0] = t0; r[1] = t1; r[2] = t2;
+                        s.xr(0)[i] = t0; s.xr(1)[i] = t1; s.xr(2)[i] = t2;
+                    }
+                    c.sync();
+                }
+            };
+
+            if (!factor()) status = PQP_NON_CVX;
+            const double alpha = pm.alpha;
+            double pri_res = 0, dua_res = 0, pri_nrm = 0, dua_nrm = 0;
+            double inf_nrm = 0, inf_lhs = 0, inf_cert = 0;
+            iter = 1;
+            while (status == PQP_UNSOLVED && iter < pm.max_iter) {
+                ++iter;
+                // rhs = sigma x + A' W (2 clamp(v) - v)
+                double z[11], g[11];
+#pragma unroll
+                for (int k = 0; k < 11; ++k) {
+                    z[k] = clamp2(v[k], lo[k], hi[k]);
+                    g[k] = W[k] * (2.0 * z[k] - v[k]);
+                }
+                if (live) { s.gr(0)[i] = g[0]; s.gr(1)[i] = g[1]; }
+                c.sync();
+                double r[4] = {0, 0, 0, 0}, xt[4] = {0, 0, 0, 0};
+                if (live) {
+                    cols_of(g, r);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) r[q] += sg[q] * x[q];
+                    if (!hasd) r[2] = 0.0;
+                }
+                xt[3] = r[3] * inv_e;
+                kkt_solve(r);
+                xt[0] = r[0]; xt[1] = r[1]; xt[2] = r[2];
+                const bool chk = (pm.check_termination && (iter % pm.check_termination == 0)) || iter == pm.max_iter;
+                if (live) {
+                    double ax[11];
+                    rows_of(xt[0], xt[1], xt[2], xt[3], ax);
+#pragma unroll
+                    for (int k = 0; k < 11; ++k) {
+                        if (chk) s.wold(k)[tid] = v[k] - z[k];
+                        v[k] = v[k] + alpha * (ax[k] - z[k]);
+                    }
+                    if (last) v[4] = 0.0;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) x[q] = alpha * xt[q] + (1.0 - alpha) * x[q];
+                }
+                const bool can_check = pm.check_termination && (iter % pm.check_termination == 0);
+                const bool can_adapt = pm.adaptive_rho && pm.adaptive_rho_interval && (iter % pm.adaptive_rho_interval == 0);
+                if (can_check || can_adapt || iter == pm.max_iter) {
+                    c.sync();                        // everybody is done with the x-tilde rows
+                    const double cinv = 1.0 / cost_c;
+                    double yv[11];
+#pragma unroll
+                    for (int k = 0; k < 11; ++k) {
+                        z[k] = clamp2(v[k], lo[k], hi[k]);
+                        yv[k] = W[k] * (v[k] - z[k]) * cinv;
+                    }
+                    if (live) {
+                        s.xr(0)[i] = x[0]; s.xr(1)[i] = x[1]; s.xr(2)[i] = x[2];
+                        s.gr(0)[i] = yv[0]; s.gr(1)[i] = yv[1];
+                    }
+                    c.sync();
+                    double red[12];
+#pragma unroll
+                    for (int k = 0; k < 12; ++k) red[k] = 0.0;
+                    if (live) {
+                        double ax[11];
+                        rows_of(x[0], x[1], x[2], x[3], ax);
+#pragma unroll
+                        for (int k = 0; k < 11; ++k) {
+                            if (k == 4 && last) continue;
+                            const double rr = ax[k] - z[k], e = s.E(k)[tid];
+                            red[0] = fmax(red[0], fabs(rr)); red[1] = fmax(red[1], fabs(z[k])); red[2] = fmax(red[2], fabs(ax[k]));
+                            red[3] = fmax(red[3], e * fabs(rr)); red[4] = fmax(red[4], e * fabs(z[k])); red[5] = fmax(red[5], e * fabs(ax[k]));
+                        }
+                        double aty[4], px[4];
+                        cols_of(yv, aty);
+                        px[0] = Pd[0] * x[0]; px[1] = Pd[1] * x[1]; px[3] = Pd[3] * x[3];
+                        px[2] = Pd[2] * x[2];
+                        if (dprev) px[2] += (-w_cr) * s.xr(2)[i - 1];
+                        if (dnext) px[2] += (-w_cr) * s.xr(2)[i + 1];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            if (q == 2 && !hasd) continue;
+                            const double rr = px[q] + aty[q], cd = cost_c * D[q];
+                            red[6] = fmax(red[6], fabs(rr)); red[7] = fmax(red[7], fabs(px[q])); red[8] = fmax(red[8], fabs(aty[q]));
+                            red[9] = fmax(red[9], cd * fabs(rr)); red[10] = fmax(red[10], cd * fabs(px[q])); red[11] = fmax(red[11], cd * fabs(aty[q]));
+                        }
+                    }
+                    c.max_n(red, 12);
+                    const double pr = red[0], nz = red[1], nax = red[2], prs = red[3], nzs = red[4], naxs = red[5];
+                    const double dr = red[6], npx = red[7], naty = red[8], drs = red[9], npxs = red[10], natys = red[11];
+                    if (chk) {
+                        // primal-infeasibility certificate (OSQP is_primal_infeasible), see pqp_gen_core.cuh
+                        double gq[11], c_nrm = 0, c_lhs = 0, c_cert = 0;
+#pragma unroll
+                        for (int k = 0; k < 11; ++k) {
+                            gq[k] = 0.0;
+                            if (!live || (k == 4 && last)) continue;
+                            const double e = s.E(k)[tid];
+                            double gg = W[k] * ((v[k] - z[k]) - s.wold(k)[tid]);
+                            const bool u_inf = e * hi[k] > kOsqpInfty * kMinScaling;
+                            const bool l_inf = e * lo[k] < -kOsqpInfty * kMinScaling;
+                            if (u_inf) gg = l_inf ? 0.0 : fmin(gg, 0.0);
+                            else if (l_inf) gg = fmax(gg, 0.0);
+                            gq[k] = gg;
+                            c_nrm = fmax(c_nrm, fabs(gg));
+                            c_lhs += hi[k] * fmax(gg, 0.0) + lo[k] * fmin(gg, 0.0);
+                        }
+                        if (live) { s.gr(0)[i] = gq[0]; s.gr(1)[i] = gq[1]; }
+                        c.sync();
+                        if (live) {
+                            double aty[4];
+                            cols_of(gq, aty);
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                if (q == 2 && !hasd) continue;
+                                c_cert = fmax(c_cert, fabs(aty[q]));
+                            }
+                        }
+                        double r2[2] = {c_nrm, c_cert};
+                        c.max_n(r2, 2);
+                        inf_nrm = r2[0]; inf_cert = r2[1];
+                        inf_lhs = c.sum(c_lhs);
+                    }
+                    pri_res = pr; dua_res = dr; pri_nrm = fmax(nz, nax); dua_nrm = fmax(npx, naty);
+                    if (can_check || iter == pm.max_iter) {
+                        const bool prim_ok = pri_res < pm.eps_abs + pm.eps_rel * pri_nrm;
+                        if (pri_res > kOsqpInfty || dua_res > kOsqpInfty) status = PQP_NON_CVX;
+                        else if (prim_ok && dua_res < pm.eps_abs + pm.eps_rel * dua_nrm) status = PQP_SOLVED;
+                        else if (!prim_ok && primal_infeasible(inf_nrm, inf_lhs, inf_cert, pm.eps_prim_inf))
+                            status = PQP_PRIMAL_INFEASIBLE;
+                    }
+                    if (status == PQP_UNSOLVED && can_adapt) {
+                        const double pn = prs / (fmax(nzs, naxs) + 1e-10);
+                        const double dn = drs / (fmax(npxs, natys) + 1e-10);
+                        double rho_new = rho * sqrt(pn / (dn + 1e-10));
+                        rho_new = fmin(fmax(rho_new, kRhoMin), kRhoMax);
+                        if (rho_new > rho * pm.adaptive_rho_tolerance || rho_new < rho / pm.adaptive_rho_tolerance) {
+                            if (live) {
+#pragma unroll
+                                for (int k = 0; k < 11; ++k) {
+                                    if (k == 4 && last) continue;
+                                    const double e = s.E(k)[tid];
+                                    const double El = e * lo[k], Eu = e * hi[k];
+                                    const double ro = rho_bar(El, Eu, rho), rn = rho_bar(El, Eu, rho_new);
+                                    const double zz = clamp2(v[k], lo[k], hi[k]);
+                                    v[k] = zz + (v[k] - zz) * (ro / rn);
+                                    W[k] = rn * e * e;
+                                }
+                            }
+                            rho = rho_new;
+                            if (!factor()) status = PQP_NON_CVX;
+                        }
+                    }
+                }
+            }
+            if (status == PQP_UNSOLVED) {
+                const bool prim_ok = pri_res < 10 * pm.eps_abs + 10 * pm.eps_rel * pri_nrm;
+                if (prim_ok && dua_res < 10 * pm.eps_abs + 10 * pm.eps_rel * dua_nrm) status = PQP_SOLVED_INACCURATE;
+                else if (!prim_ok && primal_infeasible(inf_nrm, inf_lhs, inf_cert, 10 * pm.eps_prim_inf))
+                    status = PQP_PRIMAL_INFEASIBLE;
+                else status = PQP_MAX_ITER_REACHED;
+            }
+        }
+        // ---- epilogue: getOptimizedPath (solver_k_as_input.cpp:22-44)
+        const bool has_sol = (status == PQP_SOLVED || status == PQP_SOLVED_INACCURATE || status == PQP_MAX_ITER_REACHED);
+        c.sync();
+        if (live) s.xr(2)[i] = x[2];
+        c.sync();
+        if (live) {
+            double ey = qnan, ephi = qnan, kk = qnan;
+            if (has_sol) { ey = x[1]; ephi = x[0]; kk = last ? s.xr(2)[i - 1] : x[2]; }
+            const double angle = ref[i].z;
+            const double new_angle = constraint_angle(angle + 1.57079632679489661923);
+            const double tx = ref[i].x + ey * cos(new_angle), ty = ref[i].y + ey * sin(new_angle);
+            out[i].x = tx; out[i].y = ty; out[i].z = angle + ephi; out[i].k = kk; out[i].v = 0.0; out[i].a = 0.0;
+            s.ox()[i] = tx; s.oy()[i] = ty;
+            if (bv.out_frenet) {
+                double *f = bv.out_frenet + 3 * (size_t)(off + i);
+                f[0] = ey; f[1] = ephi; f[2] = kk;
+            }
+        }
+        c.sync();
+        if (tid == 0) {
+            double acc = 0.0;
+            for (int k = 0; k < N; ++k) {
+                if (k > 0) {
+                    const double dx = s.ox()[k] - s.ox()[k - 1], dy = s.oy()[k] - s.oy()[k - 1];
+                    acc += sqrt(dx * dx + dy * dy);
+                }
+                out[k].s = acc;
+            }
+            bv.status[prob] = status;
+            if (bv.iters) bv.iters[prob] = iter;
+        }
+    }
+};
+
+}  // namespace pqp

@@ -8,6 +8,7 @@
 #include <string.h>
 
 #include "../../path_optimizer_b200/csrc/pqp_kp_core3.cuh"
+#include "../../path_optimizer_b200/csrc/pqp_kk_core.cuh"
 
 namespace {
 struct LaneArgs {
@@ -40,6 +41,9 @@ void *lane_main(void *p) {
     case 20: pqp::Kp3<23, 7, 4, 17, 2>::solve_path(c, *a->prm, *a->bv, a->prob, sm, cap); break;    // "KPC" classes
     case 21: pqp::Kp3<23, 7, 8, 34, 2>::solve_path(c, *a->prm, *a->bv, a->prob, sm, cap); break;
     case 22: pqp::Kp3<13, 7, 8, 34, 2>::solve_path(c, *a->prm, *a->bv, a->prob, sm, cap); break;
+    case 30: pqp::Kk<4>::solve_path(c, *a->prm, *a->bv, a->prob, sm, cap); break;                      // "K" classes
+    case 31: pqp::Kk<8>::solve_path(c, *a->prm, *a->bv, a->prob, sm, cap); break;
+    case 32: pqp::Kk<13>::solve_path(c, *a->prm, *a->bv, a->prob, sm, cap); break;
     default: pqp::kp_solve_path(w, *a->prm, *a->bv, a->prob, sm, cap);   // generic core: one warp
     }
     return nullptr;
@@ -62,6 +66,9 @@ extern "C" int kp_emu_solve_batch(const pqp_params *params, int batch, const int
     if (variant == 12) nwarps = 10;
     if (variant == 20) nwarps = 4;
     if (variant == 21 || variant == 22) nwarps = 8;
+    if (variant == 30) nwarps = 4;
+    if (variant == 31) nwarps = 8;
+    if (variant == 32) nwarps = 13;
     pqp::DevParams prm = pqp::dev_params_from(*params);
     pqp::BatchView bv;
     bv.batch = batch; bv.n_points = n_points; bv.offsets = offsets; bv.ref = ref; bv.bounds = bounds;

@@ -212,3 +212,52 @@ def test_emu_kpc_infeasible_and_parameters(oracle_params):
     o = oracle.solve_batch(p, 2, b, threads=4, max_k=mk, max_kp=mkp)
     assert np.array_equal(e["status"], o["status"]) and np.array_equal(e["iters"], o["iters"])
     np.testing.assert_allclose(e["frenet"], o["frenet"], rtol=0, atol=TOL)
+
+
+def _check_k(batch, params, variant):
+    e = emu.solve_batch(params, batch, variant=variant)
+    o = oracle.solve_batch(params, 1, batch, threads=4)
+    assert np.array_equal(e["status"], o["status"]) and np.array_equal(e["iters"], o["iters"])
+    np.testing.assert_allclose(e["frenet"], o["frenet"], rtol=0, atol=TOL)
+    for f in "xyzks":
+        np.testing.assert_allclose(e["states"][f], o["states"][f], rtol=0, atol=TOL)
+    return o
+
+
+@pytest.mark.parametrize("variant,n_points", [(30, [2, 3, 5, 33, 100]), (31, [129]), (32, [416])])
+def test_emu_k_thread_per_station(oracle_params, variant, n_points):
+    """"K" (SolverKAsInput) on its thread-per-station kernel (pqp_kk_core.cuh: stencils in registers, block cyclic
+    reduction for the reduced KKT): same status, iteration count and iterates as the oracle's restatement of
+    solver_k_as_input.cpp, at every tree depth of the reduction (2 .. 416 stations) and for both corridor kinds."""
+    p = oracle_params.copy()
+    if variant == 32:
+        p.max_iter = 150     # (416 host threads per barrier: keep the emulated run short; both sides stop at max_iter)
+    o = _check_k(synth.curvy_corridors(len(n_points), n_points=n_points), p, variant)
+    assert (o["status"] == (1 if variant != 32 else -2)).all()
+    if variant == 30:
+        _check_k(synth.straight_corridors(1, 64), oracle_params, variant)
+
+
+def test_emu_k_infeasible_and_parameters(oracle_params):
+    # (eps_prim_inf 1e-2 lets the certificate fire after 325 iterations instead of 1875: same code path, a fifth of the
+    # emulated barriers; the default tolerance runs on the GPU, test_gpu_parity.py::test_k_thread_per_station_classes)
+    p = oracle_params.copy()
+    p.eps_prim_inf = 1e-2
+    b = synth.infeasible_corridors(2, 40)
+    o = _check_k(b, p, 30)
+    assert o["status"][0] == -3 and o["status"][1] == 1 and o["iters"][0] < 1000
+    for case in ("adaptive_off_maxiter", "check7_interval35", "scaling0_rho1", "check0"):
+        p = oracle_params.copy()
+        for k, v in PARAM_CASES[case].items():
+            setattr(p, k, v)
+        _check_k(synth.curvy_corridors(1, n_points=[24]), p, 30)
+    p = oracle_params.copy()
+    p.constraint_end_heading = 0; p.K_curvature_weight = 7.0; p.K_curvature_rate_weight = 60.0
+    p.K_deviation_weight = 0.4; p.KP_slack_weight = 10.0; p.max_steering_angle = 0.2
+    _check_k(synth.curvy_corridors(1, n_points=[40]), p, 30)
+    # an invalid corridor (lower bound above the upper bound): OSQP's setup refuses it
+    b = synth.curvy_corridors(2, n_points=[30, 30])
+    b["bounds"]["c0_lb"][10] = b["bounds"]["c0_ub"][10] + 1.0
+    e = emu.solve_batch(oracle_params, b, variant=30)
+    o = oracle.solve_batch(oracle_params, 1, b)
+    assert np.array_equal(e["status"], o["status"]) and e["status"][0] == -100 and e["status"][1] == 1

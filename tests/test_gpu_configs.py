@@ -225,7 +225,7 @@ def test_kpc_thread_per_station_classes_and_fallback(oracle_params):
     r2 = s.solve(b2, formulation="KPC", max_k=mk2, max_kp=mkp2)
     o2 = oracle.solve_batch(oracle_params, 2, b2, threads=4, max_k=mk2, max_kp=mkp2)
     assert r2["status"][1] == -100 and np.isnan(r2["frenet"][40:340]).all()
-    assert L.pqp_max_points_keep(s._h, 2, 4) == 256 and s.max_points("KPC") == 256 and s.max_points("K") == 0
+    assert L.pqp_max_points_keep(s._h, 2, 4) == 256 and s.max_points("KPC") == 256 and s.max_points("K") == 416
     keep = np.array([0, 2])
     assert np.array_equal(r2["status"][keep], o2["status"][keep]) and np.array_equal(r2["iters"][keep], o2["iters"][keep])
     np.testing.assert_allclose(r2["frenet"][:40], o2["frenet"][:40], rtol=0, atol=TOL)
@@ -252,3 +252,95 @@ def test_kpc_plan_chain(oracle_params):
     for f in "xyzks":
         np.testing.assert_allclose(r["states"][f], o["states"][f], rtol=0, atol=TOL)
     s.close()
+
+
+def test_k_thread_per_station_classes_and_plan(oracle_params):
+    """"K" (SolverKAsInput) runs on its own thread-per-station classes (pqp_kk_core.cuh: 4 / 8 / 13 warps, up to 416
+    stations, block cyclic reduction), assembled in the kernel: every length class and an infeasible corridor against the
+    oracle; the device entry gives the same bits as the host-buffer one; a longer path is PQP_INVALID_PROBLEM for itself;
+    the solveWithoutSmoothing chain takes "K" too."""
+    import torch
+    from path_optimizer_b200 import _lib
+    L = _lib.load()
+    v, t, sm = C.c_int(), C.c_int(), C.c_int64()
+    assert L.pqp_class_info_form(1, 100, 0, 0, C.byref(v), C.byref(t), C.byref(sm)) == 0 and t.value == 128
+    assert L.pqp_class_name(v.value).decode() == "pqp_kk_solve_kernel<4>"
+    assert L.pqp_class_info_form(1, 200, 0, 0, C.byref(v), C.byref(t), C.byref(sm)) == 0 and t.value == 256
+    assert L.pqp_class_info_form(1, 416, 0, 0, C.byref(v), C.byref(t), C.byref(sm)) == 0 and t.value == 416
+    assert L.pqp_class_info_form(1, 417, 0, 0, C.byref(v), C.byref(t), C.byref(sm)) != 0
+    rng = np.random.default_rng(9)
+    n_points = rng.integers(2, 417, size=96)
+    n_points[:8] = [2, 3, 4, 128, 129, 256, 257, 416]
+    batch = synth.curvy_corridors(96, n_points=n_points)
+    total = int(batch["offsets"][-1])
+    s = _solver(96, total)
+    assert s.max_points("K") == 416
+    res = s.solve(batch, formulation="K")
+    assert res["stats"].kernel_launches == 3
+    ref = oracle.solve_batch(oracle_params, 1, batch, threads=8)
+    assert np.array_equal(res["status"], ref["status"]) and np.array_equal(res["iters"], ref["iters"])
+    assert (ref["status"] == SOLVED).sum() >= 90
+    np.testing.assert_allclose(res["frenet"], ref["frenet"], rtol=0, atol=TOL)
+    for f in "xyzks":
+        np.testing.assert_allclose(res["states"][f], ref["states"][f], rtol=0, atol=TOL)
+    # device-resident entry == host-buffer entry
+    dev = torch.device("cuda", 0)
+
+    def up(a):
+        return torch.from_numpy(np.frombuffer(np.ascontiguousarray(a).tobytes(), dtype=np.uint8).copy()).to(dev)
+    d_n, d_off, d_ref, d_bnd = up(batch["n_points"]), up(batch["offsets"]), up(batch["ref"]), up(batch["bounds"])
+    d_x0, d_end = up(batch["x0"]), up(batch["end_heading"])
+    d_out = torch.zeros(total * STATE_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+    d_fr = torch.zeros(total * 3, dtype=torch.float64, device=dev)
+    d_st = torch.zeros(96, dtype=torch.int32, device=dev)
+    d_it = torch.zeros(96, dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()
+    hn = np.ascontiguousarray(batch["n_points"], dtype=np.int32)
+    rc = L.pqp_solve_batch_device_classes(s._h, 1, 96, total, hn.ctypes.data_as(C.c_void_p), None, d_n.data_ptr(),
+                                          d_off.data_ptr(), d_ref.data_ptr(), d_bnd.data_ptr(), d_x0.data_ptr(), d_end.data_ptr(),
+                                          None, None, d_out.data_ptr(), d_fr.data_ptr(), d_st.data_ptr(), d_it.data_ptr(), None, None)
+    assert rc == 0, _lib.last_error()
+    torch.cuda.synchronize()
+    assert np.array_equal(d_st.cpu().numpy(), res["status"]) and np.array_equal(d_it.cpu().numpy(), res["iters"])
+    assert np.array_equal(d_fr.cpu().numpy().reshape(-1, 3), res["frenet"], equal_nan=True)
+    # one class for a whole device batch from the caller's bound
+    d_st.zero_()
+    rc = L.pqp_solve_batch_device(s._h, 1, 96, total, 416, 0, 0, d_n.data_ptr(), d_off.data_ptr(), d_ref.data_ptr(), d_bnd.data_ptr(),
+                                  d_x0.data_ptr(), d_end.data_ptr(), None, None, d_out.data_ptr(), d_fr.data_ptr(), d_st.data_ptr(),
+                                  d_it.data_ptr(), None, None)
+    assert rc == 0, _lib.last_error()
+    torch.cuda.synchronize()
+    assert np.array_equal(d_st.cpu().numpy(), res["status"]) and np.array_equal(d_it.cpu().numpy(), res["iters"])
+    # infeasible corridors (default eps_prim_inf) and a path beyond the largest class
+    b2 = synth.infeasible_corridors(8, 50)
+    r2 = s.solve(b2, formulation="K")
+    o2 = oracle.solve_batch(oracle_params, 1, b2, threads=8)
+    assert np.array_equal(r2["status"], o2["status"]) and np.array_equal(r2["iters"], o2["iters"])
+    assert (o2["status"][0::2] == -3).all() and np.isnan(r2["frenet"][:50]).all()
+    s.close()
+    n3 = np.array([40, 450, 100], dtype=np.int32)
+    b3 = synth.curvy_corridors(3, n_points=n3)
+    s3 = _solver(3, 590)
+    r3 = s3.solve(b3, formulation="K")
+    o3 = oracle.solve_batch(oracle_params, 1, b3, threads=4)
+    assert r3["status"][1] == -100 and np.isnan(r3["frenet"][40:490]).all()
+    keep = np.array([0, 2])
+    assert np.array_equal(r3["status"][keep], o3["status"][keep]) and np.array_equal(r3["iters"][keep], o3["iters"][keep])
+    np.testing.assert_allclose(r3["frenet"][:40], o3["frenet"][:40], rtol=0, atol=TOL)
+    np.testing.assert_allclose(r3["frenet"][490:], o3["frenet"][490:], rtol=0, atol=TOL)
+    s3.close()
+    # the planner chain with optimization_method "K"
+    field = synth.disc_field_map()
+    b = synth.map_reference_paths(24, 150)
+    sp = _solver(24, int(b["offsets"][-1]))
+    sp.set_map(field)
+    r = sp.plan(b, formulation="K")
+    o = oracle.plan(oracle_params, field, b, formulation=1)
+    assert np.array_equal(r["status"], o["status"]) and np.array_equal(r["iters"], o["iters"])
+    assert np.array_equal(r["ok"], o["ok"]) and np.array_equal(r["n_out"], o["n_out"])
+    assert (o["status"] == SOLVED).sum() >= 12
+    for i in range(24):     # the kept part of every path (what solveWithoutSmoothing returns)
+        lo_, k = int(b["offsets"][i]), int(o["n_out"][i])
+        for f in "xyzks":
+            np.testing.assert_allclose(r["states"][f][lo_:lo_ + k], o["states"][f][lo_:lo_ + k], rtol=0, atol=TOL)
+    sp.close()
