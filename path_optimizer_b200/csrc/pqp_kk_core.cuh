@@ -28,6 +28,10 @@
 #pragma once
 #include "pqp_kp_core.cuh"
 
+#ifndef PQP_KK_G_SMEM
+#define PQP_KK_G_SMEM 0     // 1: G_L / G_R are read from their shared-memory rows in every solve instead of living in registers (measured slower: 13.5 vs 12.0 ms per 1024 x 100)
+#endif
+
 namespace pqp {
 
 template <int NW>
@@ -36,8 +40,8 @@ struct Kk {
     static constexpr int kP = kT + 2;             // pitch of the exchange rows: entry 0 = "station -1", entry N+1 = "station N" (zeros)
     static constexpr int kCtaScratch = (NW <= 8) ? 128 : 256;
     // shared memory (doubles): 3 x-rows + 2 dual rows + 2 weight rows + 1 delta-scale row (pitch kP); 6 push rows, 9 coupling
-    // rows, 18 G rows, 11 parked-dual rows, 11 E rows, 2 output rows (pitch kT)
-    static constexpr int kXRows = 8, kTRows = 6 + 9 + 18 + 11 + 11 + 2;
+    // rows, 18 G rows, 11 parked-dual rows, 11 E rows, 2 output rows, 1 row of pushes that cross a warp boundary (pitch kT)
+    static constexpr int kXRows = 8, kTRows = 6 + 9 + 18 + 11 + 11 + 2 + 1;
     PQP_HD static size_t smem_doubles(int /*N*/) { return (size_t)kXRows * kP + (size_t)kTRows * kT; }
     PQP_HD static bool fits(int N, int /*keep*/) { return N >= 2 && N <= kT; }
 
@@ -56,6 +60,7 @@ struct Kk {
         PQP_DEV double *E(int k) const { return t(44 + k); }
         PQP_DEV double *ox() const { return t(55); }
         PQP_DEV double *oy() const { return t(56); }
+        PQP_DEV double *bp() const { return t(57); }                          // [level < 5][warp][3]
     };
 
     // 3 x 3 helpers (row-major)
@@ -376,36 +381,101 @@ struct Kk {
                 return !c.any(!ok);
             };
 
-            // K x = r for the (e_phi, e_y, delta) blocks; r in / x out in registers, x also left in the exchange rows
+            // K x = r for the (e_phi, e_y, delta) blocks; r in / x out in registers, x also left in the exchange rows.
+            // Levels 0..4 (strides < 32) stay inside a warp: pushes and x travel by shuffles, no barrier; the one push per
+            // level that crosses into the next warp (lane 32 - st -> lane 0 of the next warp) is parked in shared memory
+            // and collected after the first barrier, and x of the next warp's lane 0 is read from its exchange row.
+            // Levels >= 5 (the stations 32 w) go through shared memory, one barrier per level.
+            const int lane = c.lane(), wid = c.wid;
+            constexpr int kLoc = 5;
+            const int Ll = Lv < kLoc ? Lv : kLoc;
             auto kkt_solve = [&](double *r) {
-                for (int l = 0; l < Lv; ++l) {
-                    const int st = 1 << l;
-                    if (live && lev == l) {
+#pragma unroll
+                for (int l = 0; l < kLoc; ++l) {
+                    if (l < Ll) {
+                        const int st = 1 << l;
+                        const bool el = live && lev == l;
+                        double pl[3] = {0.0, 0.0, 0.0}, pr[3] = {0.0, 0.0, 0.0};
+                        if (el) {
+#if PQP_KK_G_SMEM
+                            double GL[9], GR[9];
+#pragma unroll
+                            for (int k = 0; k < 9; ++k) { GL[k] = s.gl(k)[i]; GR[k] = s.gR(k)[i]; }
+#endif
+#pragma unroll
+                            for (int cc = 0; cc < 3; ++cc) {
+                                pl[cc] = GL[cc] * r[0] + GL[3 + cc] * r[1] + GL[6 + cc] * r[2];
+                                pr[cc] = GR[cc] * r[0] + GR[3 + cc] * r[1] + GR[6 + cc] * r[2];
+                            }
+                            if (lane + st == 32) {
+#pragma unroll
+                                for (int cc = 0; cc < 3; ++cc) s.bp()[(l * NW + wid) * 3 + cc] = pr[cc];
+                            }
+                        }
+                        double fl[3], fr[3];
 #pragma unroll
                         for (int cc = 0; cc < 3; ++cc) {
-                            s.push(cc)[i] = GL[cc] * r[0] + GL[3 + cc] * r[1] + GL[6 + cc] * r[2];
-                            s.push(3 + cc)[i] = GR[cc] * r[0] + GR[3 + cc] * r[1] + GR[6 + cc] * r[2];
+                            fl[cc] = c.w.shfl(pl[cc], lane + st);      // what the station st to my right pushes left
+                            fr[cc] = c.w.shfl(pr[cc], lane - st);      // what the station st to my left pushes right
                         }
-                    }
-                    c.sync();
-                    if (live && lev > l) {
-                        if (i + st < N) {
+                        if (live && lev > l) {
 #pragma unroll
-                            for (int cc = 0; cc < 3; ++cc) r[cc] -= s.push(cc)[i + st];
-                        }
-                        if (i > 0) {
+                            for (int cc = 0; cc < 3; ++cc) r[cc] -= fl[cc];
+                            if (lane > 0) {
 #pragma unroll
-                            for (int cc = 0; cc < 3; ++cc) r[cc] -= s.push(3 + cc)[i - st];
+                                for (int cc = 0; cc < 3; ++cc) r[cc] -= fr[cc];
+                            }
                         }
                     }
                 }
-                for (int l = Lv; l >= 0; --l) {
+                if (Lv > kLoc) {
+                    c.sync();
+                    if (live && lane == 0 && wid > 0) {
+#pragma unroll
+                        for (int l = 0; l < kLoc; ++l)
+#pragma unroll
+                            for (int cc = 0; cc < 3; ++cc) r[cc] -= s.bp()[(l * NW + wid - 1) * 3 + cc];
+                    }
+                    for (int l = kLoc; l < Lv; ++l) {
+                        const int st = 1 << l;
+                        if (live && lev == l) {
+#if PQP_KK_G_SMEM
+                            double GL[9], GR[9];
+#pragma unroll
+                            for (int k = 0; k < 9; ++k) { GL[k] = s.gl(k)[i]; GR[k] = s.gR(k)[i]; }
+#endif
+#pragma unroll
+                            for (int cc = 0; cc < 3; ++cc) {
+                                s.push(cc)[i] = GL[cc] * r[0] + GL[3 + cc] * r[1] + GL[6 + cc] * r[2];
+                                s.push(3 + cc)[i] = GR[cc] * r[0] + GR[3 + cc] * r[1] + GR[6 + cc] * r[2];
+                            }
+                        }
+                        c.sync();
+                        if (live && lev > l) {
+                            if (i + st < N) {
+#pragma unroll
+                                for (int cc = 0; cc < 3; ++cc) r[cc] -= s.push(cc)[i + st];
+                            }
+                            if (i > 0) {
+#pragma unroll
+                                for (int cc = 0; cc < 3; ++cc) r[cc] -= s.push(3 + cc)[i - st];
+                            }
+                        }
+                    }
+                }
+                // up: the stations 32 w (and station 0) through shared memory ...
+                for (int l = Lv; l >= kLoc || l == Lv; --l) {
                     if (live && lev == l) {
                         double t0 = Ai[0] * r[0] + Ai[1] * r[1] + Ai[2] * r[2];
                         double t1 = Ai[1] * r[0] + Ai[3] * r[1] + Ai[4] * r[2];
                         double t2 = Ai[2] * r[0] + Ai[4] * r[1] + Ai[5] * r[2];
                         if (l < Lv) {
                             const int st = 1 << l;
+#if PQP_KK_G_SMEM
+                            double GL[9], GR[9];
+#pragma unroll
+                            for (int k = 0; k < 9; ++k) { GL[k] = s.gl(k)[i]; GR[k] = s.gR(k)[i]; }
+#endif
                             const double a0 = s.xr(0)[i - st], a1 = s.xr(1)[i - st], a2 = s.xr(2)[i - st];
                             t0 -= GL[0] * a0 + GL[1] * a1 + GL[2] * a2;
                             t1 -= GL[3] * a0 + GL[4] * a1 + GL[5] * a2;
@@ -420,8 +490,47 @@ struct Kk {
                         r[0] = t0; r[1] = t1; r[2] = t2;
                         s.xr(0)[i] = t0; s.xr(1)[i] = t1; s.xr(2)[i] = t2;
                     }
-                    c.sync();
+                    if (Lv > kLoc) c.sync();
+                    if (l == 0) break;
                 }
+                // ... then down the warp-local levels with shuffles
+#pragma unroll
+                for (int l = kLoc - 1; l >= 0; --l) {
+                    if (l < Ll) {
+                        const int st = 1 << l;
+                        double xa[3], xb[3];
+#pragma unroll
+                        for (int cc = 0; cc < 3; ++cc) {
+                            xa[cc] = c.w.shfl(r[cc], lane - st);
+                            xb[cc] = c.w.shfl(r[cc], lane + st);
+                        }
+                        if (live && lev == l) {
+                            if (lane + st == 32) {      // right neighbour = lane 0 of the next warp
+#pragma unroll
+                                for (int cc = 0; cc < 3; ++cc) xb[cc] = (i + st < N) ? s.xr(cc)[i + st] : 0.0;
+                            }
+#if PQP_KK_G_SMEM
+                            double GL[9], GR[9];
+#pragma unroll
+                            for (int k = 0; k < 9; ++k) { GL[k] = s.gl(k)[i]; GR[k] = s.gR(k)[i]; }
+#endif
+                            double t0 = Ai[0] * r[0] + Ai[1] * r[1] + Ai[2] * r[2];
+                            double t1 = Ai[1] * r[0] + Ai[3] * r[1] + Ai[4] * r[2];
+                            double t2 = Ai[2] * r[0] + Ai[4] * r[1] + Ai[5] * r[2];
+                            t0 -= GL[0] * xa[0] + GL[1] * xa[1] + GL[2] * xa[2];
+                            t1 -= GL[3] * xa[0] + GL[4] * xa[1] + GL[5] * xa[2];
+                            t2 -= GL[6] * xa[0] + GL[7] * xa[1] + GL[8] * xa[2];
+                            if (i + st < N) {
+                                t0 -= GR[0] * xb[0] + GR[1] * xb[1] + GR[2] * xb[2];
+                                t1 -= GR[3] * xb[0] + GR[4] * xb[1] + GR[5] * xb[2];
+                                t2 -= GR[6] * xb[0] + GR[7] * xb[1] + GR[8] * xb[2];
+                            }
+                            r[0] = t0; r[1] = t1; r[2] = t2;
+                        }
+                    }
+                }
+                if (live) { s.xr(0)[i] = r[0]; s.xr(1)[i] = r[1]; s.xr(2)[i] = r[2]; }
+                c.sync();
             };
 
             if (!factor()) status = PQP_NON_CVX;
@@ -429,8 +538,15 @@ struct Kk {
             double pri_res = 0, dua_res = 0, pri_nrm = 0, dua_nrm = 0;
             double inf_nrm = 0, inf_lhs = 0, inf_cert = 0;
             iter = 1;
+            // (iter % interval == 0 without a division per iteration: the next multiple is tracked)
+            const int ct = pm.check_termination, ai = (pm.adaptive_rho ? pm.adaptive_rho_interval : 0);
+            int next_chk = ct == 1 ? 2 : ct, next_ad = ai == 1 ? 2 : ai;
             while (status == PQP_UNSOLVED && iter < pm.max_iter) {
                 ++iter;
+                const bool can_check = ct > 0 && iter == next_chk;
+                const bool can_adapt = ai > 0 && iter == next_ad;
+                if (can_check) next_chk += ct;
+                if (can_adapt) next_ad += ai;
                 // rhs = sigma x + A' W (2 clamp(v) - v)
                 double z[11], g[11];
 #pragma unroll
@@ -450,7 +566,7 @@ struct Kk {
                 xt[3] = r[3] * inv_e;
                 kkt_solve(r);
                 xt[0] = r[0]; xt[1] = r[1]; xt[2] = r[2];
-                const bool chk = (pm.check_termination && (iter % pm.check_termination == 0)) || iter == pm.max_iter;
+                const bool chk = can_check || iter == pm.max_iter;
                 if (live) {
                     double ax[11];
                     rows_of(xt[0], xt[1], xt[2], xt[3], ax);
@@ -463,8 +579,6 @@ struct Kk {
 #pragma unroll
                     for (int q = 0; q < 4; ++q) x[q] = alpha * xt[q] + (1.0 - alpha) * x[q];
                 }
-                const bool can_check = pm.check_termination && (iter % pm.check_termination == 0);
-                const bool can_adapt = pm.adaptive_rho && pm.adaptive_rho_interval && (iter % pm.adaptive_rho_interval == 0);
                 if (can_check || can_adapt || iter == pm.max_iter) {
                     c.sync();                        // everybody is done with the x-tilde rows
                     const double cinv = 1.0 / cost_c;

@@ -3,9 +3,10 @@
 #include "pqp_kernels.h"
 #include "pqp_kk_core.cuh"
 
-#ifndef PQP_KK_MINBLOCKS
-#define PQP_KK_MINBLOCKS(NW) ((NW) <= 4 ? 2 : 1)
+#ifndef PQP_KK_MINBLOCKS4
+#define PQP_KK_MINBLOCKS4 2      // resident CTAs per SM the four-warp class is compiled for (register cap 255 / 168 / 128)
 #endif
+#define PQP_KK_MINBLOCKS(NW) ((NW) <= 4 ? PQP_KK_MINBLOCKS4 : 1)
 template <int NW>
 __global__ void __launch_bounds__(NW * 32, PQP_KK_MINBLOCKS(NW))
 pqp_kk_solve_kernel(const __grid_constant__ pqp::DevParams prm, const __grid_constant__ pqp::BatchView bv,
