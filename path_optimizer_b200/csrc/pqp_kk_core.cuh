@@ -42,11 +42,41 @@ struct Kk {
     // shared memory (doubles): 3 x-rows + 2 dual rows + 2 weight rows + 1 delta-scale row (pitch kP); 6 push rows, 9 coupling
     // rows, 18 G rows, 11 parked-dual rows, 11 E rows, 2 output rows, 1 row of pushes that cross a warp boundary (pitch kT)
     static constexpr int kXRows = 8, kTRows = 6 + 9 + 18 + 11 + 11 + 2 + 1;
-    PQP_HD static size_t smem_doubles(int /*N*/) { return (size_t)kXRows * kP + (size_t)kTRows * kT; }
+    // The four-warp class (N <= 128, the BASELINE shapes) solves the reduced KKT in SPIKE form instead (see factor_spike):
+    // separators every L stations (at most kMS of them), dense interior inverses, a dense inverse of the separator system.
+    static constexpr bool kSpike = (NW == 4);
+    static constexpr int kMS = 26;                 // most separators
+    static constexpr int kIM = 12;                 // most interior unknowns of a chunk (L <= 5)
+    static constexpr int kKP = 13;                 // row pitch of an interior inverse
+    static constexpr int kKC = kIM * kKP + 3;      // chunk stride (odd: chunks start on different banks)
+    static constexpr int kSpRows = 7;              // rhs (3), y (3), separator rhs (1); the Schur scratch of a factorisation overlays them
+    static constexpr int kSpScratch = 4500;        // doubles a factorisation needs in the (later) separator-inverse region
+    struct SpDims { int L, M, pitch; size_t reg; };
+    PQP_HD static SpDims sp_dims(int N) {
+        SpDims d;
+        d.L = (N + kMS - 1) / kMS;
+        if (d.L < 2) d.L = 2;
+        d.M = (N - 1) / d.L + 1;
+        int pch = 3 * d.M;
+        pch += (pch & 1);
+        if ((pch & 3) == 0) pch += 2;              // even (128-bit loads), = 2 mod 4 (rows of neighbouring threads on different banks)
+        d.pitch = pch;
+        d.reg = (size_t)pch * 3 * d.M;
+        if (d.reg < (size_t)kSpScratch) d.reg = kSpScratch;
+        return d;
+    }
+    PQP_HD static size_t smem_doubles(int N) {
+        if (kSpike) {
+            const SpDims d = sp_dims(N < 2 ? 2 : N);
+            return (size_t)kXRows * kP + (size_t)kSpRows * kT + (size_t)((d.M * kKC + 1) & ~1) + d.reg;
+        }
+        return (size_t)kXRows * kP + (size_t)kTRows * kT;
+    }
     PQP_HD static bool fits(int N, int /*keep*/) { return N >= 2 && N <= kT; }
 
     struct Sm {
         double *b;
+        int M;                                                                // (SPIKE form: separators)
         PQP_DEV double *xr(int c) const { return b + c * kP + 1; }            // c: 0 e_phi, 1 e_y, 2 delta; index i in [-1, N]
         PQP_DEV double *gr(int c) const { return b + (3 + c) * kP + 1; }      // dual-like values of rows 0 / 1
         PQP_DEV double *wr(int c) const { return b + (5 + c) * kP + 1; }      // W (or E) of rows 0 / 1
@@ -58,11 +88,27 @@ struct Kk {
         PQP_DEV double *gR(int k) const { return t(24 + k); }
         PQP_DEV double *wold(int k) const { return t(33 + k); }
         PQP_DEV double *E(int k) const { return t(44 + k); }
-        PQP_DEV double *ox() const { return t(55); }
-        PQP_DEV double *oy() const { return t(56); }
+        PQP_DEV double *ox() const { return t(kSpike ? 0 : 55); }
+        PQP_DEV double *oy() const { return t(kSpike ? 1 : 56); }
+        // SPIKE form
+        PQP_DEV double *rr(int c) const { return t(c); }                      // rhs per station
+        PQP_DEV double *yy(int c) const { return t(3 + c); }                  // K_I^-1 r_I per station
+        PQP_DEV double *gg() const { return t(6); }                           // separator rhs [3M], zero up to the pitch
+        PQP_DEV double *sch() const { return t(0); }                          // Schur blocks [M][27] while a factorisation runs
+        PQP_DEV double *kinv() const { return t(kSpRows); }                   // [M][kKC]
+        PQP_DEV double *sinv() const { return t(kSpRows) + (size_t)((M * kKC + 1) & ~1); } // [3M][pitch]; factor scratch before it is written
         PQP_DEV double *bp() const { return t(57); }                          // [level < 5][warp][3]
     };
 
+    // two consecutive doubles from a 16-byte aligned shared-memory address
+    PQP_DEV static void ld2(const double *q, double &a, double &b) {
+#ifdef PQP_HOST_EMU
+        a = q[0]; b = q[1];
+#else
+        const double2 t = *reinterpret_cast<const double2 *>(q);
+        a = t.x; b = t.y;
+#endif
+    }
     // 3 x 3 helpers (row-major)
     PQP_DEV static void mm(const double *a, const double *b, double *o) {          // o = a b
 #pragma unroll
@@ -86,7 +132,7 @@ struct Kk {
         const pqp_station_bounds *bnd = bv.bounds + off;
         pqp_state *out = bv.out_states + off;
         const double qnan = nan("");
-        if (!fits(N, 1) || smem_doubles(N) > smem_cap) {
+        if (!fits(N, 1) || smem_doubles(N) > smem_cap || (kSpike && !bv.workspace)) {
             if (tid == 0) {
                 bv.status[prob] = PQP_INVALID_PROBLEM;
                 if (bv.iters) bv.iters[prob] = 0;
@@ -101,7 +147,13 @@ struct Kk {
             }
             return;
         }
-        Sm s{smem};
+        const SpDims sd = sp_dims(N);
+        Sm s{smem, sd.M};
+        // scalings E and the parked duals of the last check: shared memory, or (SPIKE form: no room) the path's slice of
+        // the global workspace -- both only touched at termination checks
+        double *const ews = kSpike ? kp_ws_base(bv.workspace, off, prob) : nullptr;
+        auto Ek = [&](int k) -> double * { return kSpike ? ews + (size_t)k * N : s.E(k); };
+        auto Wk = [&](int k) -> double * { return kSpike ? ews + (size_t)(11 + k) * N : s.wold(k); };
         const int i = tid;
         const bool live = i < N, first = (i == 0), last = (i == N - 1);
         const bool hasd = live && !last;                 // delta_i exists
@@ -273,7 +325,7 @@ struct Kk {
 #pragma unroll
             for (int k = 0; k < 11; ++k) {
                 W[k] = rho_bar(E[k] * lo[k], E[k] * hi[k], rho) * E[k] * E[k];
-                s.E(k)[tid] = E[k];
+                if (live) Ek(k)[tid] = E[k];
             }
             if (!live || last) W[4] = 0.0;               // no delta at the last station: the row does not exist
             if (!live) {
@@ -286,11 +338,10 @@ struct Kk {
 #pragma unroll
             for (int k = 0; k < 9; ++k) GL[k] = GR[k] = 0.0;
 
-            auto factor = [&]() -> int {
-                int ok = 1;
+            // my diagonal block A = K[i, i] and the coupling C = K[i, i+1] of the reduced KKT (block tridiagonal by station)
+            auto blocks = [&](double *A, double *C) {
                 if (live) { s.wr(0)[i] = W[0]; s.wr(1)[i] = W[1]; }
                 c.sync();
-                double A[9], C[9];
 #pragma unroll
                 for (int k = 0; k < 9; ++k) { A[k] = 0.0; C[k] = 0.0; }
                 A[0] = A[4] = A[8] = 1.0;
@@ -313,6 +364,15 @@ struct Kk {
                         if (dnext) C[8] = cost_c * (-w_cr);
                     }
                     inv_e = 1.0 / (cost_c * Pd[3] + sg[3] + W[5] + W[9] + W[10]);
+                }
+            };
+
+            // ---- block cyclic reduction (classes of more than four warps) ----
+            auto factor_cr = [&]() -> int {
+                int ok = 1;
+                double A[9], C[9];
+                blocks(A, C);
+                if (live) {
 #pragma unroll
                     for (int k = 0; k < 9; ++k) s.cpl(k)[i] = C[k];
                 }
@@ -389,7 +449,7 @@ struct Kk {
             const int lane = c.lane(), wid = c.wid;
             constexpr int kLoc = 5;
             const int Ll = Lv < kLoc ? Lv : kLoc;
-            auto kkt_solve = [&](double *r) {
+            auto solve_cr = [&](double *r) {
 #pragma unroll
                 for (int l = 0; l < kLoc; ++l) {
                     if (l < Ll) {
@@ -533,6 +593,311 @@ struct Kk {
                 c.sync();
             };
 
+
+            // ---- SPIKE form (four-warp class) --------------------------------------------------------------------------
+            // Separator p = station p L (3 unknowns), chunk p = the L - 1 stations after it (I <= 12 unknowns, block
+            // tridiagonal K_I).  Per factorisation: the first interior thread of a chunk factors K_I = L D L' (3 x 3
+            // blocks); every interior thread then solves its three unit vectors = its three rows of K_I^-1 (kept dense in
+            // shared memory) and its rows of the spikes T_l = K_I^-1 E_l, T_r = K_I^-1 E_r (kept in registers); the
+            // separator threads form the block-tridiagonal Schur complement, thread 0 factors it, and 3 M threads
+            // solve one unit vector each: its inverse is kept dense.  Per iteration:
+            //     y = K_I^-1 r_I  (interior threads, dense rows)        g = r_S - E' y  (separator threads)
+            //     x_S = S^-1 g    (3 M threads, dense rows)             x_I = y - T_l x_p - T_r x_{p+1}
+            // five barriers, no chain longer than one dense row.
+            const int L = sd.L, M = sd.M, pitch = sd.pitch;
+            const int p = i / L, jj = i - p * L;                               // chunk, position in it (0 = separator)
+            int nI = N - 1 - p * L;                                            // interior stations of my chunk
+            if (nI > L - 1) nI = L - 1;
+            if (nI < 0) nI = 0;
+            const int I3 = 3 * nI;
+            const bool isSep = live && jj == 0, isInt = live && jj >= 1;
+            auto factor_spike = [&]() -> int {
+                int ok = 1;
+                double A[9], C[9];
+                blocks(A, C);
+                double *const reg = s.sinv();
+                double *const acs = reg, *const cfs = reg + 15 * kT, *const pub = reg + 15 * kT + kMS * 72;
+                if (live) {
+                    acs[0 * kT + i] = A[0]; acs[1 * kT + i] = A[1]; acs[2 * kT + i] = A[2];
+                    acs[3 * kT + i] = A[4]; acs[4 * kT + i] = A[5]; acs[5 * kT + i] = A[8];
+#pragma unroll
+                    for (int k = 0; k < 9; ++k) acs[(6 + k) * kT + i] = C[k];
+                }
+                c.sync();
+                auto ldA = [&](int st_, double *o) {
+                    o[0] = acs[0 * kT + st_]; o[1] = o[3] = acs[1 * kT + st_]; o[2] = o[6] = acs[2 * kT + st_];
+                    o[4] = acs[3 * kT + st_]; o[5] = o[7] = acs[4 * kT + st_]; o[8] = acs[5 * kT + st_];
+                };
+                auto ldC = [&](int st_, double *o) {
+#pragma unroll
+                    for (int k = 0; k < 9; ++k) o[k] = acs[(6 + k) * kT + st_];
+                };
+                double *const cf_ = cfs + p * 72;          // block k (station p L + k): D_k^-1 at [(k-1) 18], L_k at [(k-1) 18 + 9]
+                if (isInt && jj == 1) {
+                    double Dm[9], Di[9], Cp[9], Lk[9], Tm[9];
+                    ldA(i, Dm);
+#pragma unroll
+                    for (int k = 1; k <= kIM / 3; ++k) {
+                        if (k <= nI) {
+                            if (!(Dm[0] > 0.0)) ok = 0;
+                            inv3_spd(Dm, Di);
+#pragma unroll
+                            for (int q = 0; q < 9; ++q) cf_[(k - 1) * 18 + q] = Di[q];
+                            if (k < nI) {
+                                ldC(i + k - 1, Cp);                    // K[s_k, s_k+1]
+                                mtm(Cp, Di, Lk);                       // L_{k+1} = K[s_k+1, s_k] D_k^-1
+#pragma unroll
+                                for (int q = 0; q < 9; ++q) cf_[k * 18 + 9 + q] = Lk[q];
+                                ldA(i + k, Dm);
+                                mm(Lk, Cp, Tm);
+#pragma unroll
+                                for (int q = 0; q < 9; ++q) Dm[q] -= Tm[q];
+                                Dm[3] = Dm[1]; Dm[6] = Dm[2]; Dm[7] = Dm[5];
+                            }
+                        }
+                    }
+                }
+                c.sync();
+                if (isInt) {
+                    const int m = jj;
+                    double Cl[9], Cr[9];
+                    ldC(p * L, Cl);                                    // K[separator p, s_1]
+                    const bool hasr = (p * L + nI + 1 < N);            // separator p + 1 exists
+#pragma unroll
+                    for (int q = 0; q < 9; ++q) Cr[q] = 0.0;
+                    if (hasr) ldC(p * L + nI, Cr);                     // K[s_nI, separator p + 1]
+                    double *const kv = s.kinv() + (size_t)p * kKC + 3 * (m - 1) * kKP;
+#pragma unroll
+                    for (int cu = 0; cu < 3; ++cu) {
+                        double xk[kIM / 3][3], w[3] = {cu == 0 ? 1.0 : 0.0, cu == 1 ? 1.0 : 0.0, cu == 2 ? 1.0 : 0.0};
+#pragma unroll
+                        for (int k = 1; k <= kIM / 3; ++k) {
+                            xk[k - 1][0] = xk[k - 1][1] = xk[k - 1][2] = 0.0;
+                            if (k >= m && k <= nI) {
+                                const double *Dk = cf_ + (k - 1) * 18;
+                                if (k > m) {
+                                    const double *Lk = Dk + 9;
+                                    const double w0 = -(Lk[0] * w[0] + Lk[1] * w[1] + Lk[2] * w[2]);
+                                    const double w1 = -(Lk[3] * w[0] + Lk[4] * w[1] + Lk[5] * w[2]);
+                                    const double w2 = -(Lk[6] * w[0] + Lk[7] * w[1] + Lk[8] * w[2]);
+                                    w[0] = w0; w[1] = w1; w[2] = w2;
+                                }
+#pragma unroll
+                                for (int q = 0; q < 3; ++q) xk[k - 1][q] = Dk[q * 3] * w[0] + Dk[q * 3 + 1] * w[1] + Dk[q * 3 + 2] * w[2];
+                            }
+                        }
+#pragma unroll
+                        for (int k = kIM / 3 - 1; k >= 1; --k) {
+                            if (k < nI) {                              // x_k -= L_{k+1}' x_{k+1}
+                                const double *Ln = cf_ + k * 18 + 9;
+#pragma unroll
+                                for (int q = 0; q < 3; ++q)
+                                    xk[k - 1][q] -= Ln[q] * xk[k][0] + Ln[3 + q] * xk[k][1] + Ln[6 + q] * xk[k][2];
+                            }
+                        }
+#pragma unroll
+                        for (int k = 1; k <= kIM / 3; ++k) {
+                            if (k <= nI) {
+#pragma unroll
+                                for (int q = 0; q < 3; ++q) kv[cu * kKP + 3 * (k - 1) + q] = xk[k - 1][q];
+                            }
+                        }
+                        // my rows of the spikes: T_l = K_I^-1[:, first] K[s_1, sep p], T_r = K_I^-1[:, last] K[s_nI, sep p+1]
+                        double xl[3] = {xk[0][0], xk[0][1], xk[0][2]}, xr_[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+                        for (int k = 1; k <= kIM / 3; ++k)
+                            if (k == nI) { xr_[0] = xk[k - 1][0]; xr_[1] = xk[k - 1][1]; xr_[2] = xk[k - 1][2]; }
+#pragma unroll
+                        for (int q = 0; q < 3; ++q) {
+                            GL[cu * 3 + q] = xl[0] * Cl[q * 3] + xl[1] * Cl[q * 3 + 1] + xl[2] * Cl[q * 3 + 2];
+                            GR[cu * 3 + q] = xr_[0] * Cr[q] + xr_[1] * Cr[3 + q] + xr_[2] * Cr[6 + q];
+                        }
+                    }
+                    // the pieces the Schur complement needs: rows 0..2 of T_l and T_r (first interior station), the last
+                    // three rows of T_r (last interior station)
+                    double *const pb = pub + p * 27;
+                    if (m == 1) {
+#pragma unroll
+                        for (int q = 0; q < 9; ++q) { pb[q] = GL[q]; pb[9 + q] = GR[q]; }
+                    }
+                    if (m == nI) {
+#pragma unroll
+                        for (int q = 0; q < 9; ++q) pb[18 + q] = GR[q];
+                    }
+                }
+                c.sync();
+                double *const sc = s.sch();
+                if (isSep) {
+                    double S[9], Of[9], Co[9], Cpv[9], Tm[9], Pb[9];
+                    ldA(i, S);
+                    ldC(i, Co);
+#pragma unroll
+                    for (int q = 0; q < 9; ++q) { Of[q] = 0.0; Cpv[q] = 0.0; }
+                    if (nI >= 1) {
+#pragma unroll
+                        for (int q = 0; q < 9; ++q) Pb[q] = pub[p * 27 + q];
+                        mm(Co, Pb, Tm);
+#pragma unroll
+                        for (int q = 0; q < 9; ++q) S[q] -= Tm[q];
+                        if (p + 1 < M) {
+#pragma unroll
+                            for (int q = 0; q < 9; ++q) Pb[q] = pub[p * 27 + 9 + q];
+                            mm(Co, Pb, Tm);
+#pragma unroll
+                            for (int q = 0; q < 9; ++q) Of[q] = -Tm[q];
+                        }
+                    }
+                    if (p >= 1) {
+                        ldC(i - 1, Cpv);                               // K[last interior station of chunk p - 1, separator p]
+#pragma unroll
+                        for (int q = 0; q < 9; ++q) Pb[q] = pub[(p - 1) * 27 + 18 + q];
+                        mtm(Cpv, Pb, Tm);
+#pragma unroll
+                        for (int q = 0; q < 9; ++q) S[q] -= Tm[q];
+                    }
+                    S[3] = S[1]; S[6] = S[2]; S[7] = S[5];
+#pragma unroll
+                    for (int q = 0; q < 9; ++q) { GL[q] = Co[q]; GR[q] = Cpv[q]; }
+#pragma unroll
+                    for (int q = 0; q < 9; ++q) { sc[p * 27 + q] = S[q]; sc[p * 27 + 9 + q] = Of[q]; }
+                }
+                c.sync();
+                if (tid == 0) {                                        // block L D L' of the separator system
+                    double Dg[9], Di[9], Of[9], Lb[9], Tm[9];
+#pragma unroll
+                    for (int q = 0; q < 9; ++q) Dg[q] = sc[q];
+                    for (int q_ = 0; q_ < M; ++q_) {
+                        if (!(Dg[0] > 0.0)) ok = 0;
+                        inv3_spd(Dg, Di);
+#pragma unroll
+                        for (int q = 0; q < 9; ++q) sc[q_ * 27 + q] = Di[q];
+                        if (q_ + 1 < M) {
+#pragma unroll
+                            for (int q = 0; q < 9; ++q) Of[q] = sc[q_ * 27 + 9 + q];
+                            mtm(Of, Di, Lb);                           // L_{q+1} = S[q+1, q] D_q^-1
+#pragma unroll
+                            for (int q = 0; q < 9; ++q) { sc[(q_ + 1) * 27 + 18 + q] = Lb[q]; Dg[q] = sc[(q_ + 1) * 27 + q]; }
+                            mm(Lb, Of, Tm);
+#pragma unroll
+                            for (int q = 0; q < 9; ++q) Dg[q] -= Tm[q];
+                            Dg[3] = Dg[1]; Dg[6] = Dg[2]; Dg[7] = Dg[5];
+                        }
+                    }
+                }
+                c.sync();
+                if (tid < 3 * M) {                                     // row tid of the dense inverse: one unit vector
+                    double *const sv = reg + (size_t)tid * pitch;
+                    const int bt = tid / 3, ct = tid - 3 * bt;
+                    double w[3] = {ct == 0 ? 1.0 : 0.0, ct == 1 ? 1.0 : 0.0, ct == 2 ? 1.0 : 0.0};
+                    for (int q_ = 0; q_ < bt; ++q_) { sv[3 * q_] = 0.0; sv[3 * q_ + 1] = 0.0; sv[3 * q_ + 2] = 0.0; }
+                    for (int q_ = bt; q_ < M; ++q_) {
+                        const double *Dk = sc + q_ * 27;
+                        if (q_ > bt) {
+                            const double *Lk = Dk + 18;
+                            const double w0 = -(Lk[0] * w[0] + Lk[1] * w[1] + Lk[2] * w[2]);
+                            const double w1 = -(Lk[3] * w[0] + Lk[4] * w[1] + Lk[5] * w[2]);
+                            const double w2 = -(Lk[6] * w[0] + Lk[7] * w[1] + Lk[8] * w[2]);
+                            w[0] = w0; w[1] = w1; w[2] = w2;
+                        }
+#pragma unroll
+                        for (int q = 0; q < 3; ++q) sv[3 * q_ + q] = Dk[q * 3] * w[0] + Dk[q * 3 + 1] * w[1] + Dk[q * 3 + 2] * w[2];
+                    }
+                    for (int q_ = M - 2; q_ >= 0; --q_) {
+                        const double *Ln = sc + (q_ + 1) * 27 + 18;
+                        const double x0 = sv[3 * q_ + 3], x1 = sv[3 * q_ + 4], x2 = sv[3 * q_ + 5];
+#pragma unroll
+                        for (int q = 0; q < 3; ++q) sv[3 * q_ + q] -= Ln[q] * x0 + Ln[3 + q] * x1 + Ln[6 + q] * x2;
+                    }
+                    for (int k = 3 * M; k < pitch; ++k) sv[k] = 0.0;
+                }
+                c.sync();
+                // (the Schur scratch lay over the rhs rows: leave the separator rhs row finite up to the pitch)
+                for (int k = tid; k < kT; k += kT) s.gg()[k] = 0.0;
+                return !c.any(!ok);
+            };
+            auto solve_spike = [&](double *r) {
+                if (live) { s.rr(0)[i] = r[0]; s.rr(1)[i] = r[1]; s.rr(2)[i] = r[2]; }
+                c.sync();
+                double y[3] = {0.0, 0.0, 0.0};
+                if (isInt) {
+                    const double *kv = s.kinv() + (size_t)p * kKC + 3 * (jj - 1) * kKP;
+                    const int s1 = p * L + 1;
+#pragma unroll
+                    for (int k = 0; k < kIM / 3; ++k) {
+                        if (k < nI) {
+                            const double r0 = s.rr(0)[s1 + k], r1 = s.rr(1)[s1 + k], r2 = s.rr(2)[s1 + k];
+#pragma unroll
+                            for (int q = 0; q < 3; ++q)
+                                y[q] += kv[q * kKP + 3 * k] * r0 + kv[q * kKP + 3 * k + 1] * r1 + kv[q * kKP + 3 * k + 2] * r2;
+                        }
+                    }
+                    s.yy(0)[i] = y[0]; s.yy(1)[i] = y[1]; s.yy(2)[i] = y[2];
+                }
+                c.sync();
+                if (isSep) {
+                    double g0 = r[0], g1 = r[1], g2 = r[2];
+                    if (nI >= 1) {                                     // - K[sep, s_1] y_{s_1}
+                        const double a0 = s.yy(0)[i + 1], a1 = s.yy(1)[i + 1], a2 = s.yy(2)[i + 1];
+                        g0 -= GL[0] * a0 + GL[1] * a1 + GL[2] * a2;
+                        g1 -= GL[3] * a0 + GL[4] * a1 + GL[5] * a2;
+                        g2 -= GL[6] * a0 + GL[7] * a1 + GL[8] * a2;
+                    }
+                    if (p >= 1) {                                      // - K[sep, last interior station of chunk p - 1] y
+                        const double a0 = s.yy(0)[i - 1], a1 = s.yy(1)[i - 1], a2 = s.yy(2)[i - 1];
+                        g0 -= GR[0] * a0 + GR[3] * a1 + GR[6] * a2;
+                        g1 -= GR[1] * a0 + GR[4] * a1 + GR[7] * a2;
+                        g2 -= GR[2] * a0 + GR[5] * a1 + GR[8] * a2;
+                    }
+                    s.gg()[3 * p] = g0; s.gg()[3 * p + 1] = g1; s.gg()[3 * p + 2] = g2;
+                }
+                c.sync();
+                if (tid < 3 * M) {
+                    const double *sv = s.sinv() + (size_t)tid * pitch, *gv = s.gg();
+                    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+                    int k = 0;
+                    for (; k + 4 <= pitch; k += 4) {
+                        double s0, s1_, s2, s3, h0, h1, h2, h3;
+                        ld2(sv + k, s0, s1_); ld2(sv + k + 2, s2, s3);
+                        ld2(gv + k, h0, h1); ld2(gv + k + 2, h2, h3);
+                        a0 += s0 * h0; a1 += s1_ * h1; a2 += s2 * h2; a3 += s3 * h3;
+                    }
+                    for (; k < pitch; k += 2) {
+                        double s0, s1_, h0, h1;
+                        ld2(sv + k, s0, s1_); ld2(gv + k, h0, h1);
+                        a0 += s0 * h0; a1 += s1_ * h1;
+                    }
+                    const int bt = tid / 3;
+                    s.xr(tid - 3 * bt)[bt * L] = (a0 + a1) + (a2 + a3);
+                }
+                c.sync();
+                if (isSep) {
+                    r[0] = s.xr(0)[i]; r[1] = s.xr(1)[i]; r[2] = s.xr(2)[i];
+                } else if (isInt) {
+                    const int sp_ = p * L, sn = (p + 1) * L;
+                    const double a0 = s.xr(0)[sp_], a1 = s.xr(1)[sp_], a2 = s.xr(2)[sp_];
+                    double t0 = y[0] - (GL[0] * a0 + GL[1] * a1 + GL[2] * a2);
+                    double t1 = y[1] - (GL[3] * a0 + GL[4] * a1 + GL[5] * a2);
+                    double t2 = y[2] - (GL[6] * a0 + GL[7] * a1 + GL[8] * a2);
+                    if (sn < N) {
+                        const double b0 = s.xr(0)[sn], b1 = s.xr(1)[sn], b2 = s.xr(2)[sn];
+                        t0 -= GR[0] * b0 + GR[1] * b1 + GR[2] * b2;
+                        t1 -= GR[3] * b0 + GR[4] * b1 + GR[5] * b2;
+                        t2 -= GR[6] * b0 + GR[7] * b1 + GR[8] * b2;
+                    }
+                    r[0] = t0; r[1] = t1; r[2] = t2;
+                    s.xr(0)[i] = t0; s.xr(1)[i] = t1; s.xr(2)[i] = t2;
+                }
+                c.sync();
+            };
+            auto factor = [&]() -> int {
+                if constexpr (kSpike) return factor_spike();
+                else return factor_cr();
+            };
+            auto kkt_solve = [&](double *r) {
+                if constexpr (kSpike) solve_spike(r);
+                else solve_cr(r);
+            };
+
             if (!factor()) status = PQP_NON_CVX;
             const double alpha = pm.alpha;
             double pri_res = 0, dua_res = 0, pri_nrm = 0, dua_nrm = 0;
@@ -572,7 +937,7 @@ struct Kk {
                     rows_of(xt[0], xt[1], xt[2], xt[3], ax);
 #pragma unroll
                     for (int k = 0; k < 11; ++k) {
-                        if (chk) s.wold(k)[tid] = v[k] - z[k];
+                        if (chk) Wk(k)[tid] = v[k] - z[k];
                         v[k] = v[k] + alpha * (ax[k] - z[k]);
                     }
                     if (last) v[4] = 0.0;
@@ -602,7 +967,7 @@ struct Kk {
 #pragma unroll
                         for (int k = 0; k < 11; ++k) {
                             if (k == 4 && last) continue;
-                            const double rr = ax[k] - z[k], e = s.E(k)[tid];
+                            const double rr = ax[k] - z[k], e = Ek(k)[tid];
                             red[0] = fmax(red[0], fabs(rr)); red[1] = fmax(red[1], fabs(z[k])); red[2] = fmax(red[2], fabs(ax[k]));
                             red[3] = fmax(red[3], e * fabs(rr)); red[4] = fmax(red[4], e * fabs(z[k])); red[5] = fmax(red[5], e * fabs(ax[k]));
                         }
@@ -630,8 +995,8 @@ struct Kk {
                         for (int k = 0; k < 11; ++k) {
                             gq[k] = 0.0;
                             if (!live || (k == 4 && last)) continue;
-                            const double e = s.E(k)[tid];
-                            double gg = W[k] * ((v[k] - z[k]) - s.wold(k)[tid]);
+                            const double e = Ek(k)[tid];
+                            double gg = W[k] * ((v[k] - z[k]) - Wk(k)[tid]);
                             const bool u_inf = e * hi[k] > kOsqpInfty * kMinScaling;
                             const bool l_inf = e * lo[k] < -kOsqpInfty * kMinScaling;
                             if (u_inf) gg = l_inf ? 0.0 : fmin(gg, 0.0);
@@ -674,7 +1039,7 @@ struct Kk {
 #pragma unroll
                                 for (int k = 0; k < 11; ++k) {
                                     if (k == 4 && last) continue;
-                                    const double e = s.E(k)[tid];
+                                    const double e = Ek(k)[tid];
                                     const double El = e * lo[k], Eu = e * hi[k];
                                     const double ro = rho_bar(El, Eu, rho), rn = rho_bar(El, Eu, rho_new);
                                     const double zz = clamp2(v[k], lo[k], hi[k]);
