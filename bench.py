@@ -312,13 +312,14 @@ class GpuWorkload:
             self.comm = True
         self.h_n = np.ascontiguousarray(b["n_points"], dtype=np.int32)
         self._pinned = None
+        self.force_classes = False   # route a uniform batch through the per-class entry (it carries a launch order)
 
     # ---- device-resident call (asynchronous on `stream`)
     def solve_device(self, stream, stats=None):
         d = self.d
         sp = C.c_void_p(stream.cuda_stream)
         st = C.byref(stats) if stats is not None else None
-        if self.uniform:
+        if self.uniform and not self.force_classes:
             k = int(self.keep[0])
             rc = self.L.pqp_solve_batch_device(self.solver._h, 0, self.B, self.total, self.nmax, k, k, d["n"].data_ptr(),
                                                d["off"].data_ptr(), d["ref"].data_ptr(), d["bounds"].data_ptr(),
@@ -546,7 +547,8 @@ def run_ours(args, rank, world, local_rank):
         if world == 1:
             line["cpu_baseline"] = cpu_baseline(args)
             if args.config == 2 and not args.no_extras:
-                line["extras"] = {"configs": extras_configs(torch, local_rank, flush, stream, barrier),
+                line["extras"] = {"order_hint": extras_order_hint(w, torch, 5, 3, flush, stream, barrier),
+                                  "configs": extras_configs(torch, local_rank, flush, stream, barrier),
                                   "formulations": extras_formulations(local_rank)}
         print(json.dumps(line), flush=True)
     w.close()
@@ -600,10 +602,32 @@ def extras_configs(torch, local_rank, flush, stream, barrier):
     return out
 
 
+def extras_order_hint(w, torch, steps, warmup, flush, stream, barrier):
+    """The launch tail, measured: the same device-resident batch through the per-class entry point in index order and
+    with pqp_set_order_hint(iterations of a previous solve) = longest expected work first.  Context only: the headline
+    `value` never uses a hint (a bench that repeats one batch would make the hint exact)."""
+    try:
+        w.force_classes = True
+        plain = time_workload(w, torch, steps, warmup, flush, stream, barrier, with_e2e=False)
+        it = np.ascontiguousarray(plain["iters"], dtype=np.int32)
+        assert w.L.pqp_set_order_hint(w.solver._h, w.B, it.ctypes.data_as(C.c_void_p)) == 0
+        hinted = time_workload(w, torch, steps, warmup, flush, stream, barrier, with_e2e=False)
+        w.L.pqp_set_order_hint(w.solver._h, 0, None)
+        w.force_classes = False
+        same = bool(np.array_equal(plain["iters"], hinted["iters"]) and np.array_equal(plain["status"], hinted["status"]))
+        return {"what": "config-2 shard through pqp_solve_batch_device_classes: launch order longest path first (= index order "
+                        "here) vs pqp_set_order_hint with the iteration counts of a previous solve of the same batch (an exact "
+                        "predictor: upper bound of what an ordering can recover)",
+                "ms_per_step_index_order": plain["solve_ms"] / steps, "ms_per_step_hinted": hinted["solve_ms"] / steps,
+                "solves_per_sec_hinted": w.B * steps / (hinted["solve_ms"] * 1e-3), "same_results": same}
+    except Exception as ex:
+        w.force_classes = False
+        return {"error": repr(ex)[:300]}
+
+
 def extras_formulations(device, reps=3):
-    """The other two type strings of OsqpSolver::create on the config-2 shape (1024 x 100, host buffers, host wall clock):
-    "KPC" runs on the thread-per-station classes (assembled in the kernel), "K" is assembled sparse on the host and solved
-    by the generic one-warp kernel."""
+    """The other two type strings of OsqpSolver::create on the config-2 shape (1024 x 100 curved corridors, host buffers,
+    host wall clock): "KPC" and "K" run on thread-per-station kernels of their own, assembled in the kernel."""
     out = {}
     try:
         from path_optimizer_b200 import planner

@@ -266,6 +266,14 @@ int pqp_solve_batch_device_classes(pqp_handle *h, int formulation, int batch, in
                                    pqp_stats *stats);
 
 /* Last error text for this thread (CUDA error strings etc.); never NULL. */
+/* Launch-order hint for the next solves of a batch of `batch` paths: expected ADMM iterations per path, e.g. the
+ * `iters` the previous planning cycle reported for the same candidates.  Inside a kernel class the paths are then
+ * launched longest expected work (stations x iterations) first instead of longest path first, which shortens the tail of
+ * a launch whose paths outnumber the resident CTA slots only a few times (1024 paths on one B200: 23 % of the launch is
+ * tail, an exact hint recovers about half of it).  Results do not depend on the order.  NULL or batch 0 clears
+ * the hint; a hint whose length differs from a call's batch is ignored by that call.  No reference counterpart. */
+int pqp_set_order_hint(pqp_handle *h, int batch, const int32_t *expected_iters);
+
 const char *pqp_last_error(void);
 
 /* "pqp <abi> sm_100a <build info>" */

@@ -12,7 +12,7 @@ LIB_PATH = os.environ.get("PQP_LIB") or os.path.join(_HERE, "libpqp.so")   # PQP
 SYMBOLS = ["pqp_params_default", "pqp_params_update_config", "pqp_keep_control_steps", "pqp_problem_size",
            "pqp_create", "pqp_destroy", "pqp_set_params", "pqp_solve_batch", "pqp_solve_batch_device",
            "pqp_solve_batch_device_classes", "pqp_last_error", "pqp_version", "pqp_max_points", "pqp_max_points_keep",
-           "pqp_class_info", "pqp_class_info_kpc", "pqp_class_info_form", "pqp_class_name", "pqp_device_class_info"]
+           "pqp_class_info", "pqp_class_info_kpc", "pqp_class_info_form", "pqp_set_order_hint", "pqp_class_name", "pqp_device_class_info"]
 # ... and include/pqp_env.h
 ENV_SYMBOLS = ["pqp_update_limits", "pqp_update_limits_device", "pqp_set_map", "pqp_map_distance", "pqp_spline_fit", "pqp_spline_eval", "pqp_update_bounds_batch",
                "pqp_check_states", "pqp_finish_raw_batch", "pqp_densify_batch", "pqp_plan_batch"]
@@ -50,6 +50,7 @@ def load():
     L.pqp_max_points.argtypes = [vp, C.c_int]
     L.pqp_max_points_keep.argtypes = [vp, C.c_int, C.c_int]
     L.pqp_class_info.argtypes = [C.c_int] * 3 + [C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int64)]
+    L.pqp_set_order_hint.argtypes = [vp, C.c_int, vp]
     L.pqp_class_info_form.argtypes = [C.c_int] * 4 + [C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int64)]
     L.pqp_class_info_kpc.argtypes = [C.c_int] * 2 + [C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int64)]
     L.pqp_class_name.argtypes = [C.c_int]

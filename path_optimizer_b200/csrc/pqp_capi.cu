@@ -183,8 +183,14 @@ int pqp_launch_kp_classes(pqp_handle *h, const pqp::BatchView &bv, int batch, co
         int fill[kNumVariants];
         for (int v = 0; v < kNumVariants; ++v) fill[v] = pl.start_v[v];
         for (int b = 0; b < batch; ++b) h->h_order[fill[cls[b]]++] = b;
+        // longest first; with a hint (pqp_set_order_hint) longest EXPECTED WORK first: stations x expected iterations
+        const bool hinted = h->order_hint.size() == (size_t)batch;
+        const int32_t *hint = h->order_hint.data();
         for (int v = 0; v < kNumVariants; ++v)
-            std::stable_sort(h->h_order + pl.start_v[v], h->h_order + pl.start_v[v + 1], [&](int a, int b) { return n[a] > n[b]; });
+            std::stable_sort(h->h_order + pl.start_v[v], h->h_order + pl.start_v[v + 1], [&](int a, int b) {
+                if (hinted) return (long long)n[a] * hint[a] > (long long)n[b] * hint[b];
+                return n[a] > n[b];
+            });
         PQP_CUDA(cudaMemcpyAsync(h->d_order, h->h_order, (size_t)batch * sizeof(int32_t), cudaMemcpyHostToDevice, st));
         pl.n.assign(n, n + batch);
         pl.keep = keepv;
@@ -422,6 +428,14 @@ int pqp_class_info_kpc(int n_points, int smem_optin, int *variant, int *threads,
     if (threads) *threads = ok ? kVariants[v].threads : 0;
     if (smem_bytes) *smem_bytes = (int64_t)need;
     return ok ? PQP_OK : PQP_ERR_UNSUPPORTED;
+}
+
+int pqp_set_order_hint(pqp_handle *h, int batch, const int32_t *expected_iters) {
+    if (!h || batch < 0) return PQP_ERR_ARG;
+    if (!expected_iters || batch == 0) h->order_hint.clear();
+    else h->order_hint.assign(expected_iters, expected_iters + batch);
+    h->plan.valid = false;     // the cached class plan carries the launch order
+    return PQP_OK;
 }
 
 int pqp_class_info_form(int formulation, int n_points, int keep, int smem_optin, int *variant, int *threads, int64_t *smem_bytes) {
@@ -810,9 +824,13 @@ int pqp_solve_batch(pqp_handle *h, int formulation, int batch, const int32_t *n_
         int fill[kNumVariants];
         for (int v = 0; v < kNumVariants; ++v) fill[v] = start_cv[k][v];
         for (int b = cb[k]; b < cb[k + 1]; ++b) h->h_order[fill[cls[b]]++] = b;
+        const bool hinted = h->order_hint.size() == (size_t)batch;
+        const int32_t *hint = h->order_hint.data();
         for (int v = 0; v < kNumVariants; ++v)
-            std::stable_sort(h->h_order + start_cv[k][v], h->h_order + start_cv[k][v + 1],
-                             [&](int a, int b) { return n_points[a] > n_points[b]; });
+            std::stable_sort(h->h_order + start_cv[k][v], h->h_order + start_cv[k][v + 1], [&](int a, int b) {
+                if (hinted) return (long long)n_points[a] * hint[a] > (long long)n_points[b] * hint[b];
+                return n_points[a] > n_points[b];
+            });
     }
     PQP_CUDA(cudaSetDevice(h->device));
     const size_t B = (size_t)batch, T = (size_t)total;

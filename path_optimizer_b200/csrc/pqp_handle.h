@@ -46,6 +46,9 @@ struct pqp_handle {
         int count_v[PQP_MAX_VARIANTS] = {}, start_v[PQP_MAX_VARIANTS + 1] = {};
         size_t smem_v[PQP_MAX_VARIANTS] = {};
     } plan;
+    // pqp_set_order_hint: expected ADMM iterations per path (e.g. the previous planning cycle's counts); launch order
+    // inside a class becomes longest-expected-first
+    std::vector<int32_t> order_hint;
     // device buffers for the host-pointer entry point
     int32_t *d_n = nullptr, *d_off = nullptr, *d_order = nullptr, *d_status = nullptr, *d_iters = nullptr;
     pqp_state *d_ref = nullptr, *d_out = nullptr;

@@ -344,3 +344,28 @@ def test_k_thread_per_station_classes_and_plan(oracle_params):
         for f in "xyzks":
             np.testing.assert_allclose(r["states"][f][lo_:lo_ + k], o["states"][f][lo_:lo_ + k], rtol=0, atol=TOL)
     sp.close()
+
+
+def test_order_hint_changes_the_launch_order_only(oracle_params):
+    """pqp_set_order_hint: longest expected work first inside a class.  Results are bit-identical with and without it,
+    through the per-class device entry and through pqp_solve_batch; a hint of another length is ignored."""
+    import torch
+    from path_optimizer_b200 import _lib
+    L = _lib.load()
+    rng = np.random.default_rng(3)
+    n_points = rng.integers(20, 200, size=160)
+    batch = synth.curvy_corridors(160, n_points=n_points)
+    total = int(batch["offsets"][-1])
+    s = _solver(160, total)
+    r0 = s.solve(batch)
+    it = np.ascontiguousarray(r0["iters"], dtype=np.int32)
+    assert L.pqp_set_order_hint(s._h, 160, it.ctypes.data_as(C.c_void_p)) == 0
+    r1 = s.solve(batch)
+    assert np.array_equal(r0["status"], r1["status"]) and np.array_equal(r0["iters"], r1["iters"])
+    assert np.array_equal(r0["frenet"], r1["frenet"], equal_nan=True)
+    # a hint of another length is ignored; NULL clears it
+    assert L.pqp_set_order_hint(s._h, 7, it.ctypes.data_as(C.c_void_p)) == 0
+    r2 = s.solve(batch)
+    assert np.array_equal(r0["frenet"], r2["frenet"], equal_nan=True)
+    assert L.pqp_set_order_hint(s._h, 0, None) == 0 and L.pqp_set_order_hint(None, 0, None) != 0
+    s.close()
