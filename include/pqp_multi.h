@@ -48,7 +48,7 @@ void pqp_multi_destroy(pqp_multi *m);
 int pqp_multi_devices(const pqp_multi *m);
 
 /* pqp_solve_batch over all devices: the batch is cut into contiguous shards of (nearly) equal station count, every
- * device uploads, solves and downloads its shard concurrently (host buffers as in pqp_solve_batch; KP only), and, when
+ * device uploads, solves and downloads its shard concurrently (host buffers as in pqp_solve_batch; "KP" and "K"), and, when
  * `gather` is non-zero, ONE all-gather leaves the Frenet states of the WHOLE batch on every device:
  * pqp_multi_gathered(m, d) = device pointer on device index d to [n_devices][rows][3] doubles, rows =
  * pqp_multi_gather_rows(m) (the largest shard's station count; shard k's stations start at row 0 of block k).

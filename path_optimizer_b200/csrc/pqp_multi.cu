@@ -201,7 +201,10 @@ int pqp_multi_solve_batch(pqp_multi *m, int formulation, int batch, const int32_
         pqp_set_err("pqp_multi_solve_batch: bad argument");
         return PQP_ERR_ARG;
     }
-    if (formulation != PQP_FORM_KP) { pqp_set_err("pqp_multi_solve_batch: KP only"); return PQP_ERR_UNSUPPORTED; }
+    if (formulation != PQP_FORM_KP && formulation != PQP_FORM_K) {   // (KPC would need the per-station limits as well)
+        pqp_set_err("pqp_multi_solve_batch: KP and K only");
+        return PQP_ERR_UNSUPPORTED;
+    }
     if (stats) memset(stats, 0, sizeof(*stats));
     if (batch == 0) return PQP_OK;
     // contiguous shards of (nearly) equal station count

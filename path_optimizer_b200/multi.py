@@ -33,7 +33,7 @@ class MultiGpuSolver:
         except Exception:
             pass
 
-    def solve(self, batch, gather=True):
+    def solve(self, batch, gather=True, formulation="KP"):
         """Returns dict(states, frenet, status, iters, ok, stats, shards, gather_rows); the gathered device buffers stay
         inside the library (gathered_ptr(k))."""
         n_points = np.ascontiguousarray(batch["n_points"], dtype=np.int32)
@@ -47,7 +47,7 @@ class MultiGpuSolver:
         status = np.zeros(B, dtype=np.int32)
         iters = np.zeros(B, dtype=np.int32)
         stats = Stats()
-        rc = self._L.pqp_multi_solve_batch(self._m, 0, B, ptr(n_points), ptr(ref), ptr(bounds), ptr(x0), ptr(end_heading),
+        rc = self._L.pqp_multi_solve_batch(self._m, {"KP": 0, "K": 1}[formulation], B, ptr(n_points), ptr(ref), ptr(bounds), ptr(x0), ptr(end_heading),
                                            ptr(states), ptr(frenet), ptr(status), ptr(iters), int(bool(gather)), C.byref(stats))
         if rc != OK:
             raise PqpError(f"pqp_multi_solve_batch failed (rc={rc}): {_lib.last_error()}")

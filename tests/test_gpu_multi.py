@@ -60,6 +60,13 @@ def test_multi_solver_matches_single_device(n_dev):
     # second call reuses the buffers
     again = ms.solve(batch, gather=True)
     assert np.array_equal(again["frenet"], ref["frenet"])
+    # "K" shards the same way
+    single = BatchPathSolver(max_batch=300, max_total_points=int(n_points.sum()))
+    refk = single.solve(batch, "K")
+    single.close()
+    resk = ms.solve(batch, gather=True, formulation="K")
+    assert np.array_equal(resk["status"], refk["status"]) and np.array_equal(resk["iters"], refk["iters"])
+    assert np.array_equal(resk["frenet"], refk["frenet"])
     ms.close()
 
 
