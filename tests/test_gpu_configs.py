@@ -369,3 +369,28 @@ def test_order_hint_changes_the_launch_order_only(oracle_params):
     assert np.array_equal(r0["frenet"], r2["frenet"], equal_nan=True)
     assert L.pqp_set_order_hint(s._h, 0, None) == 0 and L.pqp_set_order_hint(None, 0, None) != 0
     s.close()
+
+
+def test_k_and_kpc_full_size_samples(oracle_params):
+    """"K" and "KPC" at a BASELINE shard size (8192 paths x 100 stations, config-4 shape): every path reaches a verdict, and
+    a 48-path sample of each agrees with the oracle (status, iteration count, states at 1e-8)."""
+    from path_optimizer_b200 import planner
+    b = synth.straight_corridors(8192, 100, config=4)
+    total = 8192 * 100
+    b["ref"]["v"] = 4.0 + 3.0 * np.sin(np.arange(total) * 0.05)
+    b["ref"]["a"] = 0.5 * np.cos(np.arange(total) * 0.05)
+    s = _solver(8192, total)
+    mk, mkp = planner.update_limits(s.params, b["ref"])
+    idx = np.sort(np.random.default_rng(5).choice(8192, size=48, replace=False))
+    sub = synth.take_paths(b, idx)
+    o = b["offsets"]
+    sel = np.concatenate([np.arange(o[i], o[i + 1]) for i in idx])
+    for form, fid, kw, okw in (("K", 1, {}, {}), ("KPC", 2, dict(max_k=mk, max_kp=mkp), dict(max_k=mk[sel], max_kp=mkp[sel]))):
+        res = s.solve(b, formulation=form, **kw)
+        assert (res["status"] != 0).all() and (res["status"] == SOLVED).mean() > 0.9
+        ref = oracle.solve_batch(oracle_params, fid, sub, threads=8, **okw)
+        assert np.array_equal(res["status"][idx], ref["status"]) and np.array_equal(res["iters"][idx], ref["iters"])
+        np.testing.assert_allclose(res["frenet"][sel], ref["frenet"], rtol=0, atol=TOL)
+        for f in "xyzks":
+            np.testing.assert_allclose(res["states"][f][sel], ref["states"][f], rtol=0, atol=TOL)
+    s.close()
