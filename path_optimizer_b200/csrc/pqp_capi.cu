@@ -146,6 +146,48 @@ bool device_class(pqp_handle *h, int nmax, int k_lo, int k_hi, int *v_out, size_
 }  // namespace
 
 
+// ---- launch order from the inputs ------------------------------------------------------------------------------
+// A launch of a few paths per resident CTA slot ends with a tail set by the paths that happen to start last.  Paths that
+// start far from the corridor centre relative to its width tend to need more ADMM iterations (correlation 0.3-0.4 on the
+// BASELINE corridors: weak, but enough to keep the long ones out of the last wave), so small batches are launched in the
+// order of  stations x (1 + min(|e_y0| / w, 2)),  largest first.  Results do not depend on the order.
+constexpr int kAutoOrderMax = 2048;    // beyond ~7 paths per slot the tail is a few per cent: index order
+PQP_HD double order_key(int n, double ey0, double lb, double ub) {
+    const double w = 0.5 * (ub - lb);
+    double sc = fabs(ey0) / (w > 1e-3 ? w : 1e-3);
+    if (!(sc == sc)) sc = 0.0;
+    if (sc > 2.0) sc = 2.0;
+    return (double)n * (1.0 + sc);
+}
+__global__ void __launch_bounds__(1024)
+pqp_order_kernel(const int32_t *__restrict__ n_points, const int32_t *__restrict__ offsets, const pqp_station_bounds *__restrict__ bounds,
+                 const double *__restrict__ x0, int batch, int32_t *__restrict__ order) {
+    __shared__ double key[kAutoOrderMax];
+    for (int b = threadIdx.x; b < batch; b += blockDim.x) {
+        const int n = n_points[b];
+        double k = 0.0;
+        if (n >= 1) {
+            const pqp_station_bounds bb = bounds[offsets[b]];
+            k = order_key(n, x0[3 * (size_t)b], bb.c0_lb, bb.c0_ub);
+        }
+        key[b] = k;
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < batch; b += blockDim.x) {
+        const double kb = key[b];
+        int rank = 0;
+        for (int j = 0; j < batch; ++j) {
+            const double kj = key[j];
+            rank += (kj > kb) || (kj == kb && j < b);
+        }
+        order[rank] = b;
+    }
+}
+bool auto_order_enabled() {
+    static const bool on = [] { const char *e = getenv("PQP_NO_AUTO_ORDER"); return !(e && *e == '1'); }();
+    return on;
+}
+
 extern "C" {
 static int launch_variant(pqp_handle *h, int v, const pqp::BatchView &bv, int count, const int32_t *d_order,
                           size_t smem_bytes, cudaStream_t st);
@@ -312,7 +354,7 @@ void pqp_destroy(pqp_handle *h) {
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->nccl_comm) pqp_comm_destroy(h);
-    cudaFree(h->d_n); cudaFree(h->d_off); cudaFree(h->d_order); cudaFree(h->d_status); cudaFree(h->d_iters);
+    cudaFree(h->d_n); cudaFree(h->d_off); cudaFree(h->d_order); cudaFree(h->d_order_auto); cudaFree(h->d_status); cudaFree(h->d_iters);
     cudaFree(h->d_ref); cudaFree(h->d_out); cudaFree(h->d_bounds);
     cudaFree(h->d_x0); cudaFree(h->d_end); cudaFree(h->d_frenet); cudaFree(h->d_ws);
     cudaFree(h->d_max_k); cudaFree(h->d_max_kp);
@@ -384,6 +426,7 @@ int pqp_create(pqp_handle **out, const pqp_params *params, int device, int max_b
     PQP_TRY(cudaMalloc(&h->d_n, B * sizeof(int32_t)));
     PQP_TRY(cudaMalloc(&h->d_off, (B + 1) * sizeof(int32_t)));
     PQP_TRY(cudaMalloc(&h->d_order, B * sizeof(int32_t)));
+    PQP_TRY(cudaMalloc(&h->d_order_auto, (size_t)std::min(max_batch, kAutoOrderMax) * sizeof(int32_t)));
     PQP_TRY(cudaMalloc(&h->d_status, B * sizeof(int32_t)));
     PQP_TRY(cudaMalloc(&h->d_iters, B * sizeof(int32_t)));
     PQP_TRY(cudaMalloc(&h->d_ref, T * sizeof(pqp_state)));
@@ -554,14 +597,22 @@ int pqp_solve_batch_device(pqp_handle *h, int formulation, int batch, int total_
         return PQP_ERR_UNSUPPORTED;
     }
     if (stats) PQP_CUDA(cudaEventRecord(h->ev[0], st));
-    int rc = launch_variant(h, v, bv, batch, nullptr, smem, st);
+    // small batches: launch order from the inputs (see pqp_order_kernel); the host sees none of them here
+    const int32_t *order = nullptr;
+    const bool ordered = auto_order_enabled() && batch > h->num_sms && batch <= kAutoOrderMax;
+    if (ordered) {
+        pqp_order_kernel<<<1, 1024, 0, st>>>(d_n_points, d_offsets, d_bounds, d_x0, batch, h->d_order_auto);
+        PQP_CUDA(cudaGetLastError());
+        order = h->d_order_auto;
+    }
+    int rc = launch_variant(h, v, bv, batch, order, smem, st);
     if (rc != PQP_OK) return rc;
     if (stats) {
         memset(stats, 0, sizeof(*stats));
         PQP_CUDA(cudaEventRecord(h->ev[1], st));
         PQP_CUDA(cudaEventSynchronize(h->ev[1]));
         PQP_CUDA(cudaEventElapsedTime(&stats->kernel_ms, h->ev[0], h->ev[1]));
-        stats->kernel_launches = 1;
+        stats->kernel_launches = ordered ? 2 : 1;
     }
     return PQP_OK;
 }
@@ -809,6 +860,14 @@ int pqp_solve_batch(pqp_handle *h, int formulation, int batch, const int32_t *n_
         cb[k] = (k == n_chunks) ? batch : std::max(b, cb[k - 1]);
     }
     h->plan.valid = false;   // (this call rewrites the order array the class plan of the device entry points refers to)
+    std::vector<double> okey;
+    if (batch <= kAutoOrderMax && auto_order_enabled()) {
+        okey.resize((size_t)batch);
+        for (int b = 0; b < batch; ++b) {
+            const int n = n_points[b];
+            okey[b] = n >= 1 ? order_key(n, x0[3 * (size_t)b], bounds[h->h_off[b]].c0_lb, bounds[h->h_off[b]].c0_ub) : 0.0;
+        }
+    }
     // per chunk: per-class longest-first order (written into the pinned order array at the chunk's range)
     int count_cv[kMaxChunks][kNumVariants];
     int start_cv[kMaxChunks][kNumVariants + 1];
@@ -826,9 +885,11 @@ int pqp_solve_batch(pqp_handle *h, int formulation, int batch, const int32_t *n_
         for (int b = cb[k]; b < cb[k + 1]; ++b) h->h_order[fill[cls[b]]++] = b;
         const bool hinted = h->order_hint.size() == (size_t)batch;
         const int32_t *hint = h->order_hint.data();
+        const bool keyed = !hinted && auto_order_enabled() && batch <= kAutoOrderMax;   // as pqp_order_kernel does on the device
         for (int v = 0; v < kNumVariants; ++v)
             std::stable_sort(h->h_order + start_cv[k][v], h->h_order + start_cv[k][v + 1], [&](int a, int b) {
                 if (hinted) return (long long)n_points[a] * hint[a] > (long long)n_points[b] * hint[b];
+                if (keyed) return okey[a] > okey[b];
                 return n_points[a] > n_points[b];
             });
     }

@@ -51,6 +51,7 @@ struct pqp_handle {
     std::vector<int32_t> order_hint;
     // device buffers for the host-pointer entry point
     int32_t *d_n = nullptr, *d_off = nullptr, *d_order = nullptr, *d_status = nullptr, *d_iters = nullptr;
+    int32_t *d_order_auto = nullptr;   // launch order computed on the device (pqp_solve_batch_device, small batches)
     pqp_state *d_ref = nullptr, *d_out = nullptr;
     pqp_station_bounds *d_bounds = nullptr;
     double *d_x0 = nullptr, *d_end = nullptr, *d_frenet = nullptr, *d_ws = nullptr;

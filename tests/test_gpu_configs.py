@@ -394,3 +394,29 @@ def test_k_and_kpc_full_size_samples(oracle_params):
         for f in "xyzks":
             np.testing.assert_allclose(res["states"][f][sel], ref["states"][f], rtol=0, atol=TOL)
     s.close()
+
+
+def test_device_entry_input_derived_launch_order(oracle_params):
+    """Batches of more paths than SMs and at most 2048 are launched by pqp_solve_batch_device in an order computed on the
+    device from the inputs (pqp_order_kernel: stations x (1 + |e_y0| / w), largest first).  The order must be a
+    permutation -- every path gets its verdict -- and the results must be those of the host-buffer entry, bit for bit,
+    including with NaN / degenerate inputs in the key."""
+    rng = np.random.default_rng(12)
+    n_points = rng.integers(60, 103, size=700)
+    batch = synth.curvy_corridors(700, n_points=n_points)
+    batch["x0"][5, 0] = np.nan                      # NaN key (whatever the solve makes of a NaN start offset)
+    o = batch["offsets"]
+    batch["bounds"]["c0_ub"][o[9]] = batch["bounds"]["c0_lb"][o[9]]     # zero-width first station
+    total = int(o[-1])
+    s = _solver(700, total)
+    res = s.solve(batch)
+    dres = _device_call(s, batch, classes=False)
+    assert (dres["status"] != 0).all()
+    assert np.array_equal(dres["status"], res["status"]) and np.array_equal(dres["iters"], res["iters"])
+    assert np.array_equal(dres["frenet"], res["frenet"], equal_nan=True)
+    idx = np.arange(0, 700, 11)
+    keep = idx[(idx != 5)]
+    sub = synth.take_paths(batch, keep)
+    ref = oracle.solve_batch(oracle_params, 0, sub, threads=8)
+    assert np.array_equal(res["status"][keep], ref["status"]) and np.array_equal(res["iters"][keep], ref["iters"])
+    s.close()
