@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- batched path-QP solves/s on B200 (BASELINE.json metric), one rank per GPU.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config 2|3|4|5]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config 2|3|4|5] [--formulation KP|K|KPC]
 
 A "step" is one pass of the hot path (QP assembly -> ADMM solve -> state extraction) over one batch of
 synthetic corridor paths.  The default workload is BASELINE config 2 (1024 paths x 100 stations per GPU);
@@ -186,6 +186,18 @@ def oracle_bounds_fn(oracle, params):
     return fn
 
 
+def cpu_solve(oracle, params, formulation, batch, threads):
+    """One CPU-arm solve of `batch` with the formulation's inputs (KPC: limits from the synthetic speed profile)."""
+    form = workloads.FORMULATION_IDS[formulation]
+    kw = {}
+    if formulation == "KPC":
+        ref = batch["ref"].copy()
+        ref["v"], ref["a"] = workloads.speed_profile(len(ref))
+        batch = dict(batch, ref=ref)
+        kw["max_k"], kw["max_kp"] = oracle.update_limits(params, ref)
+    return oracle.solve_batch(params, form, batch, threads=threads, **kw)
+
+
 def cpu_sample(config, oracle, params):
     """The bounded per-step sample of a config for the CPU arm + a description of it."""
     c = workloads.CONFIGS[config]
@@ -211,13 +223,14 @@ def run_reference(args, rank, world):
     threads = args.cpu_threads or n_phys
     batch, sample_text = cpu_sample(args.config, oracle, params)
     B = len(batch["n_points"])
-    oracle.solve_batch(params, 0, synth.slice_batch(batch, 0, min(B, 8)), threads=1)   # builds the symbolic cache
+    F = args.formulation
+    cpu_solve(oracle, params, F, synth.slice_batch(batch, 0, min(B, 8)), 1)   # builds the symbolic cache
     for _ in range(args.warmup):
-        oracle.solve_batch(params, 0, synth.slice_batch(batch, 0, min(B, 4 * threads)), threads=threads)
+        cpu_solve(oracle, params, F, synth.slice_batch(batch, 0, min(B, 4 * threads)), threads)
     step_s = []
     solved = 0
     for _ in range(args.steps):
-        r = oracle.solve_batch(params, 0, batch, threads=threads)
+        r = cpu_solve(oracle, params, F, batch, threads)
         step_s.append(r["seconds"])
         solved += int((r["status"] == 1).sum())
     secs = sum(step_s)
@@ -226,7 +239,7 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workloads.describe(args.config, args.gpus),
+        "config": workloads.describe(args.config, args.gpus, args.formulation),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
                          "hardware_threads_visible": n_log, "physical_cores_visible": n_phys,
                          "sample": sample_text, "paths_per_step": B,
@@ -248,9 +261,11 @@ def run_reference(args, rank, world):
 class GpuWorkload:
     """One config's shard resident on one GPU + the two timed calls (device-resident, host-buffer)."""
 
-    def __init__(self, config, rank, world, local_rank, torch, join_comm=True):
+    def __init__(self, config, rank, world, local_rank, torch, join_comm=True, formulation="KP"):
         from path_optimizer_b200 import _lib, planner
         self.torch = torch
+        self.formulation = formulation
+        self.form = workloads.FORMULATION_IDS[formulation]
         self.config, self.rank, self.world = config, rank, world
         self.L = _lib.load()
         self._lib = _lib
@@ -275,6 +290,10 @@ class GpuWorkload:
         self.total = int(b["offsets"][-1])
         self.nmax = int(b["n_points"].max())
         self.solver = planner.PathPlanner(device=local_rank, max_batch=self.B, max_total_points=self.total)
+        self.mk = self.mkp = None
+        if formulation == "KPC":
+            b["ref"]["v"], b["ref"]["a"] = workloads.speed_profile(self.total)
+            self.mk, self.mkp = planner.update_limits(self.solver.params, b["ref"])
         off = b["offsets"]
         self.keep = np.array([self.L.pqp_keep_control_steps(0, np.ascontiguousarray(b["ref"][off[i]:off[i + 1]]).ctypes.data_as(C.c_void_p),
                                                             int(b["n_points"][i])) for i in range(self.B)], dtype=np.int32)
@@ -285,6 +304,10 @@ class GpuWorkload:
             return t.to(self.dev)
         self.d = dict(n=dev_bytes(b["n_points"]), off=dev_bytes(b["offsets"]), ref=dev_bytes(b["ref"]),
                       bounds=dev_bytes(b["bounds"]), x0=dev_bytes(b["x0"]), end=dev_bytes(b["end_heading"]))
+        self.d_mk = self.d_mkp = None
+        if self.mk is not None:
+            self._limits_dev = (dev_bytes(self.mk), dev_bytes(self.mkp))     # keep the device copies alive
+            self.d_mk, self.d_mkp = self._limits_dev[0].data_ptr(), self._limits_dev[1].data_ptr()
         self.d_out = torch.zeros(self.total * STATE_DTYPE.itemsize, dtype=torch.uint8, device=self.dev)
         self.d_status = torch.zeros(self.B, dtype=torch.int32, device=self.dev)
         self.d_iters = torch.zeros(self.B, dtype=torch.int32, device=self.dev)
@@ -321,15 +344,15 @@ class GpuWorkload:
         st = C.byref(stats) if stats is not None else None
         if self.uniform and not self.force_classes:
             k = int(self.keep[0])
-            rc = self.L.pqp_solve_batch_device(self.solver._h, 0, self.B, self.total, self.nmax, k, k, d["n"].data_ptr(),
+            rc = self.L.pqp_solve_batch_device(self.solver._h, self.form, self.B, self.total, self.nmax, k, k, d["n"].data_ptr(),
                                                d["off"].data_ptr(), d["ref"].data_ptr(), d["bounds"].data_ptr(),
-                                               d["x0"].data_ptr(), d["end"].data_ptr(), None, None, self.d_out.data_ptr(),
+                                               d["x0"].data_ptr(), d["end"].data_ptr(), self.d_mk, self.d_mkp, self.d_out.data_ptr(),
                                                self.d_frenet.data_ptr(), self.d_status.data_ptr(), self.d_iters.data_ptr(), sp, st)
         else:
-            rc = self.L.pqp_solve_batch_device_classes(self.solver._h, 0, self.B, self.total, self.h_n.ctypes.data_as(C.c_void_p),
+            rc = self.L.pqp_solve_batch_device_classes(self.solver._h, self.form, self.B, self.total, self.h_n.ctypes.data_as(C.c_void_p),
                                                        self.keep.ctypes.data_as(C.c_void_p), d["n"].data_ptr(), d["off"].data_ptr(),
                                                        d["ref"].data_ptr(), d["bounds"].data_ptr(), d["x0"].data_ptr(),
-                                                       d["end"].data_ptr(), None, None, self.d_out.data_ptr(),
+                                                       d["end"].data_ptr(), self.d_mk, self.d_mkp, self.d_out.data_ptr(),
                                                        self.d_frenet.data_ptr(), self.d_status.data_ptr(),
                                                        self.d_iters.data_ptr(), sp, st)
         assert rc == 0, self._lib.last_error()
@@ -351,6 +374,7 @@ class GpuWorkload:
         pin = lambda a: torch.from_numpy(np.frombuffer(np.ascontiguousarray(a).tobytes(), dtype=np.uint8).copy()).pin_memory()  # noqa: E731
         self._pinned = dict(ref=pin(b["ref"]), bounds=pin(b["bounds"]), x0=pin(b["x0"]), end=pin(b["end_heading"]),
                             n=pin(b["n_points"]),
+                            mk=pin(self.mk) if self.mk is not None else None, mkp=pin(self.mkp) if self.mkp is not None else None,
                             out=torch.zeros(self.total * STATE_DTYPE.itemsize, dtype=torch.uint8).pin_memory(),
                             frenet=torch.zeros(self.total * 3, dtype=torch.float64).pin_memory(),
                             status=torch.zeros(self.B, dtype=torch.int32).pin_memory(),
@@ -360,8 +384,9 @@ class GpuWorkload:
         if self._pinned is None:
             self._pin()
         p = self._pinned
-        rc = self.L.pqp_solve_batch(self.solver._h, 0, self.B, p["n"].data_ptr(), p["ref"].data_ptr(), p["bounds"].data_ptr(),
-                                    p["x0"].data_ptr(), p["end"].data_ptr(), None, None, p["out"].data_ptr(),
+        rc = self.L.pqp_solve_batch(self.solver._h, self.form, self.B, p["n"].data_ptr(), p["ref"].data_ptr(), p["bounds"].data_ptr(),
+                                    p["x0"].data_ptr(), p["end"].data_ptr(), p["mk"].data_ptr() if p["mk"] is not None else None,
+                                    p["mkp"].data_ptr() if p["mkp"] is not None else None, p["out"].data_ptr(),
                                     p["frenet"].data_ptr(), p["status"].data_ptr(), p["iters"].data_ptr(), C.byref(stats))
         assert rc == 0, self._lib.last_error()
 
@@ -377,6 +402,12 @@ class GpuWorkload:
         """{kernel name: paths} as the library selects classes for this shard."""
         mix = {}
         v, t, s = C.c_int(), C.c_int(), C.c_int64()
+        if self.form != 0:
+            for n in self.h_n:
+                self.L.pqp_class_info_form(self.form, int(n), 1, 0, C.byref(v), C.byref(t), C.byref(s))
+                name = self.L.pqp_class_name(v.value).decode()
+                mix[name] = mix.get(name, 0) + 1
+            return mix
         if self.uniform:
             self.L.pqp_device_class_info(self.nmax, int(self.keep[0]), int(self.keep[0]), 0, C.byref(v), C.byref(t), C.byref(s))
             return {self.L.pqp_class_name(v.value).decode(): self.B}
@@ -461,7 +492,7 @@ def run_ours(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
-    w = GpuWorkload(args.config, rank, world, local_rank, torch)
+    w = GpuWorkload(args.config, rank, world, local_rank, torch, formulation=args.formulation)
     sampler = ClockSampler(local_rank)
     # warm-up of both arms happens inside time_workload; the clock sampler covers the timed regions
     if rank == 0:
@@ -487,7 +518,7 @@ def run_ours(args, rank, world, local_rank):
     control = None
     if world > 1 and args.config in (2, 4):
         # control run: every rank solves shard 0 (identical work) -- separates data-dependent tails from the collective
-        w0 = GpuWorkload(args.config, 0, 1, local_rank, torch)
+        w0 = GpuWorkload(args.config, 0, 1, local_rank, torch, formulation=args.formulation)
         w0.world, w0.gathered, w0.gather_rows = world, w.gathered, w.gather_rows
         w0.d_frenet = w.d_frenet
         w0.gather = w.gather_from(w0)   # the collective goes through the main workload's communicator
@@ -516,7 +547,7 @@ def run_ours(args, rank, world, local_rank):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps,
             "warmup": args.warmup, "ms_per_step": dev_ms / steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workloads.describe(args.config, world),
+            "config": workloads.describe(args.config, world, args.formulation),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"],
                     "ms_per_step": e2e_ms / steps, "timer": "host wall clock (time.perf_counter) around pqp_solve_batch, max over ranks",
                     "library_event_span_ms_per_step": r["e2e_span_ms"] / steps, "kernel_span_ms_per_step": r["e2e_kernel_ms"] / steps,
@@ -546,7 +577,7 @@ def run_ours(args, rank, world, local_rank):
             line["scaling_control"] = control
         if world == 1:
             line["cpu_baseline"] = cpu_baseline(args)
-            if args.config == 2 and not args.no_extras:
+            if args.config == 2 and args.formulation == "KP" and not args.no_extras:
                 line["extras"] = {"order_hint": extras_order_hint(w, torch, 5, 3, flush, stream, barrier),
                                   "configs": extras_configs(torch, local_rank, flush, stream, barrier),
                                   "formulations": extras_formulations(local_rank)}
@@ -564,11 +595,12 @@ def cpu_baseline(args):
     threads = args.cpu_threads or n_phys
     batch, sample_text = cpu_sample(args.config, oracle, params)
     B = len(batch["n_points"])
-    oracle.solve_batch(params, 0, synth.slice_batch(batch, 0, 8), threads=1)
-    oracle.solve_batch(params, 0, synth.slice_batch(batch, 0, min(B, 4 * threads)), threads=threads)
-    secs = [oracle.solve_batch(params, 0, batch, threads=threads)["seconds"] for _ in range(3)]
+    F = args.formulation
+    cpu_solve(oracle, params, F, synth.slice_batch(batch, 0, 8), 1)
+    cpu_solve(oracle, params, F, synth.slice_batch(batch, 0, min(B, 4 * threads)), threads)
+    secs = [cpu_solve(oracle, params, F, batch, threads)["seconds"] for _ in range(3)]
     one = synth.slice_batch(batch, 0, 32)
-    r1 = oracle.solve_batch(params, 0, one, threads=1)
+    r1 = cpu_solve(oracle, params, F, one, 1)
     return {"value": B / statistics.median(secs), "unit": UNIT, "cores": threads, "hardware_threads_visible": n_log,
             "physical_cores_visible": n_phys, "kind": "port",
             "sample": sample_text.replace("per step", "per repetition") + "; 3 repetitions, median",
@@ -685,6 +717,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--config", type=int, choices=[2, 3, 4, 5], default=2)
+    ap.add_argument("--formulation", choices=["KP", "K", "KPC"], default="KP",
+                    help="type string of OsqpSolver::create to solve the config with (default KP: the BASELINE metric)")
     ap.add_argument("--cpu-threads", type=int, default=0, help="CPU arm thread count (default: physical cores)")
     ap.add_argument("--no-extras", action="store_true", help="skip the config 3/4/5 context measurements of the default run")
     args = ap.parse_args()

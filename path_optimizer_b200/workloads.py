@@ -33,11 +33,22 @@ CONFIGS = {
 }
 
 
-def describe(config, world=1):
+FORMULATION_IDS = {"KP": 0, "K": 1, "KPC": 2}
+
+
+def speed_profile(total):
+    """Synthetic (v, a) per station for the "KPC" limits (ReferencePathImpl::updateLimits reads them from the reference states)."""
+    t = np.arange(total)
+    return 4.0 + 3.0 * np.sin(t * 0.05), 0.5 * np.cos(t * 0.05)
+
+
+def describe(config, world=1, formulation="KP"):
     """The `config` object of a bench line: identical for the product arm and the CPU reference arm."""
     c = CONFIGS[config]
-    return {
-        "workload": c["text"] + "; KP formulation, OSQP defaults (eps 1e-3, check every 25 it, adaptive rho every 25 it)",
+    d = {
+        "workload": c["text"] + f"; {formulation} formulation, OSQP defaults (eps 1e-3, check every 25 it, adaptive rho every 25 it)"
+                    + ("; curvature limits from a synthetic speed profile (v = 4 + 3 sin(0.05 i), a = 0.5 cos(0.05 i))" if formulation == "KPC" else ""),
+        "formulation": formulation,
         "baseline_config": config,
         "paths_per_gpu": c["paths_per_gpu"],
         "n_points": c["n_points"] if isinstance(c["n_points"], int) else f"U{{{c['n_points'][0]}..{c['n_points'][1]}}}",
@@ -46,6 +57,7 @@ def describe(config, world=1):
         "l2": "GPU arm: L2 flushed between timed steps (256 MiB fill); CPU arm: not applicable",
         "multi_gpu": "independent shards, one NCCL all-gather of the Frenet states per step (pqp_allgather: NCCL inside libpqp.so)" if world > 1 else "single GPU",
     }
+    return d
 
 
 def config3_candidates(count, first_path=0):
