@@ -694,15 +694,21 @@ def plan_chain(w, device, reps=3):
     from path_optimizer_b200 import planner
     pl = planner.PathPlanner(device=device, max_batch=w.B, max_total_points=w.total)
     pl.set_map(w.field)
+    torch = w.torch
+    # pinned host buffers, as the e2e arm uses: the reference states in, the output path states out
     b = dict(w.batch)
-    pl.plan(b)
+    ref_pin = torch.from_numpy(np.frombuffer(np.ascontiguousarray(b["ref"]).tobytes(), dtype=np.uint8).copy()).pin_memory()
+    b["ref"] = np.frombuffer(ref_pin.numpy(), dtype=STATE_DTYPE)
+    out_pin = torch.zeros(w.total * STATE_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
+    outs = {"states": np.frombuffer(out_pin.numpy(), dtype=STATE_DTYPE)}
+    pl.plan(b, out=outs)
     best = None
     for _ in range(reps):
         t0 = time.perf_counter()
-        r = pl.plan(b)
+        r = pl.plan(b, out=outs)
         ms = (time.perf_counter() - t0) * 1e3
         best = ms if best is None else min(best, ms)
-    out = {"what": "updateBounds -> KP QP -> raw tail with collision check, host buffers, host wall clock, best of 3",
+    out = {"what": "updateBounds -> KP QP -> raw tail with collision check, pinned host buffers, host wall clock, best of 3",
            "ms_per_call": best, "planner_iterations_per_sec": w.B / (best * 1e-3),
            "library_event_span_ms": r["stats"].h2d_ms + r["stats"].kernel_ms + r["stats"].d2h_ms,
            "qp_solved": int(r["solved"].sum()), "ok": int(r["ok"].sum())}

@@ -145,8 +145,9 @@ class PathPlanner(BatchPathSolver):
         return dict(states=out, n_out=n_out, ok=ok, stats=stats)
 
     def plan(self, batch, formulation="KP", bounds_mode=BOUNDS_SIMPLE, splines=None, output_mode=OUTPUT_RAW,
-             output_spacing=0.3, collision_check=True, max_out=512, want_bounds=False):
-        """PathOptimizer::solveWithoutSmoothing for every path of the batch (bounds -> QP -> tail)."""
+             output_spacing=0.3, collision_check=True, max_out=512, want_bounds=False, out=None):
+        """PathOptimizer::solveWithoutSmoothing for every path of the batch (bounds -> QP -> tail).
+        `out` may carry a preallocated (e.g. pinned) `states` array of the output shape."""
         form = FORMULATIONS[formulation] if isinstance(formulation, str) else int(formulation)
         n_points = np.ascontiguousarray(batch["n_points"], dtype=np.int32)
         B = len(n_points)
@@ -154,10 +155,12 @@ class PathPlanner(BatchPathSolver):
         x0 = np.ascontiguousarray(batch["x0"], dtype=np.float64)
         end_heading = np.ascontiguousarray(batch["end_heading"], dtype=np.float64)
         nk, kn, xc, yc = self._spl(splines)
-        if output_mode == OUTPUT_RAW:
-            states = np.zeros(len(ref), dtype=STATE_DTYPE)
+        shape = (len(ref),) if output_mode == OUTPUT_RAW else (B, max_out)
+        if out is not None and "states" in out:
+            states = out["states"]
+            assert states.dtype == STATE_DTYPE and states.shape == shape and states.flags["C_CONTIGUOUS"]
         else:
-            states = np.zeros((B, max_out), dtype=STATE_DTYPE)
+            states = np.zeros(shape, dtype=STATE_DTYPE)
         n_out = np.zeros(B, dtype=np.int32)
         ok = np.zeros(B, dtype=np.int32)
         status = np.zeros(B, dtype=np.int32)
