@@ -42,15 +42,17 @@ struct Kk {
     // shared memory (doubles): 3 x-rows + 2 dual rows + 2 weight rows + 1 delta-scale row (pitch kP); 6 push rows, 9 coupling
     // rows, 18 G rows, 11 parked-dual rows, 11 E rows, 2 output rows, 1 row of pushes that cross a warp boundary (pitch kT)
     static constexpr int kXRows = 8, kTRows = 6 + 9 + 18 + 11 + 11 + 2 + 1;
-    // The four-warp class (N <= 128, the BASELINE shapes) solves the reduced KKT in SPIKE form instead (see factor_spike):
+    // The four- and eight-warp classes (N <= 256) solve the reduced KKT in SPIKE form instead (see factor_spike):
     // separators every L stations (at most kMS of them), dense interior inverses, a dense inverse of the separator system.
-    static constexpr bool kSpike = (NW == 4);
-    static constexpr int kMS = 26;                 // most separators
-    static constexpr int kIM = 12;                 // most interior unknowns of a chunk (L <= 5)
-    static constexpr int kKP = 13;                 // row pitch of an interior inverse
-    static constexpr int kKC = kIM * kKP + 3;      // chunk stride (odd: chunks start on different banks)
+    static constexpr bool kSpike = (NW <= 8);
+    static constexpr int kMS = (NW <= 4) ? 26 : 32;   // most separators
+    static constexpr int kIM = (NW <= 4) ? 12 : 21;   // most interior unknowns of a chunk (L <= 5 / L <= 8)
+    static constexpr int kNB = kIM / 3;              // most interior stations of a chunk
+    static constexpr int kKP = kIM + 1 + (kIM & 1);   // row pitch of an interior inverse (odd)
+    static constexpr int kKC = kIM * kKP + 3 - ((kIM * kKP) & 1);   // chunk stride (odd: chunks start on different banks)
+    static constexpr int kCF = kNB * 18;              // block factor of a chunk: D_k^-1 | L_k per interior station
     static constexpr int kSpRows = 7;              // rhs (3), y (3), separator rhs (1); the Schur scratch of a factorisation overlays them
-    static constexpr int kSpScratch = 4500;        // doubles a factorisation needs in the (later) separator-inverse region
+    static constexpr int kSpScratch = 15 * kT + kMS * kCF + kMS * 27;   // doubles a factorisation needs in the (later) separator-inverse region
     struct SpDims { int L, M, pitch; size_t reg; };
     PQP_HD static SpDims sp_dims(int N) {
         SpDims d;
@@ -594,7 +596,7 @@ struct Kk {
             };
 
 
-            // ---- SPIKE form (four-warp class) --------------------------------------------------------------------------
+            // ---- SPIKE form (four- and eight-warp classes) -----------------------------------------------------------------
             // Separator p = station p L (3 unknowns), chunk p = the L - 1 stations after it (I <= 12 unknowns, block
             // tridiagonal K_I).  Per factorisation: the first interior thread of a chunk factors K_I = L D L' (3 x 3
             // blocks); every interior thread then solves its three unit vectors = its three rows of K_I^-1 (kept dense in
@@ -616,7 +618,7 @@ struct Kk {
                 double A[9], C[9];
                 blocks(A, C);
                 double *const reg = s.sinv();
-                double *const acs = reg, *const cfs = reg + 15 * kT, *const pub = reg + 15 * kT + kMS * 72;
+                double *const acs = reg, *const cfs = reg + 15 * kT, *const pub = reg + 15 * kT + kMS * kCF;
                 if (live) {
                     acs[0 * kT + i] = A[0]; acs[1 * kT + i] = A[1]; acs[2 * kT + i] = A[2];
                     acs[3 * kT + i] = A[4]; acs[4 * kT + i] = A[5]; acs[5 * kT + i] = A[8];
@@ -632,12 +634,12 @@ struct Kk {
 #pragma unroll
                     for (int k = 0; k < 9; ++k) o[k] = acs[(6 + k) * kT + st_];
                 };
-                double *const cf_ = cfs + p * 72;          // block k (station p L + k): D_k^-1 at [(k-1) 18], L_k at [(k-1) 18 + 9]
+                double *const cf_ = cfs + p * kCF;          // block k (station p L + k): D_k^-1 at [(k-1) 18], L_k at [(k-1) 18 + 9]
                 if (isInt && jj == 1) {
                     double Dm[9], Di[9], Cp[9], Lk[9], Tm[9];
                     ldA(i, Dm);
 #pragma unroll
-                    for (int k = 1; k <= kIM / 3; ++k) {
+                    for (int k = 1; k <= kNB; ++k) {
                         if (k <= nI) {
                             if (!(Dm[0] > 0.0)) ok = 0;
                             inv3_spd(Dm, Di);
@@ -669,9 +671,9 @@ struct Kk {
                     double *const kv = s.kinv() + (size_t)p * kKC + 3 * (m - 1) * kKP;
 #pragma unroll
                     for (int cu = 0; cu < 3; ++cu) {
-                        double xk[kIM / 3][3], w[3] = {cu == 0 ? 1.0 : 0.0, cu == 1 ? 1.0 : 0.0, cu == 2 ? 1.0 : 0.0};
+                        double xk[kNB][3], w[3] = {cu == 0 ? 1.0 : 0.0, cu == 1 ? 1.0 : 0.0, cu == 2 ? 1.0 : 0.0};
 #pragma unroll
-                        for (int k = 1; k <= kIM / 3; ++k) {
+                        for (int k = 1; k <= kNB; ++k) {
                             xk[k - 1][0] = xk[k - 1][1] = xk[k - 1][2] = 0.0;
                             if (k >= m && k <= nI) {
                                 const double *Dk = cf_ + (k - 1) * 18;
@@ -687,7 +689,7 @@ struct Kk {
                             }
                         }
 #pragma unroll
-                        for (int k = kIM / 3 - 1; k >= 1; --k) {
+                        for (int k = kNB - 1; k >= 1; --k) {
                             if (k < nI) {                              // x_k -= L_{k+1}' x_{k+1}
                                 const double *Ln = cf_ + k * 18 + 9;
 #pragma unroll
@@ -696,7 +698,7 @@ struct Kk {
                             }
                         }
 #pragma unroll
-                        for (int k = 1; k <= kIM / 3; ++k) {
+                        for (int k = 1; k <= kNB; ++k) {
                             if (k <= nI) {
 #pragma unroll
                                 for (int q = 0; q < 3; ++q) kv[cu * kKP + 3 * (k - 1) + q] = xk[k - 1][q];
@@ -705,7 +707,7 @@ struct Kk {
                         // my rows of the spikes: T_l = K_I^-1[:, first] K[s_1, sep p], T_r = K_I^-1[:, last] K[s_nI, sep p+1]
                         double xl[3] = {xk[0][0], xk[0][1], xk[0][2]}, xr_[3] = {0.0, 0.0, 0.0};
 #pragma unroll
-                        for (int k = 1; k <= kIM / 3; ++k)
+                        for (int k = 1; k <= kNB; ++k)
                             if (k == nI) { xr_[0] = xk[k - 1][0]; xr_[1] = xk[k - 1][1]; xr_[2] = xk[k - 1][2]; }
 #pragma unroll
                         for (int q = 0; q < 3; ++q) {
@@ -823,7 +825,7 @@ struct Kk {
                     const double *kv = s.kinv() + (size_t)p * kKC + 3 * (jj - 1) * kKP;
                     const int s1 = p * L + 1;
 #pragma unroll
-                    for (int k = 0; k < kIM / 3; ++k) {
+                    for (int k = 0; k < kNB; ++k) {
                         if (k < nI) {
                             const double r0 = s.rr(0)[s1 + k], r1 = s.rr(1)[s1 + k], r2 = s.rr(2)[s1 + k];
 #pragma unroll
