@@ -24,7 +24,8 @@
 // level l the stations with index = 2^l (mod 2^(l+1)) are eliminated, each by its own thread, which keeps
 // A_j^-1, G_L = A_j^-1 C_{j,j-s}, G_R = A_j^-1 C_{j,j+s} (24 doubles) in registers.  One solve is ceil(log2 N) levels
 // down (each eliminated station pushes G' r to its two neighbours) and as many up (x_j = A_j^-1 r_j - G_L x_a - G_R x_b),
-// one barrier per level, no serial chain longer than a 3 x 3 product.
+// one barrier per level, no serial chain longer than a 3 x 3 product (thirteen-warp class, up to 416 stations).  The four- and
+// eight-warp classes (up to 256 stations) use a SPIKE form with dense inverses instead: see factor_spike / solve_spike.
 #pragma once
 #include "pqp_kp_core.cuh"
 

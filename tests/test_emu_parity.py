@@ -227,8 +227,8 @@ def _check_k(batch, params, variant):
 @pytest.mark.parametrize("variant,n_points", [(30, [2, 3, 5, 26, 27, 53, 100, 105, 128]), (31, [129]), (32, [416])])
 def test_emu_k_thread_per_station(oracle_params, variant, n_points):
     """"K" (SolverKAsInput) on its thread-per-station kernels (pqp_kk_core.cuh: stencils in registers; reduced KKT in SPIKE
-    form with dense inverses in the four-warp class -- lengths either side of every change of the chunk length --, by block
-    cyclic reduction with warp-local shuffle levels in the eight- and thirteen-warp classes): same status, iteration count
+    form with dense inverses in the four- and eight-warp classes -- lengths either side of every change of the chunk length
+    of the former --, by block cyclic reduction with warp-local shuffle levels in the thirteen-warp class): same status, iteration count
     and iterates as the oracle's restatement of solver_k_as_input.cpp, for both corridor kinds."""
     p = oracle_params.copy()
     if variant != 30:

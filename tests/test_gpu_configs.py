@@ -256,7 +256,7 @@ def test_kpc_plan_chain(oracle_params):
 
 def test_k_thread_per_station_classes_and_plan(oracle_params):
     """"K" (SolverKAsInput) runs on its own thread-per-station classes (pqp_kk_core.cuh: 4 / 8 / 13 warps, up to 416
-    stations, block cyclic reduction), assembled in the kernel: every length class and an infeasible corridor against the
+    stations; SPIKE form to 256 stations, block cyclic reduction beyond), assembled in the kernel: every length class and an infeasible corridor against the
     oracle; the device entry gives the same bits as the host-buffer one; a longer path is PQP_INVALID_PROBLEM for itself;
     the solveWithoutSmoothing chain takes "K" too."""
     import torch
