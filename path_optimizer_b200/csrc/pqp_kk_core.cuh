@@ -592,7 +592,8 @@ struct Kk {
                         }
                     }
                 }
-                if (live) { s.xr(0)[i] = r[0]; s.xr(1)[i] = r[1]; s.xr(2)[i] = r[2]; }
+                // (the stations 32 w published their x on the way up: the warp before them may still be reading it)
+                if (live && !(Lv > kLoc && lane == 0)) { s.xr(0)[i] = r[0]; s.xr(1)[i] = r[1]; s.xr(2)[i] = r[2]; }
                 c.sync();
             };
 
